@@ -1,0 +1,56 @@
+"""Builds dzahui_b200/libdzahui_b200.so (the C-ABI library of include/dzahui_b200.h) in-tree with nvcc for sm_100a.
+
+`python -m dzahui_b200.build` or `dzahui_b200.build.build()`.  nvcc cross-compiles without a GPU.
+-fmad=false: the FAITHFUL kernels must keep the reference's separate multiply/add roundings; the FAST kernels
+call fma() explicitly where they want it."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libdzahui_b200.so")
+SOURCES = ["dzb_api.cu", "gl_quadrature.cpp", "mesh_ingest.cpp"]
+HEADERS = ["assembly_kernels.cuh", "tridiag_kernels.cuh", "bigsys_kernels.cuh", "gl_quadrature.h", "mesh_ingest.h",
+           "gl_tables_generated.h", os.path.join("..", "..", "include", "dzahui_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    # this image's $CXX wrapper lacks parts of the toolchain; the distro g++ is the host compiler
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    log = os.path.join(HERE, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout)
+    if verbose or r.returncode:
+        print(r.stdout)
+    if r.returncode:
+        raise RuntimeError(f"nvcc failed (see {log})")
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(OUT)

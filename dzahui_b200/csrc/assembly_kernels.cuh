@@ -1,0 +1,298 @@
+// assembly_kernels.cuh — element integrals of the 1D linear-Lagrange FEM of Dzahui, on the device.
+//
+// Two evaluations of the same (quirky) reference quadrature (see DESIGN.md "assembly"):
+//   FAITHFUL  the reference's loops, same operation order, separate mul/add (file compiled with -fmad=false):
+//             diffusion_solver/time_independent.rs:102-171, time_dependent.rs:121-234, stokes_solver/dim1.rs:125-236.
+//             One thread per matrix row, O(G) per row, bands bit-identical to the reference arithmetic.
+//   FAST      closed form of those sums over prefix moments of the rule, keeping the dropped last node and the
+//             floating-point split predicate `cs*x_k + ms < x_i` at the kink (piecewise_polynomials_1degree.rs:133-148).
+//             O(log G) per row; HBM-bound: reads x (8 B/row), writes 4 (TI) or 6 (TD) bands.
+// Layout: nodes and bands are bar-major [n_bars][n] f64 (n_bars = 1 for a single bar).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dzb {
+
+struct RuleView {      // device pointers into one allocation, see gl_quadrature.h for the meaning
+  const double* x;     // [m]
+  const double* w;     // [m]
+  const double* u0;    // [m+1] ...
+  const double* u1;
+  const double* u2;
+  const double* v0;
+  const double* v1;
+  const double* v2;
+  int m;               // G - 1
+  double t0, t1p, t1m, q;
+};
+
+// ---- the reference's basis pieces, restated -----------------------------------------------------------------
+// FirstDegreePolynomial (polynomials_1d.rs:16-19): evaluate = coefficient*x + independent_term (two roundings).
+struct Affine {
+  double c, t;
+  __device__ __forceinline__ double operator()(double x) const { return c * x + t; }
+};
+__device__ __forceinline__ Affine to_0_1(double beg, double end) {  // transformation_to_0_1 :64-71
+  return {1.0 / (end - beg), -beg / (end - beg)};
+}
+__device__ __forceinline__ Affine from_m1_p1(double beg, double end) {  // transformation_from_m1_p1 :74-81
+  return {(end - beg) / 2.0, (end + beg) / 2.0};
+}
+__device__ __forceinline__ Affine compose(Affine s, Affine o) {  // self(other(x)) :116-121
+  return {s.c * o.c, s.c * o.t + s.t};
+}
+// PiecewiseFirstDegreePolynomial (piecewise_polynomials_1degree.rs:17-20,133-148) of a hat function:
+// np pieces (3 at the two ends, 4 inside), first and last identically zero.
+struct Hat {
+  Affine p[4];
+  double bp[3];
+  int np;
+  __device__ __forceinline__ double eval(double x) const {
+    const int nb = np - 1;
+    for (int i = 0; i < nb; ++i)
+      if (x < bp[i]) return p[i](x);
+    return p[nb](x);
+  }
+  __device__ __forceinline__ double deriv(double x) const {  // differentiate(): pieces (0, c), same breakpoints
+    const int nb = np - 1;
+    for (int i = 0; i < nb; ++i)
+      if (x < bp[i]) return 0.0 * x + p[i].c;
+    return 0.0 * x + p[nb].c;
+  }
+};
+// LinearBasis::new (linear_basis.rs:31-94), function i of a bar whose nodes are mesh[0..n)
+__device__ __forceinline__ Hat make_hat(const double* __restrict__ mesh, long long n, long long i) {
+  Hat h;
+  const Affine zero = {0.0, 0.0}, phi1 = {1.0, 0.0}, phi2 = {-1.0, 1.0};
+  if (i == 0) {
+    h.np = 3;
+    h.p[0] = zero, h.p[1] = compose(phi2, to_0_1(mesh[0], mesh[1])), h.p[2] = zero, h.p[3] = zero;
+    h.bp[0] = mesh[0], h.bp[1] = mesh[1], h.bp[2] = 0.0;
+  } else if (i == n - 1) {
+    h.np = 3;
+    h.p[0] = zero, h.p[1] = compose(phi1, to_0_1(mesh[n - 2], mesh[n - 1])), h.p[2] = zero, h.p[3] = zero;
+    h.bp[0] = mesh[n - 2], h.bp[1] = mesh[n - 1], h.bp[2] = 0.0;
+  } else {
+    const double prev = mesh[i - 1], cur = mesh[i], next = mesh[i + 1];
+    h.np = 4;
+    h.p[0] = zero, h.p[1] = compose(phi1, to_0_1(prev, cur)), h.p[2] = compose(phi2, to_0_1(cur, next)), h.p[3] = zero;
+    h.bp[0] = prev, h.bp[1] = cur, h.bp[2] = next;
+  }
+  return h;
+}
+
+enum { KIND_TI = 0, KIND_TD = 1, KIND_STOKES = 2 };
+
+struct AsmParams {
+  double mu, b;          // diffusion
+  double bc0, bc1;       // TI: Dirichlet values written to rhs
+  double rho, pressure;  // Stokes
+};
+struct AsmOut {          // bar-major [n_bars][n]
+  double *lo, *di, *up, *rhs;  // TI/Stokes: K and b_vector; TD: S (rhs unused)
+  double *mlo, *mdi, *mup;     // TD: M
+};
+
+// ---- FAITHFUL row: the reference's inner loops for interior row i ---------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void faithful_row(const double* __restrict__ mesh, long long n, long long i,
+                                             const double* __restrict__ qx, const double* __restrict__ qw, int m,
+                                             const AsmParams& P, const double* __restrict__ force, long long fstride,
+                                             double out[7]) {
+  const Hat phi = make_hat(mesh, n, i), phi_prev = make_hat(mesh, n, i - 1), phi_next = make_hat(mesh, n, i + 1);
+  const Affine t_prev = from_m1_p1(mesh[i - 1], mesh[i]), t_next = from_m1_p1(mesh[i], mesh[i + 1]),
+               t_square = from_m1_p1(mesh[i - 1], mesh[i + 1]);
+  double a_prev = 0.0, a_next = 0.0, a_sq = 0.0;  // TI / Stokes integrals, or TD "prime"
+  double h_prev = 0.0, h_next = 0.0, h_sq = 0.0;  // TD "half"
+  double m_prev = 0.0, m_next = 0.0, m_sq = 0.0;  // TD "mass"
+  double b_int = 0.0;                             // Stokes load
+  for (int j = 0; j < m; ++j) {                   // `for j in 1..gauss_step`
+    const double x = qx[j], w = qw[j];
+    const double tp = t_prev(x), tn = t_next(x), ts = t_square(x);
+    const double dtp = 0.0 * x + t_prev.c, dtn = 0.0 * x + t_next.c, dts = 0.0 * x + t_square.c;
+    if (KIND == KIND_TI) {  // time_independent.rs:142-165
+      a_prev += (P.mu * phi.deriv(tp) * phi_prev.deriv(tp) + P.b * phi_prev.deriv(tp) * phi.eval(tp)) * dtp * w;
+      a_next += (P.mu * phi.deriv(tn) * phi_next.deriv(tn) + P.b * phi_next.deriv(tn) * phi.eval(tn)) * dtn * w;
+      a_sq += (P.mu * phi.deriv(ts) * phi.deriv(ts) + P.b * phi.deriv(ts) * phi.eval(ts)) * dts * w;
+    } else if (KIND == KIND_TD) {  // time_dependent.rs:180-218
+      m_prev += phi.eval(tp) * phi_prev.eval(tp) * dtp * w;
+      {
+        const double v = phi.eval(ts);
+        m_sq += (v * v) * dts * w;  // .powf(2.0)
+      }
+      m_next += phi.eval(tn) * phi_next.eval(tn) * dtn * w;
+      a_prev += phi.deriv(tp) * phi_prev.deriv(tp) * dtp * w;
+      {
+        const double v = phi.deriv(ts);
+        a_sq += (v * v) * dts * w;
+      }
+      a_next += phi.deriv(tn) * phi_next.deriv(tn) * dtn * w;
+      h_prev += phi.eval(tp) * phi_prev.deriv(tp) * dtp * w;
+      h_sq += phi.eval(ts) * phi.deriv(ts) * dts * w;
+      h_next += phi.eval(tn) * phi_next.deriv(tn) * dtn * w;
+    } else {  // dim1.rs:166-185
+      a_prev += phi.eval(tp) * phi_prev.deriv(tp) * dtp * w;
+      a_next += phi.eval(tn) * phi_next.deriv(tn) * dtn * w;
+      a_sq += phi.eval(ts) * phi.deriv(ts) * dts * w;
+      b_int += P.rho * force[(long long)j * fstride] * phi.eval(ts) * dts * w;
+    }
+  }
+  if (KIND == KIND_TD) {
+    out[0] = -P.mu * a_prev - P.b * h_prev;  // S   time_dependent.rs:226-233
+    out[1] = -P.mu * a_sq - P.b * h_sq;
+    out[2] = -P.mu * a_next - P.b * h_next;
+    out[3] = 0.0;
+    out[4] = m_prev, out[5] = m_sq, out[6] = m_next;  // M   :221-223
+  } else {
+    out[0] = a_prev, out[1] = a_sq, out[2] = a_next, out[3] = b_int;
+    out[4] = out[5] = out[6] = 0.0;
+  }
+}
+
+// Stokes row 0 (dim1.rs:195-236)
+__device__ __forceinline__ void faithful_stokes_row0(const double* __restrict__ mesh, long long n,
+                                                     const double* __restrict__ qx, const double* __restrict__ qw,
+                                                     int m, const AsmParams& P, const double* __restrict__ force,
+                                                     long long fstride, double out[7]) {
+  const Hat phi0 = make_hat(mesh, n, 0), phi1 = make_hat(mesh, n, 1);
+  const Affine t0 = from_m1_p1(mesh[0], mesh[1]);
+  double i0 = 0.0, i0n = 0.0, bf = 0.0;
+  for (int j = 0; j < m; ++j) {
+    const double x = qx[j], w = qw[j];
+    const double tr = t0(x), dt0 = 0.0 * x + t0.c;
+    i0 += phi0.eval(tr) * phi0.deriv(tr) * dt0 * w;
+    i0n += phi0.eval(tr) * phi1.deriv(tr) * dt0 * w;
+    bf += P.rho * force[(long long)j * fstride] * phi0.eval(tr) * dt0 * w;
+  }
+  out[0] = 0.0, out[1] = i0, out[2] = i0n, out[3] = bf;
+  out[4] = out[5] = out[6] = 0.0;
+}
+
+// Boundary rows shared by both modes.  TI: identity row + Dirichlet value (time_independent.rs:176-179);
+// TD: identity rows in both M and S (time_dependent.rs:236-239); Stokes last row (dim1.rs:234,236).
+template <int KIND>
+__device__ __forceinline__ void boundary_row(bool first, const AsmParams& P, double out[7]) {
+  out[0] = 0.0, out[1] = 1.0, out[2] = 0.0, out[3] = 0.0, out[4] = 0.0, out[5] = 0.0, out[6] = 0.0;
+  if (KIND == KIND_TI) out[3] = first ? P.bc0 : P.bc1;
+  if (KIND == KIND_TD) out[5] = 1.0;
+  if (KIND == KIND_STOKES) out[3] = P.pressure;  // only the last row reaches here
+}
+
+template <int KIND>
+__device__ __forceinline__ void store_row(const AsmOut& o, long long g, const double v[7]) {
+  o.lo[g] = v[0], o.di[g] = v[1], o.up[g] = v[2];
+  if (KIND != KIND_TD) o.rhs[g] = v[3];
+  if (KIND == KIND_TD) o.mlo[g] = v[4], o.mdi[g] = v[5], o.mup[g] = v[6];
+}
+
+// One thread per matrix row; the rule table is staged in shared memory when it fits (smem_rule != 0).
+// Stokes: `force` holds rho-free samples f(T_square,i(x_k)) k-major: force[(k-1)*n + i], row 0 at i = 0.
+template <int KIND>
+__global__ void __launch_bounds__(128) k_assemble_faithful(const double* __restrict__ mesh, long long n,
+                                                           long long n_bars, RuleView rule, AsmParams P, AsmOut o,
+                                                           const double* __restrict__ force, int smem_rule) {
+  extern __shared__ double s_rule[];
+  const double* qx = rule.x;
+  const double* qw = rule.w;
+  if (smem_rule) {
+    for (int j = threadIdx.x; j < rule.m; j += blockDim.x) s_rule[j] = rule.x[j], s_rule[rule.m + j] = rule.w[j];
+    __syncthreads();
+    qx = s_rule, qw = s_rule + rule.m;
+  }
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * n_bars) return;
+  const long long bar = g / n, i = g - bar * n;
+  const double* bm = mesh + bar * n;
+  double v[7];
+  if (i == n - 1 || (i == 0 && KIND != KIND_STOKES))
+    boundary_row<KIND>(i == 0, P, v);
+  else if (i == 0)
+    faithful_stokes_row0(bm, n, qx, qw, rule.m, P, force, n, v);
+  else
+    faithful_row<KIND>(bm, n, i, qx, qw, rule.m, P, force ? force + i : nullptr, n, v);
+  store_row<KIND>(o, g, v);
+}
+
+// ---- FAST row: closed form ----------------------------------------------------------------------------------
+// In exact arithmetic the reference's integrands only depend on x_k through (1 +- x_k):
+//   on [a,c] ("prev"):   phi_i = (1+x)/2, phi_{i-1} = (1-x)/2, phi_i' = 1/h1, phi_{i-1}' = -1/h1, Jacobian h1/2
+//   on [c,e] ("next"):   phi_i = (1-x)/2, phi_{i+1} = (1+x)/2, phi_i' = -1/h2, phi_{i+1}' = 1/h2, Jacobian h2/2
+//   on [a,e] ("square"): X_k < c -> phi_i = H(1+x)/(2 h1), phi_i' = 1/h1;  else phi_i = H(1-x)/(2 h2), phi_i' = -1/h2;
+//                        Jacobian H/2, H = h1 + h2.  WHICH nodes are left of the kink is decided with the reference's
+//                        own two-rounding predicate fl(fl(cs*x_k) + ms) < c, found by bisection (x_k decreasing in k).
+// Falls back to the faithful loop for a row whose pieces could be selected differently by rounding (degenerate
+// or unsorted spacing), so FAST never silently changes which polynomial piece a node hits.
+template <int KIND>
+__device__ __forceinline__ void fast_row(const double* __restrict__ mesh, long long n, long long i,
+                                         const RuleView& R, const double* __restrict__ qx,
+                                         const double* __restrict__ qw, const AsmParams& P, double out[7]) {
+  const double a = mesh[i - 1], c = mesh[i], e = mesh[i + 1];
+  const int m = R.m;
+  const Affine tp = from_m1_p1(a, c), tn = from_m1_p1(c, e), ts = from_m1_p1(a, e);
+  bool ok = m > 0 && (a < c) && (c < e);
+  if (ok) {
+    const double x_hi = qx[0], x_lo = qx[m - 1];
+    ok = (tp(x_hi) < c) && !(tp(x_lo) < a) && (tn(x_hi) < e) && !(tn(x_lo) < c) && (ts(x_hi) < e) && !(ts(x_lo) < a);
+    if (i >= 2) ok = ok && !(a < mesh[i - 2]);
+    if (i + 2 < n) ok = ok && !(mesh[i + 2] < e);
+  }
+  if (!ok) {
+    faithful_row<KIND>(mesh, n, i, qx, qw, m, P, nullptr, 0, out);
+    return;
+  }
+  // first node index whose image is left of the kink (predicate is monotone in j because x_j decreases)
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ts(qx[mid]) < c) hi = mid; else lo = mid + 1;
+  }
+  const int s = lo;
+  const double h1 = c - a, h2 = e - c, H = e - a;
+  const double ih1sq = 1.0 / (h1 * h1), ih2sq = 1.0 / (h2 * h2);
+  const double U0 = R.u0[s], U1 = R.u1[s], V0 = R.v0[s], V1 = R.v1[s];
+  const double prime_prev = -R.t0 / (2.0 * h1), prime_next = -R.t0 / (2.0 * h2);
+  const double prime_sq = (H / 2.0) * (U0 * ih1sq + V0 * ih2sq);
+  const double half_prev = -R.t1p / 4.0, half_next = R.t1m / 4.0;
+  const double half_sq = (H * H / 4.0) * (U1 * ih1sq - V1 * ih2sq);
+  if (KIND == KIND_TI) {
+    out[0] = P.mu * prime_prev + P.b * half_prev;
+    out[1] = P.mu * prime_sq + P.b * half_sq;
+    out[2] = P.mu * prime_next + P.b * half_next;
+    out[3] = 0.0;
+    out[4] = out[5] = out[6] = 0.0;
+  } else {
+    const double U2 = R.u2[s], V2 = R.v2[s];
+    out[0] = -P.mu * prime_prev - P.b * half_prev;
+    out[1] = -P.mu * prime_sq - P.b * half_sq;
+    out[2] = -P.mu * prime_next - P.b * half_next;
+    out[3] = 0.0;
+    out[4] = (h1 / 8.0) * R.q;
+    out[5] = (H * H * H / 8.0) * (U2 * ih1sq + V2 * ih2sq);
+    out[6] = (h2 / 8.0) * R.q;
+  }
+}
+
+// One thread per row, grid-stride; x table (and nothing else) staged in shared memory for the bisection.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_assemble_fast(const double* __restrict__ mesh, long long n, long long n_bars,
+                                                       RuleView rule, AsmParams P, AsmOut o, int smem_rule) {
+  extern __shared__ double s_rule[];
+  const double* qx = rule.x;
+  if (smem_rule) {
+    for (int j = threadIdx.x; j < rule.m; j += blockDim.x) s_rule[j] = rule.x[j];
+    __syncthreads();
+    qx = s_rule;
+  }
+  const long long total = n * n_bars;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long bar = g / n, i = g - bar * n;
+    double v[7];
+    if (i == 0 || i == n - 1)
+      boundary_row<KIND>(i == 0, P, v);
+    else
+      fast_row<KIND>(mesh + bar * n, n, i, rule, qx, rule.w, P, v);
+    store_row<KIND>(o, g, v);
+  }
+}
+
+}  // namespace dzb

@@ -1,0 +1,788 @@
+// dzb_api.cu — the C ABI of include/dzahui_b200.h: handles, device memory, kernel launches.
+// Build (see dzahui_b200/build.py): nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false
+// (explicit fma() only where the FAST kernels ask for it; FAITHFUL kernels keep separate mul/add like the reference).
+// No CPU fallback: every compute entry point needs a CUDA device and reports DZB_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/dzahui_b200.h"
+#include "assembly_kernels.cuh"
+#include "bigsys_kernels.cuh"
+#include "gl_quadrature.h"
+#include "mesh_ingest.h"
+#include "tridiag_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+cudaStream_t g_stream = 0;
+unsigned long long g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(DZB_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+#define LAUNCHED()                                                                            \
+  do {                                                                                        \
+    ++g_launches;                                                                             \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess) return fail(DZB_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T>
+int dalloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) return DZB_OK;
+  CK(cudaMalloc((void**)p, count * sizeof(T)));
+  return DZB_OK;
+}
+template <class T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+int sync_stream() {
+  CK(cudaStreamSynchronize(g_stream));
+  return DZB_OK;
+}
+inline unsigned blocks_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+// ---- quadrature rule cache (device copies keyed by (device, G)) -------------------------------------------------
+struct DeviceRule {
+  double* buf = nullptr;
+  dzb::RuleView view{};
+};
+std::map<std::pair<int, size_t>, DeviceRule> g_rules;
+
+int get_rule(size_t G, dzb::RuleView* out) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  auto it = g_rules.find({dev, G});
+  if (it != g_rules.end()) {
+    *out = it->second.view;
+    return DZB_OK;
+  }
+  dzb::QuadRule r;
+  if (!dzb::gl_build_rule(G, &r)) return fail(DZB_INTEGRATION, "Misuse of quad_pair function: k should be smaller than n");
+  const size_t m = r.m;
+  std::vector<double> h;
+  h.reserve(2 * m + 6 * (m + 1) + 8);
+  h.insert(h.end(), r.x.begin(), r.x.end());
+  h.insert(h.end(), r.w.begin(), r.w.end());
+  for (const std::vector<double>* v : {&r.u0, &r.u1, &r.u2, &r.v0, &r.v1, &r.v2}) h.insert(h.end(), v->begin(), v->end());
+  DeviceRule d;
+  int rc = dalloc(&d.buf, h.size() + 1);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d.buf, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  double* p = d.buf;
+  d.view.x = p, p += m;
+  d.view.w = p, p += m;
+  d.view.u0 = p, p += m + 1;
+  d.view.u1 = p, p += m + 1;
+  d.view.u2 = p, p += m + 1;
+  d.view.v0 = p, p += m + 1;
+  d.view.v1 = p, p += m + 1;
+  d.view.v2 = p, p += m + 1;
+  d.view.m = (int)m;
+  d.view.t0 = r.t0, d.view.t1p = r.t1p, d.view.t1m = r.t1m, d.view.q = r.q;
+  g_rules[{dev, G}] = d;
+  *out = d.view;
+  return DZB_OK;
+}
+
+dzb_options resolve_options(const dzb_options* opt) {
+  dzb_options o{DZB_ASSEMBLY_AUTO, DZB_SOLVE_AUTO, -1, 0};
+  if (opt) o = *opt;
+  return o;
+}
+bool options_valid(const dzb_options& o) {
+  return o.assembly_mode >= 0 && o.assembly_mode <= 2 && o.solve_mode >= 0 && o.solve_mode <= 2 && o.refine_steps >= -1 &&
+         o.refine_steps <= 8;
+}
+
+// ---- assembly launcher -----------------------------------------------------------------------------------------
+template <int KIND>
+int launch_assembly(const double* d_mesh, size_t n, size_t n_bars, size_t G, int assembly_mode, const dzb::AsmParams& P,
+                    const dzb::AsmOut& o, const double* d_force) {
+  dzb::RuleView rule;
+  int rc = get_rule(G, &rule);
+  if (rc) return rc;
+  const long long total = (long long)n * (long long)n_bars;
+  int mode = assembly_mode;
+  if (KIND == dzb::KIND_STOKES) mode = DZB_ASSEMBLY_FAITHFUL;  // the opaque force samples make every row O(G) anyway
+  if (mode == DZB_ASSEMBLY_AUTO)
+    mode = ((double)total * (double)(G ? G : 1) <= 16777216.0) ? DZB_ASSEMBLY_FAITHFUL : DZB_ASSEMBLY_FAST;
+  if (mode == DZB_ASSEMBLY_FAITHFUL) {
+    const int smem_rule = (size_t)rule.m * 16 <= 40960 ? 1 : 0;
+    const size_t smem = smem_rule ? (size_t)rule.m * 16 : 0;
+    dzb::k_assemble_faithful<KIND><<<blocks_for(total, 128), 128, smem, g_stream>>>(d_mesh, (long long)n, (long long)n_bars,
+                                                                                  rule, P, o, d_force, smem_rule);
+    LAUNCHED();
+  } else {
+    const int smem_rule = (size_t)rule.m * 8 <= 40960 ? 1 : 0;
+    const size_t smem = smem_rule ? (size_t)rule.m * 8 : 0;
+    long long blocks = (total + 255) / 256;
+    const long long cap = 148LL * 8 * 4;  // grid-stride: a few waves of 8 resident CTAs on each of the 148 SMs
+    if (blocks > cap) blocks = cap;
+    dzb::k_assemble_fast<KIND><<<(unsigned)blocks, 256, smem, g_stream>>>(d_mesh, (long long)n, (long long)n_bars, rule, P, o,
+                                                                         smem_rule);
+    LAUNCHED();
+  }
+  return DZB_OK;
+}
+
+// ---- small utility kernels ---------------------------------------------------------------------------------------
+__global__ void k_td_init_state(const double* __restrict__ ic, double* __restrict__ u, long long n, long long n_bars,
+                                double bc0, double bc1) {  // time_dependent.rs:71-76
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * n_bars) return;
+  const long long bar = g / n, i = g - bar * n;
+  u[g] = i == 0 ? bc0 : (i == n - 1 ? bc1 : ic[bar * (n - 2) + i - 1]);
+}
+// GL vertex / index / element tables from the sorted nodes (mesh_builder.rs:249-253, :278-307)
+__global__ void k_mesh_tables(const double* __restrict__ nodes, long long n, double prom_width, double* __restrict__ vertices,
+                              uint32_t* __restrict__ indices, uint32_t* __restrict__ elements) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = nodes[i];
+  double* v0 = vertices + 6 * i;
+  double* v1 = vertices + 6 * (n + i);
+  v0[0] = x, v0[1] = 0.0, v0[2] = 0.0, v0[3] = 0.0, v0[4] = 0.0, v0[5] = 1.0;
+  v1[0] = x, v1[1] = prom_width, v1[2] = 0.0, v1[3] = 0.0, v1[4] = 0.0, v1[5] = 1.0;
+  const uint32_t N = (uint32_t)n, u = (uint32_t)i;
+  if (n >= 2) {
+    if (i == 0) {
+      indices[0] = 0, indices[1] = 1, indices[2] = N;              // first triangle  :290
+      indices[3] = N - 1, indices[4] = 2 * N - 1, indices[5] = 2 * N - 2;  // last triangle   :292-296
+    } else if (i < n - 1) {
+      uint32_t* t = indices + 6 + 6 * (i - 1);                      // :298-307
+      t[0] = u, t[1] = u + N, t[2] = u + N - 1, t[3] = u, t[4] = u + 1, t[5] = u + N;
+    }
+    if (i < n - 1) elements[2 * i] = u, elements[2 * i + 1] = u + 1;  // element e = (node e, node e+1)
+  }
+}
+// Mesh::update_gradient_1d (mesh/mod.rs:73-90): min/max of |u| by one CTA, then the colour map + f32 cast.
+__global__ void k_absminmax(const double* __restrict__ u, long long n, double* __restrict__ mm) {
+  __shared__ double smin[256], smax[256];
+  double lo = INFINITY, hi = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double a = fabs(u[i]);
+    lo = fmin(lo, a), hi = fmax(hi, a);
+  }
+  smin[threadIdx.x] = lo, smax[threadIdx.x] = hi;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + s]);
+      smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mm[0] = smin[0], mm[1] = smax[0];
+}
+__global__ void k_gradient(const double* __restrict__ u, long long n, const double* __restrict__ mm, double* __restrict__ vertices,
+                           float* __restrict__ vf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double norm_sol = (fabs(u[i]) - mm[0]) / (mm[1] - mm[0]) * (3.14159265358979323846264338327950288 / 2.);
+  const double s = sin(norm_sol), c = cos(norm_sol);
+  vertices[6 * i + 3] = s, vertices[6 * i + 5] = c;
+  vertices[6 * (n + i) + 3] = s, vertices[6 * (n + i) + 5] = c;
+  for (int k = 0; k < 6; ++k) {
+    vf[6 * i + k] = (float)vertices[6 * i + k];
+    vf[6 * (n + i) + k] = (float)vertices[6 * (n + i) + k];
+  }
+}
+
+}  // namespace
+
+// ================================================================================================= handles
+struct dzb_mesh {
+  size_t n = 0;
+  bool from_obj = false;
+  std::vector<double> h_nodes;
+  double* d_nodes = nullptr;
+  double* d_vertices = nullptr;   // 12 n
+  uint32_t* d_indices = nullptr;  // 6 n - 6
+  uint32_t* d_elements = nullptr; // 2 (n - 1)
+  float* d_vertices_f32 = nullptr;
+  double* d_minmax = nullptr;
+  double max_length = 0.0, prom_width = 0.0;
+  float translation[3] = {0.f, 0.f, 0.f};
+};
+
+struct dzb_ensemble {
+  size_t B = 0, n = 0, G = 0;
+  double mu = 0, b = 0, bc0 = 0, bc1 = 0;
+  bool fast = false;
+  int L = 0;
+  double* d_mesh = nullptr;
+  double *mlo = nullptr, *mdi = nullptr, *mup = nullptr, *slo = nullptr, *sdi = nullptr, *sup = nullptr;  // natural [B][n]
+  double *c = nullptr, *den = nullptr;                                                                     // natural [B][n]
+  double *a_lo = nullptr, *a_di = nullptr, *a_up = nullptr, *alpha = nullptr, *cc = nullptr;               // interleaved [B][32 L]
+  double* u[2] = {nullptr, nullptr};
+  int cur = 0;
+  bool prepared = false;
+  double prepared_dt = 0.0;
+  dzb::BigSys big;  // single long bar (n > 1024) in PARALLEL mode
+  bool use_big = false;
+};
+
+struct dzb_solver {
+  int kind = 0;  // dzb::KIND_*
+  size_t n = 0;
+  // static solvers
+  double *lo = nullptr, *di = nullptr, *up = nullptr, *rhs = nullptr, *c = nullptr, *den = nullptr, *out = nullptr;
+  bool parallel = false;
+  int refine_steps = 0;
+  dzb::BigSys big;
+  // time dependent: an ensemble of one bar
+  dzb_ensemble* td = nullptr;
+};
+
+namespace {
+
+void ensemble_free(dzb_ensemble* e) {
+  if (!e) return;
+  for (double** p : {&e->d_mesh, &e->mlo, &e->mdi, &e->mup, &e->slo, &e->sdi, &e->sup, &e->c, &e->den, &e->a_lo, &e->a_di, &e->a_up,
+                     &e->alpha, &e->cc, &e->u[0], &e->u[1]})
+    dfree(*p);
+  dzb::bigsys_free(&e->big);
+  delete e;
+}
+
+template <int L>
+int launch_prepare(dzb_ensemble* e, double dt) {
+  long long blocks = (long long)e->B;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  dzb::k_td_prepare<L><<<(unsigned)blocks, 256, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->slo, e->sdi, e->sup, e->c, e->den, e->a_lo,
+                                                               e->a_di, e->a_up, e->alpha, e->cc, (int)e->n, (long long)e->B, dt);
+  LAUNCHED();
+  return DZB_OK;
+}
+template <int L>
+int launch_step_fast(dzb_ensemble* e) {
+  constexpr int WARPS = 4;
+  constexpr size_t smem = WARPS * (32 * L + 34) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    CK(cudaFuncSetAttribute(dzb::k_td_step_fast<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const unsigned blocks = (unsigned)((e->B + WARPS - 1) / WARPS);
+  dzb::k_td_step_fast<L, WARPS><<<blocks, 32 * WARPS, smem, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->a_lo, e->a_di, e->a_up,
+                                                                         e->alpha, e->cc, (int)e->n, (long long)e->B, e->bc0, e->bc1);
+  LAUNCHED();
+  return DZB_OK;
+}
+#define DISPATCH_L(L_, FN, ...)                  \
+  switch (L_) {                                  \
+    case 1: rc = FN<1>(__VA_ARGS__); break;      \
+    case 2: rc = FN<2>(__VA_ARGS__); break;      \
+    case 4: rc = FN<4>(__VA_ARGS__); break;      \
+    case 8: rc = FN<8>(__VA_ARGS__); break;      \
+    case 16: rc = FN<16>(__VA_ARGS__); break;    \
+    case 32: rc = FN<32>(__VA_ARGS__); break;    \
+    default: rc = fail(DZB_INVALID, "bad chunk length"); \
+  }
+
+int ensemble_step_once(dzb_ensemble* e, double dt) {
+  int rc = DZB_OK;
+  if (e->use_big) {
+    rc = dzb::bigsys_td_step(&e->big, e->u[e->cur], e->u[e->cur ^ 1], e->mlo, e->mdi, e->mup, e->slo, e->sdi, e->sup, dt, e->bc0,
+                             e->bc1, g_stream, &g_launches);
+    if (rc) return fail(DZB_CUDA, dzb::bigsys_error());
+  } else if (e->fast) {
+    if (!e->prepared || e->prepared_dt != dt) {
+      DISPATCH_L(e->L, launch_prepare, e, dt);
+      if (rc) return rc;
+      e->prepared = true;
+      e->prepared_dt = dt;
+    }
+    DISPATCH_L(e->L, launch_step_fast, e);
+    if (rc) return rc;
+  } else {
+    dzb::k_td_step_faithful<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->mlo, e->mdi, e->mup,
+                                                                                 e->slo, e->sdi, e->sup, e->c, e->den, (long long)e->n,
+                                                                                 (long long)e->B, dt, e->bc0, e->bc1);
+    LAUNCHED();
+  }
+  e->cur ^= 1;
+  return DZB_OK;
+}
+
+int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, double b, double bc0, double bc1, const double* h_ic,
+                         size_t n_ic, size_t G, const dzb_options* opt_in, dzb_ensemble** out) {
+  if (!out) return fail(DZB_INVALID, "null output handle");
+  *out = nullptr;
+  if (!h_meshes || B == 0) return fail(DZB_INVALID, "null meshes / empty ensemble");
+  const dzb_options opt = resolve_options(opt_in);
+  if (!options_valid(opt)) return fail(DZB_INVALID, "bad dzb_options");
+  if (n < 3) return fail(DZB_WRONG_DIMS, "a bar needs at least 3 nodes");
+  if (n_ic != n - 2 || (!h_ic && n_ic)) return fail(DZB_WRONG_DIMS, "initial_conditions.len() != mesh.len() - 2");  // time_dependent.rs:66-68
+  dzb::RuleView rv;
+  int rc = get_rule(G, &rv);  // surfaces the reference's Integration error before any allocation
+  if (rc) return rc;
+
+  dzb_ensemble* e = new dzb_ensemble;
+  e->B = B, e->n = n, e->G = G, e->mu = mu, e->b = b, e->bc0 = bc0, e->bc1 = bc1;
+  const size_t tot = B * n;
+  auto bail = [&](int code) {
+    ensemble_free(e);
+    return code;
+  };
+  for (double** p : {&e->d_mesh, &e->mlo, &e->mdi, &e->mup, &e->slo, &e->sdi, &e->sup, &e->c, &e->den, &e->u[0], &e->u[1]})
+    if ((rc = dalloc(p, tot))) return bail(rc);
+  if (cudaMemcpyAsync(e->d_mesh, h_meshes, tot * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess)
+    return bail(fail(DZB_CUDA, "H2D meshes"));
+  {  // initial state = [bc0, ic..., bc1]; the IC buffer is staged through u[1]
+    if (n_ic) {
+      if (cudaMemcpyAsync(e->u[1], h_ic, B * n_ic * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess)
+        return bail(fail(DZB_CUDA, "H2D initial conditions"));
+    }
+    k_td_init_state<<<blocks_for((long long)tot, 256), 256, 0, g_stream>>>(e->u[1], e->u[0], (long long)n, (long long)B, bc0, bc1);
+    ++g_launches;
+  }
+  dzb::AsmParams P{mu, b, bc0, bc1, 0.0, 0.0};
+  dzb::AsmOut o{e->slo, e->sdi, e->sup, nullptr, e->mlo, e->mdi, e->mup};
+  if ((rc = launch_assembly<dzb::KIND_TD>(e->d_mesh, n, B, G, opt.assembly_mode, P, o, nullptr))) return bail(rc);
+
+  int solve_mode = opt.solve_mode;
+  if (solve_mode == DZB_SOLVE_AUTO) solve_mode = tot <= 65536 ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
+  if (solve_mode == DZB_SOLVE_PARALLEL && n > 1024 && B != 1)
+    return bail(fail(DZB_INVALID, "PARALLEL ensembles support bars of up to 1024 nodes (longer bars: one bar per handle)"));
+  if (solve_mode == DZB_SOLVE_PARALLEL && n > 1024) {
+    e->use_big = true;
+    if (dzb::bigsys_factor(&e->big, e->mlo, e->mdi, e->mup, n, g_stream, &g_launches)) return bail(fail(DZB_CUDA, dzb::bigsys_error()));
+  } else {
+    dzb::k_thomas_factor<<<blocks_for((long long)B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)n,
+                                                                           (long long)B);
+    ++g_launches;
+    if (solve_mode == DZB_SOLVE_PARALLEL) {
+      int L = 1;
+      while ((size_t)32 * L < n) L <<= 1;
+      e->L = L;
+      e->fast = true;
+      const size_t np = B * 32 * (size_t)L;
+      for (double** p : {&e->a_lo, &e->a_di, &e->a_up, &e->alpha, &e->cc})
+        if ((rc = dalloc(p, np))) return bail(rc);
+    }
+  }
+  if (cudaStreamSynchronize(g_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    return bail(fail(DZB_CUDA, std::string("ensemble setup: ") + cudaGetErrorString(cudaGetLastError())));
+  *out = e;
+  return DZB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================= C ABI
+extern "C" {
+
+const char* dzb_last_error(void) { return g_err.c_str(); }
+int dzb_version(void) { return 100; }
+
+int dzb_device_count(int* count) {
+  if (!count) return fail(DZB_INVALID, "null pointer");
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(DZB_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  return DZB_OK;
+}
+int dzb_set_device(int device) {
+  CK(cudaSetDevice(device));
+  return DZB_OK;
+}
+int dzb_set_stream(void* s) {
+  g_stream = (cudaStream_t)s;
+  return DZB_OK;
+}
+int dzb_synchronize(void) { return sync_stream(); }
+int dzb_launch_count(unsigned long long* count, int reset) {
+  if (count) *count = g_launches;
+  if (reset) g_launches = 0;
+  return DZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- quadrature
+int dzb_quad_pair(size_t n, size_t k, double* theta, double* weight) {
+  if (!theta || !weight) return fail(DZB_INVALID, "null pointer");
+  if (!dzb::gl_quad_pair(n, k, theta, weight))
+    return fail(DZB_INTEGRATION, "Misuse of quad_pair function: k should be smaller than n");
+  return DZB_OK;
+}
+int dzb_quad_table(size_t G, double* x, double* w) {
+  dzb::QuadRule r;
+  if (!dzb::gl_build_rule(G, &r)) return fail(DZB_INTEGRATION, "Misuse of quad_pair function: k should be smaller than n");
+  if (r.m && (!x || !w)) return fail(DZB_INVALID, "null pointer");
+  std::memcpy(x, r.x.data(), r.m * sizeof(double));
+  std::memcpy(w, r.w.data(), r.m * sizeof(double));
+  return DZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- mesh
+static int mesh_finish(dzb_mesh* m, bool tables) {
+  const size_t n = m->n;
+  int rc;
+  if ((rc = dalloc(&m->d_nodes, n))) return rc;
+  CK(cudaMemcpyAsync(m->d_nodes, m->h_nodes.data(), n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  if (tables) {
+    if ((rc = dalloc(&m->d_vertices, 12 * n))) return rc;
+    if ((rc = dalloc(&m->d_indices, n > 1 ? 6 * n - 6 : 6))) return rc;
+    if ((rc = dalloc(&m->d_elements, n > 1 ? 2 * (n - 1) : 2))) return rc;
+    k_mesh_tables<<<blocks_for((long long)n, 256), 256, 0, g_stream>>>(m->d_nodes, (long long)n, m->prom_width, m->d_vertices,
+                                                                       m->d_indices, m->d_elements);
+    LAUNCHED();
+  }
+  return sync_stream();
+}
+
+int dzb_mesh_ingest_obj_1d(const char* path, int has_mult, double mult, dzb_mesh** out) {
+  if (!out || !path) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  dzb::Ingested1D ing;
+  const dzb::IngestStatus st = dzb::ingest_obj_1d(path, has_mult != 0, mult, &ing);
+  if (st == dzb::IngestStatus::Io) return fail(DZB_IO, ing.message);
+  if (st == dzb::IngestStatus::Parse) return fail(DZB_MESH_PARSE, ing.message);
+  dzb_mesh* m = new dzb_mesh;
+  m->n = ing.nodes.size();
+  m->from_obj = true;
+  m->h_nodes.swap(ing.nodes);
+  m->max_length = ing.max_length, m->prom_width = ing.prom_width;
+  for (int k = 0; k < 3; ++k) m->translation[k] = ing.translation[k];
+  int rc = mesh_finish(m, true);
+  if (rc) {
+    dzb_mesh_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return DZB_OK;
+}
+int dzb_mesh_from_nodes(const double* x, size_t n, dzb_mesh** out) {
+  if (!out || !x) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  if (n < 1) return fail(DZB_WRONG_DIMS, "empty mesh");
+  dzb_mesh* m = new dzb_mesh;
+  m->n = n;
+  m->h_nodes.assign(x, x + n);
+  m->max_length = -x[0] + x[n - 1];
+  int rc = mesh_finish(m, false);
+  if (rc) {
+    dzb_mesh_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return DZB_OK;
+}
+int dzb_mesh_node_count(const dzb_mesh* m, size_t* n) {
+  if (!m || !n) return fail(DZB_INVALID, "null pointer");
+  *n = m->n;
+  return DZB_OK;
+}
+int dzb_mesh_nodes(const dzb_mesh* m, double* out, size_t n) {
+  if (!m || !out) return fail(DZB_INVALID, "null pointer");
+  if (n != m->n) return fail(DZB_WRONG_DIMS, "node buffer length");
+  CK(cudaMemcpyAsync(out, m->d_nodes, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_mesh_vertices(const dzb_mesh* m, double* out, size_t len) {
+  if (!m || !out) return fail(DZB_INVALID, "null pointer");
+  if (!m->d_vertices || len != 12 * m->n) return fail(DZB_WRONG_DIMS, "vertex buffer length (12 n; only .obj meshes carry vertices)");
+  CK(cudaMemcpyAsync(out, m->d_vertices, len * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_mesh_indices(const dzb_mesh* m, uint32_t* out, size_t len) {
+  if (!m || !out) return fail(DZB_INVALID, "null pointer");
+  if (!m->d_indices || m->n < 2 || len != 6 * m->n - 6) return fail(DZB_WRONG_DIMS, "index buffer length (6 n - 6)");
+  CK(cudaMemcpyAsync(out, m->d_indices, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_mesh_elements(const dzb_mesh* m, uint32_t* out, size_t len) {
+  if (!m || !out) return fail(DZB_INVALID, "null pointer");
+  if (!m->d_elements || m->n < 2 || len != 2 * (m->n - 1)) return fail(DZB_WRONG_DIMS, "element buffer length (2 (n - 1))");
+  CK(cudaMemcpyAsync(out, m->d_elements, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_mesh_info(const dzb_mesh* m, double* max_length, double* prom_width, float translation[3]) {
+  if (!m) return fail(DZB_INVALID, "null pointer");
+  if (max_length) *max_length = m->max_length;
+  if (prom_width) *prom_width = m->prom_width;
+  if (translation)
+    for (int k = 0; k < 3; ++k) translation[k] = m->translation[k];
+  return DZB_OK;
+}
+int dzb_mesh_device_nodes(const dzb_mesh* m, const double** p) {
+  if (!m || !p) return fail(DZB_INVALID, "null pointer");
+  *p = m->d_nodes;
+  return DZB_OK;
+}
+int dzb_mesh_update_gradient_1d(dzb_mesh* m, const double* d_solution, size_t n, float* out, size_t len) {
+  if (!m || !d_solution || !out) return fail(DZB_INVALID, "null pointer");
+  if (!m->d_vertices || n != m->n || len != 12 * m->n) return fail(DZB_WRONG_DIMS, "gradient buffers");
+  int rc;
+  if (!m->d_vertices_f32 && (rc = dalloc(&m->d_vertices_f32, 12 * n))) return rc;
+  if (!m->d_minmax && (rc = dalloc(&m->d_minmax, 2))) return rc;
+  k_absminmax<<<1, 256, 0, g_stream>>>(d_solution, (long long)n, m->d_minmax);
+  LAUNCHED();
+  k_gradient<<<blocks_for((long long)n, 256), 256, 0, g_stream>>>(d_solution, (long long)n, m->d_minmax, m->d_vertices, m->d_vertices_f32);
+  LAUNCHED();
+  CK(cudaMemcpyAsync(out, m->d_vertices_f32, len * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+void dzb_mesh_destroy(dzb_mesh* m) {
+  if (!m) return;
+  dfree(m->d_nodes), dfree(m->d_vertices), dfree(m->d_indices), dfree(m->d_elements), dfree(m->d_vertices_f32), dfree(m->d_minmax);
+  delete m;
+}
+
+// ------------------------------------------------------------------------------------------------- static solvers
+static int static_alloc(dzb_solver* s, size_t n) {
+  int rc;
+  for (double** p : {&s->lo, &s->di, &s->up, &s->rhs, &s->out})
+    if ((rc = dalloc(p, n))) return rc;
+  return DZB_OK;
+}
+static int static_finish(dzb_solver* s, const dzb_options& opt) {
+  const size_t n = s->n;
+  int solve_mode = opt.solve_mode;
+  if (solve_mode == DZB_SOLVE_AUTO) solve_mode = n <= 65536 ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
+  if (solve_mode == DZB_SOLVE_PARALLEL) {
+    s->parallel = true;
+    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : (n > (1u << 17) ? 1 : 0);
+    if (dzb::bigsys_factor(&s->big, s->lo, s->di, s->up, n, g_stream, &g_launches)) return fail(DZB_CUDA, dzb::bigsys_error());
+  } else {
+    int rc;
+    if ((rc = dalloc(&s->c, n))) return rc;
+    if ((rc = dalloc(&s->den, n))) return rc;
+    dzb::k_thomas_factor<<<1, 32, 0, g_stream>>>(s->lo, s->di, s->up, s->c, s->den, (long long)n, 1);
+    LAUNCHED();
+  }
+  return sync_stream();
+}
+
+int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_left, double bc_right, size_t G,
+                            const dzb_options* opt_in, dzb_solver** out) {
+  if (!out || !m) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  const dzb_options opt = resolve_options(opt_in);
+  if (!options_valid(opt)) return fail(DZB_INVALID, "bad dzb_options");
+  if (m->n < 3) return fail(DZB_WRONG_DIMS, "a bar needs at least 3 nodes");
+  dzb_solver* s = new dzb_solver;
+  s->kind = dzb::KIND_TI, s->n = m->n;
+  int rc = static_alloc(s, s->n);
+  if (!rc) {
+    dzb::AsmParams P{mu, b, bc_left, bc_right, 0.0, 0.0};
+    dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
+    rc = launch_assembly<dzb::KIND_TI>(m->d_nodes, s->n, 1, G, opt.assembly_mode, P, o, nullptr);
+  }
+  if (!rc) rc = static_finish(s, opt);
+  if (rc) {
+    dzb_solver_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return DZB_OK;
+}
+
+int dzb_stokes1d_create(const dzb_mesh* m, double rho, double pressure, double (*force)(double, void*), void* ctx, size_t G,
+                        const dzb_options* opt_in, dzb_solver** out) {
+  if (!out || !m || !force) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  const dzb_options opt = resolve_options(opt_in);
+  if (!options_valid(opt)) return fail(DZB_INVALID, "bad dzb_options");
+  const size_t n = m->n;
+  if (n < 3) return fail(DZB_WRONG_DIMS, "a bar needs at least 3 nodes");
+  dzb::QuadRule rule;
+  if (!dzb::gl_build_rule(G, &rule)) return fail(DZB_INTEGRATION, "Misuse of quad_pair function: k should be smaller than n");
+  // Sample the closure on the host at the reference's points and in its order (dim1.rs:156-185 then :210-228):
+  // T(x) = ((end-beg)/2)*x + (end+beg)/2, two roundings (host code is built with -ffp-contract=off).
+  const size_t mq = rule.m;
+  std::vector<double> F(mq * n, 0.0);
+  const std::vector<double>& x = m->h_nodes;
+  for (size_t i = 1; i + 1 < n; ++i) {
+    const double cs = (x[i + 1] - x[i - 1]) / 2.0, ms = (x[i + 1] + x[i - 1]) / 2.0;
+    for (size_t k = 0; k < mq; ++k) F[k * n + i] = force(cs * rule.x[k] + ms, ctx);
+  }
+  {
+    const double cs = (x[1] - x[0]) / 2.0, ms = (x[1] + x[0]) / 2.0;
+    for (size_t k = 0; k < mq; ++k) F[k * n] = force(cs * rule.x[k] + ms, ctx);
+  }
+  dzb_solver* s = new dzb_solver;
+  s->kind = dzb::KIND_STOKES, s->n = n;
+  double* d_force = nullptr;
+  int rc = static_alloc(s, n);
+  if (!rc) rc = dalloc(&d_force, F.size() + 1);
+  if (!rc && !F.empty() &&
+      cudaMemcpyAsync(d_force, F.data(), F.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess)
+    rc = fail(DZB_CUDA, "H2D force samples");
+  if (!rc) {
+    dzb::AsmParams P{0.0, 0.0, 0.0, 0.0, rho, pressure};
+    dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
+    rc = launch_assembly<dzb::KIND_STOKES>(m->d_nodes, n, 1, G, opt.assembly_mode, P, o, d_force);
+  }
+  if (!rc) rc = static_finish(s, opt);
+  cudaStreamSynchronize(g_stream);
+  dfree(d_force);
+  if (rc) {
+    dzb_solver_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return DZB_OK;
+}
+
+int dzb_diffusion_td_create(const dzb_mesh* m, double mu, double b, double bc_left, double bc_right, const double* ic, size_t n_ic,
+                            size_t G, const dzb_options* opt, dzb_solver** out) {
+  if (!out || !m) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  dzb_ensemble* e = nullptr;
+  int rc = ensemble_create_impl(m->h_nodes.data(), 1, m->n, mu, b, bc_left, bc_right, ic, n_ic, G, opt, &e);
+  if (rc) return rc;
+  dzb_solver* s = new dzb_solver;
+  s->kind = dzb::KIND_TD, s->n = m->n, s->td = e;
+  *out = s;
+  return DZB_OK;
+}
+
+int dzb_solver_solve_device(dzb_solver* s, double dt, const double** dev) {
+  if (!s || !dev) return fail(DZB_INVALID, "null pointer");
+  if (s->kind == dzb::KIND_TD) {
+    int rc = ensemble_step_once(s->td, dt);
+    if (rc) return rc;
+    *dev = s->td->u[s->td->cur];
+    return DZB_OK;
+  }
+  if (s->parallel) {
+    if (dzb::bigsys_solve(&s->big, s->lo, s->di, s->up, s->rhs, s->out, s->refine_steps, g_stream, &g_launches))
+      return fail(DZB_CUDA, dzb::bigsys_error());
+  } else {
+    dzb::k_thomas_solve_faithful<<<1, 32, 0, g_stream>>>(s->lo, s->c, s->den, s->rhs, s->out, (long long)s->n, 1);
+    LAUNCHED();
+  }
+  *dev = s->out;
+  return DZB_OK;
+}
+int dzb_solver_solve(dzb_solver* s, double dt, double* out_host, size_t n) {
+  if (!s || !out_host) return fail(DZB_INVALID, "null pointer");
+  if (n != s->n) return fail(DZB_WRONG_DIMS, "output length != node count");
+  const double* dev = nullptr;
+  int rc = dzb_solver_solve_device(s, dt, &dev);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_solver_node_count(const dzb_solver* s, size_t* n) {
+  if (!s || !n) return fail(DZB_INVALID, "null pointer");
+  *n = s->n;
+  return DZB_OK;
+}
+int dzb_solver_bands(const dzb_solver* s, int which, double* lo, double* di, double* up, double* rhs, size_t n) {
+  if (!s || !lo || !di || !up) return fail(DZB_INVALID, "null pointer");
+  if (n != s->n) return fail(DZB_WRONG_DIMS, "band length != node count");
+  const double *dl, *dd, *du, *dr = nullptr;
+  if (s->kind == dzb::KIND_TD) {
+    if (which == 1) dl = s->td->mlo, dd = s->td->mdi, du = s->td->mup;
+    else if (which == 0) dl = s->td->slo, dd = s->td->sdi, du = s->td->sup;
+    else return fail(DZB_INVALID, "which must be 0 (stiffness) or 1 (mass)");
+  } else {
+    if (which != 0) return fail(DZB_INVALID, "static solvers only have a stiffness matrix");
+    dl = s->lo, dd = s->di, du = s->up, dr = s->rhs;
+  }
+  const size_t bytes = n * sizeof(double);
+  CK(cudaMemcpyAsync(lo, dl, bytes, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(di, dd, bytes, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(up, du, bytes, cudaMemcpyDeviceToHost, g_stream));
+  if (rhs && dr) CK(cudaMemcpyAsync(rhs, dr, bytes, cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_solver_state(const dzb_solver* s, double* out, size_t n) {
+  if (!s || !out) return fail(DZB_INVALID, "null pointer");
+  if (s->kind != dzb::KIND_TD) return fail(DZB_INVALID, "only the time-dependent solver has a state");
+  if (n != s->n) return fail(DZB_WRONG_DIMS, "state length != node count");
+  CK(cudaMemcpyAsync(out, s->td->u[s->td->cur], n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+void dzb_solver_destroy(dzb_solver* s) {
+  if (!s) return;
+  for (double** p : {&s->lo, &s->di, &s->up, &s->rhs, &s->c, &s->den, &s->out}) dfree(*p);
+  dzb::bigsys_free(&s->big);
+  ensemble_free(s->td);
+  delete s;
+}
+
+// ------------------------------------------------------------------------------------------------- ensembles
+int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double mu, double b, double bc_left, double bc_right,
+                           const double* ic, size_t n_ic, size_t G, const dzb_options* opt, dzb_ensemble** out) {
+  return ensemble_create_impl(meshes, n_bars, n, mu, b, bc_left, bc_right, ic, n_ic, G, opt, out);
+}
+int dzb_ensemble_step(dzb_ensemble* e, double dt, size_t steps) {
+  if (!e) return fail(DZB_INVALID, "null pointer");
+  for (size_t s = 0; s < steps; ++s) {
+    int rc = ensemble_step_once(e, dt);
+    if (rc) return rc;
+  }
+  return DZB_OK;
+}
+int dzb_ensemble_solve(dzb_ensemble* e, double dt, double* out_host, size_t len) {
+  if (!e || !out_host) return fail(DZB_INVALID, "null pointer");
+  if (len != e->B * e->n) return fail(DZB_WRONG_DIMS, "output length != n_bars * n");
+  int rc = ensemble_step_once(e, dt);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_host, e->u[e->cur], len * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_ensemble_state(const dzb_ensemble* e, double* out_host, size_t len) {
+  if (!e || !out_host) return fail(DZB_INVALID, "null pointer");
+  if (len != e->B * e->n) return fail(DZB_WRONG_DIMS, "output length != n_bars * n");
+  CK(cudaMemcpyAsync(out_host, e->u[e->cur], len * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_ensemble_read_bars(const dzb_ensemble* e, const size_t* ids, size_t count, double* out_host) {
+  if (!e || !ids || !out_host) return fail(DZB_INVALID, "null pointer");
+  for (size_t k = 0; k < count; ++k) {
+    if (ids[k] >= e->B) return fail(DZB_WRONG_DIMS, "bar id out of range");
+    CK(cudaMemcpyAsync(out_host + k * e->n, e->u[e->cur] + ids[k] * e->n, e->n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  }
+  return sync_stream();
+}
+int dzb_ensemble_state_device(const dzb_ensemble* e, const double** p) {
+  if (!e || !p) return fail(DZB_INVALID, "null pointer");
+  *p = e->u[e->cur];
+  return DZB_OK;
+}
+int dzb_ensemble_bands(const dzb_ensemble* e, size_t bar, int which, double* lo, double* di, double* up, size_t n) {
+  if (!e || !lo || !di || !up) return fail(DZB_INVALID, "null pointer");
+  if (n != e->n || bar >= e->B) return fail(DZB_WRONG_DIMS, "band length / bar id");
+  if (which != 0 && which != 1) return fail(DZB_INVALID, "which must be 0 (stiffness) or 1 (mass)");
+  const size_t o = bar * n, bytes = n * sizeof(double);
+  CK(cudaMemcpyAsync(lo, (which ? e->mlo : e->slo) + o, bytes, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(di, (which ? e->mdi : e->sdi) + o, bytes, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(up, (which ? e->mup : e->sup) + o, bytes, cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_ensemble_dims(const dzb_ensemble* e, size_t* n_bars, size_t* n) {
+  if (!e) return fail(DZB_INVALID, "null pointer");
+  if (n_bars) *n_bars = e->B;
+  if (n) *n = e->n;
+  return DZB_OK;
+}
+void dzb_ensemble_destroy(dzb_ensemble* e) { ensemble_free(e); }
+
+}  // extern "C"

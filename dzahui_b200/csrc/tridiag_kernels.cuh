@@ -1,0 +1,257 @@
+// tridiag_kernels.cuh — tridiagonal solves and the explicit-Euler step of the time-dependent diffusion solver.
+//
+// FAITHFUL kernels restate the reference operation for operation (one thread per bar, no FMA: the translation unit is
+// built with -fmad=false): matrix_solver::solve_by_thomas (matrix_solver/mod.rs:17-48),
+// utils::tridiagonal_matrix_vector_multiplication (fem/utils.rs:41-62) and
+// DiffussionSolverTimeDependent::solve (diffusion_solver/time_dependent.rs:257-280).
+//
+// The FAST step (k_td_step_fast) is the B200 design for ensembles: the Thomas factors of the step-invariant mass
+// matrix are computed once (k_thomas_factor, faithful recurrences), the per-step operator is pre-scaled,
+//     beta_i = A'_lo u_{i-1} + A'_di u_i + A'_up u_{i+1},   A' = (dt S + M) / den_i,
+//     d_i    = alpha_i d_{i-1} + beta_i,                    alpha_i = -M_lo,i / den_i,
+//     s_i    = d_i - c_i s_{i+1},
+// and one warp owns one bar: lane l sweeps rows [l L, (l+1) L) sequentially (Thomas inside the chunk), the 32 chunk
+// couplings are resolved by a warp-shuffle scan of the affine maps (the PCR-like step), and a second sweep applies the
+// carries.  Operators are stored "chunk-interleaved" (element j of lane l at j*32 + l) so every load is a coalesced
+// 256-byte row; u goes through a padded shared-memory transpose.  HBM traffic per DOF-step: u in/out 16 B + A' 24 B +
+// alpha 8 B + c 8 B = 56 B (the reference algorithm touches 64 B: u in/out + 3 M + 3 S bands).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dzb {
+
+// ---- FAITHFUL: Thomas factorisation of one tridiagonal matrix per thread ------------------------------------------
+// c[i] (i < n-1) and den[i] = di_i - lo_i c_{i-1} exactly as solve_by_thomas evaluates them (mod.rs:27-39);
+// den[0] = di_0.  c[n-1] := 0 so that back-substitution can treat the last row uniformly.
+__global__ void k_thomas_factor(const double* __restrict__ lo, const double* __restrict__ di,
+                                const double* __restrict__ up, double* __restrict__ c, double* __restrict__ den,
+                                long long n, long long n_bars) {
+  const long long bar = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bar >= n_bars) return;
+  const long long o = bar * n;
+  double cp = up[o] / di[o];
+  c[o] = cp;
+  den[o] = di[o];
+  for (long long i = 1; i < n - 1; ++i) {
+    const double dn = di[o + i] - lo[o + i] * cp;
+    cp = up[o + i] / dn;
+    c[o + i] = cp;
+    den[o + i] = dn;
+  }
+  den[o + n - 1] = di[o + n - 1] - lo[o + n - 1] * cp;
+  c[o + n - 1] = 0.0;
+}
+
+// ---- FAITHFUL: solve_by_thomas with precomputed (bit-identical) c / den ------------------------------------------
+__global__ void k_thomas_solve_faithful(const double* __restrict__ lo, const double* __restrict__ c,
+                                        const double* __restrict__ den, const double* __restrict__ rhs,
+                                        double* __restrict__ out, long long n, long long n_bars) {
+  const long long bar = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bar >= n_bars) return;
+  const long long o = bar * n;
+  double d = rhs[o] / den[o];
+  out[o] = d;
+  for (long long i = 1; i < n; ++i) {
+    d = (rhs[o + i] - lo[o + i] * d) / den[o + i];
+    out[o + i] = d;
+  }
+  double s = d;
+  for (long long i = n - 2; i >= 0; --i) {
+    s = out[o + i] - c[o + i] * s;
+    out[o + i] = s;
+  }
+}
+
+// ---- FAITHFUL: one DiffussionSolverTimeDependent::solve(dt) per thread (time_dependent.rs:257-280) ---------------
+__global__ void k_td_step_faithful(const double* __restrict__ u, double* __restrict__ u_new,
+                                   const double* __restrict__ mlo, const double* __restrict__ mdi,
+                                   const double* __restrict__ mup, const double* __restrict__ slo,
+                                   const double* __restrict__ sdi, const double* __restrict__ sup,
+                                   const double* __restrict__ c, const double* __restrict__ den, long long n,
+                                   long long n_bars, double dt, double bc0, double bc1) {
+  const long long bar = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bar >= n_bars) return;
+  const long long o = bar * n;
+  // b = add(c*(S u), 1*(M u))   utils.rs:52-59, :16-30
+  double d;
+  {
+    const double b1 = dt * (sdi[o] * u[o] + sup[o] * u[o + 1]);
+    const double b2 = 1.0 * (mdi[o] * u[o] + mup[o] * u[o + 1]);
+    d = (b1 + b2) / den[o];
+    u_new[o] = d;
+  }
+  for (long long i = 1; i < n - 1; ++i) {
+    const double b1 = dt * (slo[o + i] * u[o + i - 1] + sdi[o + i] * u[o + i] + sup[o + i] * u[o + i + 1]);
+    const double b2 = 1.0 * (mlo[o + i] * u[o + i - 1] + mdi[o + i] * u[o + i] + mup[o + i] * u[o + i + 1]);
+    d = ((b1 + b2) - mlo[o + i] * d) / den[o + i];
+    u_new[o + i] = d;
+  }
+  {
+    const long long i = n - 1;
+    const double b1 = dt * (slo[o + i] * u[o + i - 1] + sdi[o + i] * u[o + i]);
+    const double b2 = 1.0 * (mlo[o + i] * u[o + i - 1] + mdi[o + i] * u[o + i]);
+    d = ((b1 + b2) - mlo[o + i] * d) / den[o + i];
+    u_new[o + i] = d;
+  }
+  double s = d;
+  for (long long i = n - 2; i >= 0; --i) {
+    s = u_new[o + i] - c[o + i] * s;
+    u_new[o + i] = s;
+  }
+  u_new[o] = bc0;          // :273
+  u_new[o + n - 1] = bc1;  // :274
+}
+
+// ---- FAST path ----------------------------------------------------------------------------------------------------
+// Chunk-interleaved position of row r in a bar padded to 32*L rows.
+template <int L>
+__device__ __forceinline__ int il_pos(int r) { return (r % L) * 32 + r / L; }
+
+// Builds the per-step operator for time step dt from the natural-layout bands and factors (run when dt changes):
+//   A' = (dt*S + M)/den, alpha = -M_lo/den, cc = c      -> chunk-interleaved [n_bars][32 L]; padding rows are zero.
+// One CTA per bar; the permutation goes through padded shared memory so that both sides are coalesced.
+template <int L>
+__global__ void __launch_bounds__(256) k_td_prepare(const double* __restrict__ mlo, const double* __restrict__ mdi,
+                                                    const double* __restrict__ mup, const double* __restrict__ slo,
+                                                    const double* __restrict__ sdi, const double* __restrict__ sup,
+                                                    const double* __restrict__ c, const double* __restrict__ den,
+                                                    double* __restrict__ a_lo, double* __restrict__ a_di,
+                                                    double* __restrict__ a_up, double* __restrict__ alpha,
+                                                    double* __restrict__ cc, int n, long long n_bars, double dt) {
+  constexpr int NP = 32 * L;
+  constexpr int SP = NP + NP / 32;  // +1 pad per 32 entries of the interleaved order
+  __shared__ double sm[5][SP];
+  for (long long bar = blockIdx.x; bar < n_bars; bar += gridDim.x) {
+    const long long o = bar * (long long)n;
+    for (int r = threadIdx.x; r < NP; r += blockDim.x) {
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0;
+      if (r < n) {
+        const double inv = 1.0 / den[o + r];
+        v0 = (dt * slo[o + r] + mlo[o + r]) * inv;
+        v1 = (dt * sdi[o + r] + mdi[o + r]) * inv;
+        v2 = (dt * sup[o + r] + mup[o + r]) * inv;
+        v3 = r == 0 ? 0.0 : -mlo[o + r] * inv;
+        v4 = c[o + r];
+      }
+      const int p = il_pos<L>(r);
+      const int q = p + p / 32;
+      sm[0][q] = v0, sm[1][q] = v1, sm[2][q] = v2, sm[3][q] = v3, sm[4][q] = v4;
+    }
+    __syncthreads();
+    const long long oo = bar * (long long)NP;
+    for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+      const int q = p + p / 32;
+      a_lo[oo + p] = sm[0][q], a_di[oo + p] = sm[1][q], a_up[oo + p] = sm[2][q], alpha[oo + p] = sm[3][q],
+                cc[oo + p] = sm[4][q];
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+
+// One warp per bar, `steps`==1 step per launch.  WARPS warps per CTA; dynamic shared memory = WARPS * (33 L + 2) doubles.
+template <int L, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_td_step_fast(const double* __restrict__ u_old, double* __restrict__ u_new,
+                                                             const double* __restrict__ a_lo,
+                                                             const double* __restrict__ a_di,
+                                                             const double* __restrict__ a_up,
+                                                             const double* __restrict__ alpha,
+                                                             const double* __restrict__ cc, int n, long long n_bars,
+                                                             double bc0, double bc1) {
+  constexpr int NP = 32 * L;
+  constexpr int SW = NP + 32 + 2;  // one pad per chunk (r + r/L), +1 guard on each side
+  extern __shared__ double s_u[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long bar = (long long)blockIdx.x * WARPS + wib;
+  if (bar >= n_bars) return;
+  double* su = s_u + wib * SW + 1;  // su[-1] and su[pad(NP-1)+1] are the zero guards
+
+  // (1) issue the operator loads first (coalesced 256 B per instruction, streaming)
+  const long long ob = bar * (long long)NP + lane;
+  double al[L], be[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) al[j] = __ldcs(alpha + ob + j * 32);
+
+  // (2) u: natural order -> padded smem (transpose to chunk ownership)
+  const double* ub = u_old + bar * (long long)n;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const int r = k * 32 + lane;
+    su[r + r / L] = r < n ? __ldcs(ub + r) : 0.0;
+  }
+  if (lane == 0) su[-1] = 0.0, su[NP + 32] = 0.0;
+  __syncwarp();
+
+  // (3) beta_j = A'_lo u_{r-1} + A'_di u_r + A'_up u_{r+1},  r = lane*L + j
+  {
+    const int r0 = lane * L;
+    double um = lane == 0 ? 0.0 : su[(r0 - 1) + (r0 - 1) / L];
+    double u0 = su[r0 + lane];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const int rn = r0 + j + 1;
+      const double up1 = (j == L - 1) ? (lane == 31 ? 0.0 : su[rn + rn / L]) : su[rn + lane];
+      const double lo_ = __ldcs(a_lo + ob + j * 32), di_ = __ldcs(a_di + ob + j * 32), up_ = __ldcs(a_up + ob + j * 32);
+      be[j] = fma(up_, up1, fma(di_, u0, lo_ * um));
+      um = u0, u0 = up1;
+    }
+  }
+
+  // (4) forward: chunk-local sweep from a zero carry, warp scan of the affine maps, sweep with the carry
+  {
+    double e = 0.0, p = 1.0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) e = fma(al[j], e, be[j]), p *= al[j];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double pe = shfl_up_d(e, d), pp = shfl_up_d(p, d);
+      if (lane >= d) e = fma(p, pe, e), p *= pp;
+    }
+    double carry = shfl_up_d(e, 1);
+    if (lane == 0) carry = 0.0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) carry = fma(al[j], carry, be[j]), be[j] = carry;  // be[] now holds d
+  }
+
+  // (5) backward: s_r = d_r - c_r s_{r+1}
+#pragma unroll
+  for (int j = 0; j < L; ++j) al[j] = -__ldcs(cc + ob + j * 32);
+  {
+    double e = 0.0, p = 1.0;
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) e = fma(al[j], e, be[j]), p *= al[j];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double pe = shfl_down_d(e, d), pp = shfl_down_d(p, d);
+      if (lane + d < 32) e = fma(p, pe, e), p *= pp;
+    }
+    double carry = shfl_down_d(e, 1);
+    if (lane == 31) carry = 0.0;
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) carry = fma(al[j], carry, be[j]), be[j] = carry;  // be[] now holds s
+  }
+
+  // (6) Dirichlet values, transpose back through smem, coalesced streaming store
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    const int r = lane * L + j;
+    su[r + lane] = be[j];
+  }
+  __syncwarp();
+  double* un = u_new + bar * (long long)n;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const int r = k * 32 + lane;
+    if (r < n) {
+      double v = su[r + r / L];
+      if (r == 0) v = bc0;
+      if (r == n - 1) v = bc1;
+      __stcs(un + r, v);
+    }
+  }
+}
+
+}  // namespace dzb

@@ -1,0 +1,143 @@
+/* dzahui_b200.h — C ABI of the B200-native (sm_100a) 1D-FEM hot path of Dzahui.
+ *
+ * The reference (Arthur-phys/Dzahui, pure Rust) has no FFI: its seam is the trait object
+ * `Box<dyn DiffEquationSolver>` built in DzahuiWindow::run (simulation/dzahui_window.rs:738-800) and called
+ * once per frame (`solver.solve(self.time_step)`, :976).  This header is what a Rust shim implementing that
+ * trait binds (INTEGRATION.md shows the `extern "C"` block and the `impl DiffEquationSolver`).  Each entry
+ * point names the reference interface it replaces.  Paths are relative to /root/reference/src/lib.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a dzb_status (0 = OK) and records a
+ * message retrievable with dzb_last_error(); handles are not thread-safe (the reference calls everything from
+ * the winit event-loop thread).  All compute runs on the current CUDA device; there is NO CPU fallback: without
+ * a usable GPU every compute entry point returns DZB_CUDA.
+ */
+#ifndef DZAHUI_B200_H
+#define DZAHUI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors the variants of `Error` (error.rs:32-55) that the hot path can raise. */
+typedef enum dzb_status {
+  DZB_OK = 0,
+  DZB_WRONG_DIMS = 1,     /* Error::WrongDims        (time_dependent.rs:66-68, matrix_solver/mod.rs:19-21, utils.rs:43-45) */
+  DZB_INTEGRATION = 2,    /* Error::Integration      (quadrature/gauss_legendre.rs:5923-5925) */
+  DZB_PIECEWISE_DIMS = 3, /* Error::PieceWiseDims    (piecewise_polynomials_1degree.rs:112-114) */
+  DZB_MESH_PARSE = 4,     /* Error::MeshParse / ParseFloat / Infallible while reading the .obj (mesh_builder.rs:58-84,140-190,217-227) */
+  DZB_IO = 5,             /* Error::Io               (mesh_builder.rs:141,211) */
+  DZB_CUDA = 6,           /* no reference equivalent: CUDA runtime failure / no device */
+  DZB_INVALID = 7         /* no reference equivalent: NULL handle, bad option (the Rust builders `panic!` instead) */
+} dzb_status;
+
+typedef struct dzb_mesh dzb_mesh;         /* mesh::Mesh (mesh/mod.rs:30-37), 1D part, device resident */
+typedef struct dzb_solver dzb_solver;     /* Box<dyn DiffEquationSolver> (solvers/solver_trait.rs:12-23) */
+typedef struct dzb_ensemble dzb_ensemble; /* many independent DiffussionSolverTimeDependent bars stepped together */
+
+/* How the element integrals are evaluated on the device. */
+typedef enum dzb_assembly_mode {
+  DZB_ASSEMBLY_AUTO = 0,     /* FAITHFUL while nodes*gauss_step <= 2^24, FAST beyond */
+  DZB_ASSEMBLY_FAITHFUL = 1, /* the reference's quadrature loop, same operation order, no FMA: bands bit-identical to the reference arithmetic */
+  DZB_ASSEMBLY_FAST = 2      /* closed form over prefix moments of the same rule (incl. the dropped node and the split at the kink): O(log G) per node, differs by rounding only */
+} dzb_assembly_mode;
+
+/* How the tridiagonal systems are solved on the device. */
+typedef enum dzb_solve_mode {
+  DZB_SOLVE_AUTO = 0,     /* FAITHFUL for small problems (<= 2^16 unknowns in total), PARALLEL beyond */
+  DZB_SOLVE_FAITHFUL = 1, /* matrix_solver::solve_by_thomas (mod.rs:17-48) operation for operation, one thread per bar */
+  DZB_SOLVE_PARALLEL = 2  /* pre-factored Thomas: per-lane chunk sweeps + warp-shuffle / decoupled look-back scans of the affine recurrences */
+} dzb_solve_mode;
+
+typedef struct dzb_options {
+  int assembly_mode; /* dzb_assembly_mode */
+  int solve_mode;    /* dzb_solve_mode */
+  int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto: 1 when n > 2^17, else 0) */
+  int reserved;
+} dzb_options;
+
+/* ---- library / device ------------------------------------------------------------------------------------ */
+const char* dzb_last_error(void);
+int dzb_version(void);
+int dzb_device_count(int* count);
+int dzb_set_device(int device);            /* one process per GPU: call with LOCAL_RANK before anything else */
+int dzb_set_stream(void* cuda_stream);     /* cudaStream_t all subsequent work is enqueued on (default: stream 0) */
+int dzb_synchronize(void);
+/* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
+int dzb_launch_count(unsigned long long* count, int reset);
+
+/* ---- mesh ingestion: MeshBuilder::build_mesh_1d (mesh/mesh_builder.rs:204-328, with :58-84 and :140-190) ---- */
+/* Parses the `v x y z` lines, picks the varying axis, insertion-sorts ascending, and leaves on the device:
+ * node coordinates f64[n], GL vertices f64[12n], triangle indices u32[6n-6] and the element-to-node table
+ * u32[2(n-1)] (element e = (e, e+1): implicit in the reference), all bit-identical to the reference's indexing. */
+int dzb_mesh_ingest_obj_1d(const char* path, int has_height_multiplier, double height_multiplier, dzb_mesh** out);
+/* `mesh: Vec<f64>` handed straight to XSolver::new (time_independent.rs:57): sorted ascending, n >= 3. */
+int dzb_mesh_from_nodes(const double* x, size_t n, dzb_mesh** out);
+int dzb_mesh_node_count(const dzb_mesh* m, size_t* n);
+int dzb_mesh_nodes(const dzb_mesh* m, double* out, size_t n);         /* Mesh::filter_for_solving_1d (mesh/mod.rs:54-68) */
+int dzb_mesh_vertices(const dzb_mesh* m, double* out, size_t len);    /* Mesh.vertices, len = 12n  (0 for from_nodes meshes) */
+int dzb_mesh_indices(const dzb_mesh* m, uint32_t* out, size_t len);   /* Mesh.indices,  len = 6n-6 */
+int dzb_mesh_elements(const dzb_mesh* m, uint32_t* out, size_t len);  /* element-to-node, len = 2(n-1) */
+int dzb_mesh_info(const dzb_mesh* m, double* max_length, double* prom_width, float translation[3]); /* :270,:277,:310-318 */
+int dzb_mesh_device_nodes(const dzb_mesh* m, const double** device_ptr);
+/* Mesh::update_gradient_1d (mesh/mod.rs:73-90) fused with Drawable::get_vertices' f64->f32 cast (:108-113):
+ * colours the device-resident vertex buffer from |solution| and returns the f32[12n] buffer a renderer uploads. */
+int dzb_mesh_update_gradient_1d(dzb_mesh* m, const double* device_solution, size_t n, float* out_vertices_f32, size_t len);
+void dzb_mesh_destroy(dzb_mesh* m);
+
+/* ---- quadrature: gauss_legendre::quad_pair (quadrature/gauss_legendre.rs:5908-5927) ------------------------- */
+int dzb_quad_pair(size_t n, size_t k, double* theta, double* weight);
+/* the (cos(theta_j), w_j), j = 1..gauss_step-1 that every integration loop consumes (time_independent.rs:132-135) */
+int dzb_quad_table(size_t gauss_step, double* x, double* w);
+
+/* ---- solvers: XSolver::new(&params, mesh, gauss_step) ------------------------------------------------------ */
+/* StokesSolver1D::new (stokes_solver/dim1.rs:77-94).  `force` is sampled on the host, during this call only, at
+ * exactly the reference's points and in its order (interior rows i = 1..n-2 with j ascending, then row 0). */
+int dzb_stokes1d_create(const dzb_mesh* m, double rho, double hydrostatic_pressure,
+                        double (*force)(double x, void* ctx), void* ctx, size_t gauss_step,
+                        const dzb_options* opt, dzb_solver** out);
+/* DiffussionSolverTimeIndependent::new (diffusion_solver/time_independent.rs:57-71) */
+int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_left, double bc_right,
+                            size_t gauss_step, const dzb_options* opt, dzb_solver** out);
+/* DiffussionSolverTimeDependent::new (diffusion_solver/time_dependent.rs:62-95): DZB_WRONG_DIMS unless n_ic == n-2 */
+int dzb_diffusion_td_create(const dzb_mesh* m, double mu, double b, double bc_left, double bc_right,
+                            const double* initial_conditions, size_t n_ic, size_t gauss_step,
+                            const dzb_options* opt, dzb_solver** out);
+
+/* DiffEquationSolver::solve(&mut self, time_step) -> Result<Vec<f64>, Error> (solver_trait.rs:23).
+ * Synchronous: `out_host[0..n)` holds the nodal values on return.  Static solvers ignore time_step; the
+ * time-dependent solver advances its state by exactly one step of that size (it may change between calls). */
+int dzb_solver_solve(dzb_solver* s, double time_step, double* out_host, size_t n);
+/* Same step, result left on the device (valid until the next call on this handle): for a renderer that only
+ * reads back when it draws. */
+int dzb_solver_solve_device(dzb_solver* s, double time_step, const double** device_ptr);
+int dzb_solver_node_count(const dzb_solver* s, size_t* n);
+/* `stiffness_matrix` / `mass_matrix` / `b_vector` (pub(crate) fields the reference tests index as [[i,j]]):
+ * which = 0 -> stiffness (K or S), 1 -> mass (time-dependent only).  lo[i] = A[i][i-1], up[i] = A[i][i+1];
+ * rhs may be NULL (and is ignored for the time-dependent solver). */
+int dzb_solver_bands(const dzb_solver* s, int which, double* lo, double* di, double* up, double* rhs, size_t n);
+int dzb_solver_state(const dzb_solver* s, double* out, size_t n);  /* `state` (time_dependent.rs:55) */
+void dzb_solver_destroy(dzb_solver* s);
+
+/* ---- ensembles: B independent time-dependent bars, one solve() each per step ------------------------------- */
+/* meshes: host, bar-major [n_bars][n]; initial_conditions: host, [n_bars][n-2] (n_ic = n-2 per bar). */
+int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double mu, double b, double bc_left,
+                           double bc_right, const double* initial_conditions, size_t n_ic, size_t gauss_step,
+                           const dzb_options* opt, dzb_ensemble** out);
+/* `steps` successive solve(time_step) on every bar, states stay on the device */
+int dzb_ensemble_step(dzb_ensemble* e, double time_step, size_t steps);
+/* one solve(time_step) on every bar; out_host[n_bars][n] holds all states on return (pinned staging inside) */
+int dzb_ensemble_solve(dzb_ensemble* e, double time_step, double* out_host, size_t len);
+int dzb_ensemble_state(const dzb_ensemble* e, double* out_host, size_t len);
+int dzb_ensemble_read_bars(const dzb_ensemble* e, const size_t* bar_ids, size_t count, double* out_host);
+int dzb_ensemble_state_device(const dzb_ensemble* e, const double** device_ptr); /* bar-major [n_bars][n] */
+int dzb_ensemble_bands(const dzb_ensemble* e, size_t bar, int which, double* lo, double* di, double* up, size_t n);
+int dzb_ensemble_dims(const dzb_ensemble* e, size_t* n_bars, size_t* n);
+void dzb_ensemble_destroy(dzb_ensemble* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DZAHUI_B200_H */

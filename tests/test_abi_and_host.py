@@ -1,0 +1,138 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/dzahui_b200.h declares, the host-side logic
+(quadrature table, params builders, ingestion parser errors, synthetic workloads) is right, and — there being no
+GPU here — compute entry points fail loudly instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "dzahui_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dzb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(dz):
+    from dzahui_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    lib = C.CDLL(_lib.SO_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/dzahui_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (dzb_[a-z0-9_]+)", out))
+    assert set(syms) <= exported
+
+
+def test_library_is_sm100a_only(dz):
+    from dzahui_b200 import _lib
+    r = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", r.stdout))
+    assert archs == {"100a"}, archs
+
+
+def test_product_does_not_reference_oracle():
+    pkg = os.path.join(ROOT, "dzahui_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_lib" not in txt and "libdzahui_oracle" not in txt and "dzahui_oracle" not in txt, f
+
+
+def test_quadrature_matches_oracle_bit_for_bit(dz, oracle, golden):
+    for G in (2, 3, 7, 50, 99, 100, 101, 150, 350, 600, 1001):
+        x, w = dz.quad_table(G)
+        xo, wo = oracle.quad_table(G)
+        assert np.array_equal(x, xo) and np.array_equal(w, wo), G
+        if str(G) in golden["quad"]:
+            assert np.array_equal(x, golden["quad"][str(G)]["x"]) and np.array_equal(w, golden["quad"][str(G)]["w"])
+    for n, k in [(5, 1), (100, 99), (101, 51), (101, 52), (350, 349), (350, 1)]:
+        assert dz.quad_pair(n, k) == oracle.quad_pair(n, k)
+    x, w = dz.quad_table(1)
+    assert x.size == 0                                 # `for j in 1..1` is empty: no error
+    x, w = dz.quad_table(0)
+    assert x.size == 0
+
+
+def test_quad_pair_misuse_is_integration_error(dz):
+    with pytest.raises(dz.Integration) as e:
+        dz.quad_pair(150, 150)
+    assert "k should be smaller than n" in str(e.value)
+    with pytest.raises(dz.Integration):
+        dz.quad_pair(10, 11)
+
+
+def test_param_builders_mirror_reference(dz):
+    p = dz.StokesParams.static_pressure().hydrostatic_pressure(100.0).density(1.0).force_function(lambda _x: -10.0).build()
+    assert (p.rho, p.hydrostatic_pressure, p.force_function(3.0)) == (1.0, 100.0, -10.0)
+    assert "f(0) -> -10.0" in repr(p)
+    with pytest.raises(dz.BuilderPanic, match="Params lack 'pressure' term!"):
+        dz.StokesParams.normal_1d().density(1.0).force_function(lambda x: x).build()
+    with pytest.raises(dz.BuilderPanic, match="Params lack 'density' term!"):
+        dz.StokesParams.normal_1d().hydrostatic_pressure(1.0).force_function(lambda x: x).build()
+    with pytest.raises(dz.BuilderPanic, match="Params lack force_function!"):
+        dz.StokesParams.normal_1d().hydrostatic_pressure(1.0).density(1.0).build()
+    q = dz.DiffussionParams.time_independent().b(1.0).mu(2.0).boundary_conditions(0.0, 1.0).build()
+    assert (q.mu, q.b, q.boundary_conditions) == (2.0, 1.0, (0.0, 1.0))
+    with pytest.raises(dz.BuilderPanic, match="Params lack 'mu' term!"):
+        dz.DiffussionParams.time_independent().b(1.0).boundary_conditions(0, 1).build()
+    with pytest.raises(dz.BuilderPanic, match="Params lack boundary conditions!"):
+        dz.DiffussionParams.time_independent().b(1.0).mu(1.0).build()
+    t = dz.DiffussionParams.time_dependent().b(1.0).mu(1.0).boundary_conditions(1.0, 0.0).initial_conditions([15.0] * 1).build()
+    assert t.initial_conditions == [15.0]
+    with pytest.raises(dz.BuilderPanic, match="Params lack initial conditions!"):
+        dz.DiffussionParams.time_dependent().b(1.0).mu(1.0).boundary_conditions(1.0, 0.0).build()
+    base = dz.DiffussionParams.time_dependent().mu(1.0)
+    assert base.b(2.0) is not base and base._b is None  # setters return new builders, like `Self { .., ..self }`
+
+
+def test_no_cpu_fallback(dz):
+    """Without a GPU every compute entry point must raise CudaError; with one this test has nothing to check."""
+    if dz.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(dz.CudaError):
+        dz.Mesh.from_nodes([0.0, 0.5, 1.0])
+    with pytest.raises(dz.CudaError):
+        dz.EnsembleTimeDependent(np.array([[0.0, 0.5, 1.0]]), 1.0, 1.0, (0.0, 1.0), np.array([[0.0]]), 150)
+
+
+def test_ingest_parse_errors_precede_cuda(dz, tmp_path, assets_dir):
+    """Parsing is host code: reference error classes surface even without a device."""
+    with pytest.raises(dz.Io):
+        dz.Mesh.builder(str(tmp_path / "nope.obj")).build_mesh_1d()
+    with pytest.raises(dz.MeshParse, match="Only coordinates over a line"):
+        dz.Mesh.builder(assets_dir + "/big_mesh.obj").build_mesh_1d()
+    p = tmp_path / "bad.obj"
+    p.write_text("v 0.0 0.0 1.0\nv 0.0 0.0\n")
+    with pytest.raises(dz.MeshParse, match="3 elements"):
+        dz.Mesh.builder(str(p)).build_mesh_1d()
+    p.write_text("v 0.0 0.0 0x10\n")
+    with pytest.raises(dz.MeshParse):
+        dz.Mesh.builder(str(p)).build_mesh_1d()
+
+
+def test_synthetic_workloads_are_deterministic(dz):
+    from dzahui_b200 import synthetic
+    m = synthetic.ensemble_meshes([0, 1, 65535], 1024)
+    assert m.shape == (3, 1024) and np.all(m[:, 0] == 0.0) and np.all(m[:, -1] == 1.0)
+    assert np.all(np.diff(m, axis=1) > 0)
+    h = np.diff(m, axis=1)
+    assert h.min() >= 0.8 / 1023 - 1e-15 and h.max() <= 1.2 / 1023 + 1e-15
+    again = synthetic.ensemble_meshes([65535], 1024)
+    assert np.array_equal(again[0], m[2])
+    # splitmix64 known answer: first output of the stream seeded with 0
+    assert int(synthetic.splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
+    ic = synthetic.ensemble_initial_conditions(m, [0, 1, 65535])
+    assert ic.shape == (3, 1022)
+    x = synthetic.regular_bar(11)
+    assert x[0] == 0.0 and x[-1] == 1.0 and x[3] == 3 / 10
