@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""bench.py — FEM DOF·steps/s of the Dzahui 1D hot path on B200 (BASELINE.json metric), one process per GPU.
+
+Default workload (N = 1): BASELINE config 5 — an ensemble of 65536 independent 1024-node bars, time-dependent
+diffusion, one `solve(dt)` on every bar per step (diffusion_solver/time_dependent.rs:257-280).  N > 1: every rank owns
+its own 65536-bar slice (global bar ids rank*65536 ...), no data-path communication -> "scaling": "weak".
+`--workload c4` times BASELINE config 4 instead (one 10^7-node bar: static diffusion assemble + solve per step).
+
+  value     device-resident throughput: K steps timed with CUDA events on the launching stream, max over ranks
+  e2e       the same steps through the reference-facing call `solve(dt) -> Vec<f64>` (dzb_ensemble_solve /
+            dzb_solver_solve) with a pinned HOST result buffer: the D2H copy of every step's result is inside the region
+  roofline  dominant kernel, algorithmic bytes / CUDA-event time per launch, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (oracle/, port of the reference algorithm) on a bounded sample, rank 0, N = 1
+`--impl reference` runs only that CPU port with every host thread on the same config/metric."""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "FEM DOF-steps/sec (assemble+tridiag solve)"
+UNIT = "DOF-steps/s"
+MU, BADV, BC, G = 1.0, 1.0, (1.0, 15.0), 150
+C5_N, C5_DT = 1024, 1e-8
+ALG_BYTES_TD_STEP = 64       # u in/out 16 B + 3 M bands + 3 S bands 48 B per DOF-step
+ALG_BYTES_STATIC = 80        # assembly 40 B/DOF + solve 40 B/DOF
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="dzahui_b200", choices=["dzahui_b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c4"])
+    ap.add_argument("--bars", type=int, default=65536, help="bars per GPU (c5)")
+    ap.add_argument("--nodes", type=int, default=10_000_000, help="nodes of the single bar (c4)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 100)")
+    ap.add_argument("--cpu-sample-bars", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------- clocks during the run
+class ClockSampler(threading.Thread):
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        while not self.stop_flag:
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU legs (oracle port)
+class CpuTdSample:
+    """the oracle's DiffussionSolverTimeDependent::solve on `sample_bars` bars of the C5 ensemble"""
+
+    def __init__(self, sample_bars, threads, rank_offset=0):
+        import numpy as np
+        import oracle_lib as o
+        from dzahui_b200 import synthetic
+        ids = np.arange(sample_bars) + rank_offset
+        meshes = synthetic.ensemble_meshes(ids, C5_N)
+        ic = synthetic.ensemble_initial_conditions(meshes, ids)
+        self.o, self.threads, self.bars = o, threads, sample_bars
+        self.bands = o.ensemble_td_assemble(meshes, MU, BADV, G, threads=threads)
+        self.st = np.stack([o.td_initial_state(ic[k], C5_N, BC) for k in range(sample_bars)])
+        self.run(1)  # warm
+
+    def run(self, steps):
+        """-> (DOF-steps/s, seconds)"""
+        t0 = time.perf_counter()
+        self.st = self.o.ensemble_td_run(self.bands, self.st, C5_DT, BC, steps, threads=self.threads)
+        dt = time.perf_counter() - t0
+        return self.bars * C5_N * steps / dt, dt
+
+
+def cpu_td_sample(sample_bars, steps, threads, rank_offset=0):
+    return CpuTdSample(sample_bars, threads, rank_offset).run(steps)
+
+
+def cpu_static_sample(n, threads):
+    """the oracle's assemble (reference quadrature loop, table hoisted) + solve_by_thomas on an n-node regular bar"""
+    import oracle_lib as o
+    from dzahui_b200 import synthetic
+    mesh = synthetic.regular_bar(n)
+    t0 = time.perf_counter()
+    lo, di, up, rhs = o.ti_assemble(mesh, MU, BADV, BC, G, mode=0, threads=threads)
+    o.thomas(lo, di, up, rhs)
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def run_reference(args, rank):
+    """the reference's own CPU algorithm (oracle port; the Rust crate cannot be built in this image) with all host threads"""
+    if rank != 0:
+        return
+    import oracle_lib as o
+    threads = o.hardware_threads()
+    vals, secs = [], []
+    if args.workload == "c5":
+        sample = f"{args.cpu_sample_bars} of {args.bars} bars x {C5_N} nodes, 10 solve(dt) per bench step"
+        leg = CpuTdSample(args.cpu_sample_bars, threads)
+        for k in range(args.warmup + args.steps):
+            v, sec = leg.run(10)
+            if k >= args.warmup:
+                vals.append(v)
+                secs.append(sec)
+        cfg = {"workload": f"C5: ensemble of {args.bars} x {C5_N}-node bars per GPU, time-dependent diffusion, dt={C5_DT}, G={G}"}
+    else:
+        nn = min(args.nodes, 1_000_000)
+        sample = f"{nn}-node regular bar (of {args.nodes}), one assemble + Thomas per bench step"
+        for k in range(args.warmup + args.steps):
+            v, sec = cpu_static_sample(nn, threads)
+            if k >= args.warmup:
+                vals.append(v)
+                secs.append(sec)
+        cfg = {"workload": f"C4: one regular bar of {args.nodes} nodes, static diffusion assemble + solve, G={G}"}
+    value = statistics.mean(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": statistics.mean(secs) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dzahui_b200 as dz
+    from dzahui_b200 import synthetic
+
+    if not torch.cuda.is_available() or dz.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: dzahui_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dz.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    dz.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, peak_src = peaks()
+    extra = {}
+    if args.workload == "c5":
+        B, n = args.bars, C5_N
+        ids = np.arange(B, dtype=np.int64) + rank * B
+        meshes = synthetic.ensemble_meshes(ids, n)
+        ic = synthetic.ensemble_initial_conditions(meshes, ids)
+        t0 = time.perf_counter()
+        solver = dz.EnsembleTimeDependent(meshes, MU, BADV, BC, ic, G)   # H2D + assembly + factorisation
+        dz.synchronize()
+        extra["create_s"] = time.perf_counter() - t0
+        dof = B * n
+        step_dev = lambda: solver.step(C5_DT, 1)
+        host_out = torch.empty(dof, dtype=torch.float64, pin_memory=True)
+        step_e2e = lambda: solver.solve_into(C5_DT, host_out.data_ptr())
+        alg_bytes = ALG_BYTES_TD_STEP * dof
+        kernel = "k_td_step_fast<32,4>"
+        workload = (f"C5: ensemble of {B} x {n}-node bars per GPU, time-dependent diffusion, one solve(dt) per bar per step, "
+                    f"dt={C5_DT}, G={G}, mu=b=1, bc=(1,15)")
+        d2h = dof * 8
+    else:
+        n = args.nodes
+        mesh = synthetic.regular_bar(n)
+        params = dz.DiffussionParams.time_independent().mu(MU).b(BADV).boundary_conditions(*BC).build()
+        dmesh = dz.Mesh.from_nodes(mesh)
+        holder = {}
+
+        def step_dev():
+            old = holder.get("s")
+            s = dz.DiffussionSolverTimeIndependent(params, dmesh, G)     # assembly (+ factorisation)
+            s.solve_device(0.0)
+            holder["s"] = s
+            if old is not None:
+                old.close()
+        dof = n
+        host_out = torch.empty(dof, dtype=torch.float64, pin_memory=True)
+
+        def step_e2e():
+            import ctypes as C
+            from dzahui_b200 import _lib
+            old = holder.get("s")
+            m2 = dz.Mesh.from_nodes(mesh)                                # H2D of the node coordinates
+            s = dz.DiffussionSolverTimeIndependent(params, m2, G)
+            rc = s._lib.dzb_solver_solve(s._h, 0.0, C.cast(host_out.data_ptr(), _lib.c_double_p), n)
+            assert rc == 0
+            holder["s"] = s
+            if old is not None:
+                old.close()
+        alg_bytes = ALG_BYTES_STATIC * dof
+        kernel = "assemble + tridiagonal solve kernels"
+        workload = f"C4: one regular bar of {n} nodes per GPU, static diffusion assemble + solve per step, G={G}, mu=b=1, bc=(1,15)"
+        d2h = dof * 8
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dz.launch_count(reset=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
+        step_dev()
+        evs[k + 1].record(stream)
+    barrier()
+    launches = dz.launch_count()
+    clocks = sampler.result()
+    total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
+    per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    ms_per_step = total_ms / args.steps
+    value = dof * world * args.steps / (total_ms * 1e-3)
+    kern_ms = statistics.mean(per_step)
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-facing call
+    e2e_steps = args.e2e_steps or min(args.steps, 100)
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = dof * world * e2e_steps / e2e_s
+    h2d = 0 if args.workload == "c5" else dof * 8
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload, "dof_per_gpu": dof, "l2": "inputs larger than L2 (operators + state > 3 GB per step)"
+                   if dof * 56 > 2.6e8 else "working set may fit L2", "e2e_steps": e2e_steps,
+                   "e2e_call": "dzb_ensemble_solve(dt, host_out)" if args.workload == "c5" else
+                   "dzb_mesh_from_nodes + dzb_diffusion_ti_create + dzb_solver_solve(host_out)",
+                   "parallelism": f"{world} independent slices, no collective"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / e2e_steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src},
+        "extra": extra,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_lib as o
+        threads = o.hardware_threads()
+        if args.workload == "c5":
+            v_all, t_all = cpu_td_sample(args.cpu_sample_bars, 40, threads)
+            v_one, _ = cpu_td_sample(max(args.cpu_sample_bars // 8, 64), 40, 1)
+            sample = f"{args.cpu_sample_bars} of {B} bars x {n} nodes, 40 solve(dt) ({t_all:.1f} s); 1-thread figure on {max(args.cpu_sample_bars // 8, 64)} bars"
+        else:
+            nn = min(n, 1_000_000)
+            v_all, t_all = cpu_static_sample(nn, threads)
+            v_one, _ = cpu_static_sample(nn, 1)
+            sample = f"{nn}-node regular bar: quadrature-loop assembly + Thomas ({t_all:.1f} s)"
+        line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                "single_thread_value": v_one}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
