@@ -367,7 +367,7 @@ int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, 
     return bail(fail(DZB_INVALID, "PARALLEL ensembles support bars of up to 1024 nodes (longer bars: one bar per handle)"));
   if (solve_mode == DZB_SOLVE_PARALLEL && n > 1024) {
     e->use_big = true;
-    if (dzb::bigsys_factor(&e->big, e->mlo, e->mdi, e->mup, n, g_stream, &g_launches)) return bail(fail(DZB_CUDA, dzb::bigsys_error()));
+    if (dzb::bigsys_prepare(&e->big, n)) return bail(fail(DZB_CUDA, dzb::bigsys_error()));
   } else {
     dzb::k_thomas_factor<<<blocks_for((long long)B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)n,
                                                                            (long long)B);
@@ -563,10 +563,12 @@ static int static_finish(dzb_solver* s, const dzb_options& opt) {
   const size_t n = s->n;
   int solve_mode = opt.solve_mode;
   if (solve_mode == DZB_SOLVE_AUTO) solve_mode = n <= 65536 ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
+  // The Stokes matrix has a cancelling (~0) diagonal: only the serial recurrence started from row 0 is stable on it.
+  if (s->kind == dzb::KIND_STOKES) solve_mode = DZB_SOLVE_FAITHFUL;
   if (solve_mode == DZB_SOLVE_PARALLEL) {
     s->parallel = true;
-    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : (n > (1u << 17) ? 1 : 0);
-    if (dzb::bigsys_factor(&s->big, s->lo, s->di, s->up, n, g_stream, &g_launches)) return fail(DZB_CUDA, dzb::bigsys_error());
+    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : (n > (1u << 21) ? 2 : (n > 2048 ? 1 : 0));
+    if (dzb::bigsys_prepare(&s->big, n)) return fail(DZB_CUDA, dzb::bigsys_error());
   } else {
     int rc;
     if ((rc = dalloc(&s->c, n))) return rc;

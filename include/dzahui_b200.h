@@ -48,13 +48,13 @@ typedef enum dzb_assembly_mode {
 typedef enum dzb_solve_mode {
   DZB_SOLVE_AUTO = 0,     /* FAITHFUL for small problems (<= 2^16 unknowns in total), PARALLEL beyond */
   DZB_SOLVE_FAITHFUL = 1, /* matrix_solver::solve_by_thomas (mod.rs:17-48) operation for operation, one thread per bar */
-  DZB_SOLVE_PARALLEL = 2  /* pre-factored Thomas: per-lane chunk sweeps + warp-shuffle / decoupled look-back scans of the affine recurrences */
+  DZB_SOLVE_PARALLEL = 2  /* ensembles: pre-factored Thomas, per-lane chunk sweeps + warp-shuffle scans of the affine recurrences; long bars: recursive Thomas/PCR-style chunk reduction (registers -> shared memory -> grid) */
 } dzb_solve_mode;
 
 typedef struct dzb_options {
   int assembly_mode; /* dzb_assembly_mode */
   int solve_mode;    /* dzb_solve_mode */
-  int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto: 1 when n > 2^17, else 0) */
+  int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto: 0 up to 2048 rows, 1 up to 2^21, 2 beyond) */
   int reserved;
 } dzb_options;
 
