@@ -236,29 +236,22 @@ def main():
         mesh = synthetic.regular_bar(n)
         params = dz.DiffussionParams.time_independent().mu(MU).b(BADV).boundary_conditions(*BC).build()
         dmesh = dz.Mesh.from_nodes(mesh)
-        holder = {}
-
-        def step_dev():
-            old = holder.get("s")
-            s = dz.DiffussionSolverTimeIndependent(params, dmesh, G)     # assembly (+ factorisation)
-            s.solve_device(0.0)
-            holder["s"] = s
-            if old is not None:
-                old.close()
+        t0 = time.perf_counter()
+        solver = dz.DiffussionSolverTimeIndependent(params, dmesh, G)
+        dz.synchronize()
+        extra["create_s"] = time.perf_counter() - t0
         dof = n
         host_out = torch.empty(dof, dtype=torch.float64, pin_memory=True)
+        host_mesh = torch.from_numpy(mesh).pin_memory()
 
-        def step_e2e():
-            import ctypes as C
-            from dzahui_b200 import _lib
-            old = holder.get("s")
-            m2 = dz.Mesh.from_nodes(mesh)                                # H2D of the node coordinates
-            s = dz.DiffussionSolverTimeIndependent(params, m2, G)
-            rc = s._lib.dzb_solver_solve(s._h, 0.0, C.cast(host_out.data_ptr(), _lib.c_double_p), n)
-            assert rc == 0
-            holder["s"] = s
-            if old is not None:
-                old.close()
+        def step_dev():                       # assemble (XSolver::new into the same buffers) + solve, all on the device
+            solver.rebuild()
+            solver.solve_device(0.0)
+
+        def step_e2e():                       # host coordinates in, host nodal values out
+            dmesh.set_nodes(host_mesh.numpy())
+            solver.rebuild(dmesh)
+            solver.solve_into(0.0, host_out.data_ptr())
         alg_bytes = ALG_BYTES_STATIC * dof
         kernel = "assemble + tridiagonal solve kernels"
         workload = f"C4: one regular bar of {n} nodes per GPU, static diffusion assemble + solve per step, G={G}, mu=b=1, bc=(1,15)"
@@ -306,7 +299,7 @@ def main():
         "config": {"workload": workload, "dof_per_gpu": dof, "l2": "inputs larger than L2 (operators + state > 3 GB per step)"
                    if dof * 56 > 2.6e8 else "working set may fit L2", "e2e_steps": e2e_steps,
                    "e2e_call": "dzb_ensemble_solve(dt, host_out)" if args.workload == "c5" else
-                   "dzb_mesh_from_nodes + dzb_diffusion_ti_create + dzb_solver_solve(host_out)",
+                   "dzb_mesh_set_nodes(host_x) + dzb_solver_rebuild + dzb_solver_solve(host_out)",
                    "parallelism": f"{world} independent slices, no collective"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / e2e_steps * 1e3},

@@ -30,6 +30,7 @@ SIGNATURES = {
     "dzb_launch_count": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int]),
     "dzb_mesh_ingest_obj_1d": (C.c_int, [C.c_char_p, C.c_int, C.c_double, C.POINTER(C.c_void_p)]),
     "dzb_mesh_from_nodes": (C.c_int, [c_double_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "dzb_mesh_set_nodes": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
     "dzb_mesh_node_count": (C.c_int, [C.c_void_p, c_size_p]),
     "dzb_mesh_nodes": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
     "dzb_mesh_vertices": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
@@ -47,6 +48,7 @@ SIGNATURES = {
                                           C.POINTER(Options), C.POINTER(C.c_void_p)]),
     "dzb_diffusion_td_create": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, c_double_p,
                                           C.c_size_t, C.c_size_t, C.POINTER(Options), C.POINTER(C.c_void_p)]),
+    "dzb_solver_rebuild": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dzb_solver_solve": (C.c_int, [C.c_void_p, C.c_double, c_double_p, C.c_size_t]),
     "dzb_solver_solve_device": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_void_p)]),
     "dzb_solver_node_count": (C.c_int, [C.c_void_p, c_size_p]),

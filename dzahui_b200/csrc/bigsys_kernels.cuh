@@ -9,8 +9,8 @@
 // values follow without division, u_j = d_j - a_j u_s - c_j u_e.  The reduction is applied recursively:
 //     level 0   registers      2048 rows per CTA (256 threads x 8 rows, 128-bit loads)
 //     level 1-4 shared memory  512 -> 128 -> 32 -> 8 -> 2 rows, chunk-interleaved SoA (conflict-free)
-//     grid      k_tri_tile<REDUCE> writes 2 rows per tile; k_tri_mid (one CTA) solves that system (recursing through
-//               k_tri_tile again when it exceeds one CTA); k_tri_tile<SOLVE> redoes the up-sweep on chip and walks back
+//     grid      k_tri_tile<REDUCE> writes 2 rows per tile; k_tri_mid (one CTA, shared memory only) solves that system
+//               (recursing through k_tri_tile again while it exceeds 2048 rows); k_tri_tile<SOLVE> redoes the up-sweep on chip and walks back
 //               down.  HBM traffic: 32 B/row (reduce) + 40 B/row (solve) for materialised bands.
 // Pivoting: none, like the reference; chunk-local pivots are the diagonals of the diffusion / mass matrices
 // (M-matrices), not the cancelling diagonal of the Stokes matrix, which therefore stays on the serial kernel.
@@ -30,9 +30,7 @@ namespace dzb {
 constexpr int BS_R = 8;                       // rows per chunk at every level
 constexpr int BS_THREADS = 256;               // tile kernel
 constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
-constexpr int BS_MID_THREADS = 1024;          // single-CTA kernel (BS_MID_THREADS / 4 must be a power of 4)
-constexpr int BS_MID_MAX_R = 32;
-constexpr int BS_MID_CAP = BS_MID_THREADS * BS_MID_MAX_R;  // rows k_tri_mid solves directly
+constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
 
 // Shared-memory level: 8*P rows, SoA, row r of the level at (r % 8) * P + r / 8.
 struct LevelPtr {
@@ -45,14 +43,14 @@ __device__ __forceinline__ int lvl_pos(int r, int P) { return (r & 7) * P + (r >
 __device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, const LevelPtr& nx, int PN, int t) {
   const double L0 = lv.a[t], D0 = lv.b[t], U0 = lv.c[t], F0 = lv.d[t];
   int idx = P + t;
-  double r = 1.0 / lv.b[idx];
+  double r = __drcp_rn(lv.b[idx]);
   double aj = lv.a[idx] * r, cj = lv.c[idx] * r, dj = lv.d[idx] * r;
   lv.a[idx] = aj, lv.c[idx] = cj, lv.d[idx] = dj;
 #pragma unroll
   for (int j = 2; j < BS_R; ++j) {
     idx += P;
     const double l = lv.a[idx];
-    r = 1.0 / fma(-l, cj, lv.b[idx]);
+    r = __drcp_rn(fma(-l, cj, lv.b[idx]));
     aj = -l * aj * r;
     dj = fma(-l, dj, lv.d[idx]) * r;
     cj = lv.c[idx] * r;
@@ -131,7 +129,7 @@ struct Pyramid {
 // SOLVE == true : up-sweep again, take (u_s, u_e) of the tile from ured[2 tile + {0,1}], down-sweep, write out[]
 //                 (ACCUM: out[] += value, the iterative-refinement update).
 template <bool SOLVE, bool ACCUM>
-__global__ void __launch_bounds__(BS_THREADS) k_tri_tile(const double* __restrict__ lo, const double* __restrict__ di,
+__global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __restrict__ lo, const double* __restrict__ di,
                                                          const double* __restrict__ up, const double* __restrict__ f,
                                                          long long m, double* __restrict__ red_lo,
                                                          double* __restrict__ red_di, double* __restrict__ red_up,
@@ -169,12 +167,12 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_tile(const double* __restric
   // level 0 in registers: (L, U, F)[1..7] become (a, c, d)
   const double L0 = L[0], D0 = D[0], U0 = U[0], F0 = F[0];
   {
-    double r = 1.0 / D[1];
+    double r = __drcp_rn(D[1]);
     L[1] *= r, U[1] *= r, F[1] *= r;
 #pragma unroll
     for (int j = 2; j < BS_R; ++j) {
       const double l = L[j];
-      r = 1.0 / fma(-l, U[j - 1], D[j]);
+      r = __drcp_rn(fma(-l, U[j - 1], D[j]));
       L[j] = -l * L[j - 1] * r;
       F[j] = fma(-l, F[j - 1], F[j]) * r;
       U[j] *= r;
@@ -232,53 +230,24 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_tile(const double* __restric
   }
 }
 
-// ---- single-CTA kernel: solves an m-row system (m <= BS_MID_CAP) held in scratch arrays, IN PLACE ------------------
-// Level 0 lives in the (L2-resident) scratch arrays with R0 = ceil(m / 1024) >= 3 rows per thread; levels 1.. in
-// (dynamic, 87 KB) shared memory.
-template <bool ACCUM>
-__global__ void __launch_bounds__(BS_MID_THREADS) k_tri_mid(double* __restrict__ lo, double* __restrict__ di,
-                                                            double* __restrict__ up, double* __restrict__ f, int m,
-                                                            int R0, double* __restrict__ out) {
+// ---- single-CTA kernel: solves an m-row system (m <= 8 P1 <= 2048) entirely in shared memory ------------------------
+// The rows are loaded coalesced straight into level 1 of the pyramid (identity rows pad up to 8 P1); inputs are not
+// modified.  P1 in {4, 16, 64, 256}: 32 / 128 / 512 / 2048 rows.
+template <int P1, bool ACCUM>
+__global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict__ lo, const double* __restrict__ di,
+                                                        const double* __restrict__ up, const double* __restrict__ f, int m,
+                                                        double* __restrict__ out) {
   extern __shared__ double4 mid_smem[];
-  Pyramid<BS_MID_THREADS / 4>& pyr = *reinterpret_cast<Pyramid<BS_MID_THREADS / 4>*>(mid_smem);  // level 1: 2048 rows
-  constexpr int P1 = BS_MID_THREADS / 4;
+  Pyramid<P1>& pyr = *reinterpret_cast<Pyramid<P1>*>(mid_smem);
   const int t = threadIdx.x;
-  const int g0 = t * R0;
-  auto rd = [&](const double* p, int g, double pad) { return g < m ? p[g] : pad; };
-  {
-    const double L0 = g0 == 0 ? 0.0 : rd(lo, g0, 0.0), D0 = rd(di, g0, 1.0), F0 = rd(f, g0, 0.0);
-    const double U0 = g0 == m - 1 ? 0.0 : rd(up, g0, 0.0);
-    double r = 1.0 / rd(di, g0 + 1, 1.0);
-    double aj = rd(lo, g0 + 1, 0.0) * r, cj = (g0 + 1 == m - 1 ? 0.0 : rd(up, g0 + 1, 0.0)) * r, dj = rd(f, g0 + 1, 0.0) * r;
-    if (g0 + 1 < m) lo[g0 + 1] = aj, up[g0 + 1] = cj, f[g0 + 1] = dj;
-    for (int j = 2; j < R0; ++j) {
-      const int g = g0 + j;
-      const double l = rd(lo, g, 0.0), u = g == m - 1 ? 0.0 : rd(up, g, 0.0);
-      r = 1.0 / fma(-l, cj, rd(di, g, 1.0));
-      aj = -l * aj * r;
-      dj = fma(-l, dj, rd(f, g, 0.0)) * r;
-      cj = u * r;
-      if (g < m) lo[g] = aj, up[g] = cj, f[g] = dj;
-    }
-    const double ea = aj, ec = cj, ed = dj;
-    // rows beyond m are identity rows: a = c = d = 0
-    double a1 = rd(lo, g0 + R0 - 2, 0.0), c1 = rd(up, g0 + R0 - 2, 0.0), d1 = rd(f, g0 + R0 - 2, 0.0);
-    if (R0 == 3) {
-      // row 1 is already expressed through (u_s, u_e)
-    } else {
-      for (int j = R0 - 3; j >= 1; --j) {
-        const int g = g0 + j;
-        const double cc = rd(up, g, 0.0);
-        d1 = fma(-cc, d1, rd(f, g, 0.0));
-        a1 = fma(-cc, a1, rd(lo, g, 0.0));
-        c1 = -cc * c1;
-        if (g < m) lo[g] = a1, up[g] = c1, f[g] = d1;
-      }
-    }
-    LevelPtr l1 = pyr.level(0);
-    const int p0 = lvl_pos(2 * t, P1), p1 = lvl_pos(2 * t + 1, P1);
-    l1.a[p0] = L0, l1.b[p0] = fma(-U0, a1, D0), l1.c[p0] = -U0 * c1, l1.d[p0] = fma(-U0, d1, F0);
-    l1.a[p1] = ea, l1.b[p1] = 1.0, l1.c[p1] = ec, l1.d[p1] = ed;
+  LevelPtr l1 = pyr.level(0);
+  for (int r = t; r < 8 * P1; r += BS_THREADS) {
+    const int p = lvl_pos(r, P1);
+    const bool in = r < m;
+    l1.a[p] = (in && r > 0) ? lo[r] : 0.0;
+    l1.b[p] = in ? di[r] : 1.0;
+    l1.c[p] = (in && r < m - 1) ? up[r] : 0.0;
+    l1.d[p] = in ? f[r] : 0.0;
   }
   pyr.reduce(t);
   LevelPtr top = pyr.top();
@@ -289,18 +258,9 @@ __global__ void __launch_bounds__(BS_MID_THREADS) k_tri_mid(double* __restrict__
     top.d[1] = fma(b0, f1, -a1 * f0) / det;
   }
   pyr.backsolve(t);
-  {
-    LevelPtr l1 = pyr.level(0);
-    const double us = l1.d[lvl_pos(2 * t, P1)], ue = l1.d[lvl_pos(2 * t + 1, P1)];
-    for (int j = 0; j < R0; ++j) {
-      const int g = g0 + j;
-      if (g >= m) break;
-      double v;
-      if (j == 0) v = us;
-      else if (j == R0 - 1) v = ue;
-      else v = fma(-up[g], ue, fma(-lo[g], us, f[g]));
-      out[g] = ACCUM ? out[g] + v : v;
-    }
+  for (int r = t; r < m; r += BS_THREADS) {
+    const double v = l1.d[lvl_pos(r, P1)];
+    out[r] = ACCUM ? out[r] + v : v;
   }
 }
 
@@ -353,7 +313,6 @@ struct BigLevel {
 struct BigSys {
   size_t n = 0;
   std::vector<BigLevel> levels;  // levels[k]: reduced system of the k-th application of the tile kernel
-  double* small[4] = {nullptr, nullptr, nullptr, nullptr};  // copy of a system small enough for k_tri_mid alone
   double* resid = nullptr;       // refinement residual / explicit-Euler right-hand side
 };
 
@@ -372,8 +331,6 @@ inline void bigsys_free(BigSys* s) {
     for (double** p : {&l.lo, &l.di, &l.up, &l.f, &l.u})
       if (*p) cudaFree(*p), *p = nullptr;
   s->levels.clear();
-  for (double*& p : s->small)
-    if (p) cudaFree(p), p = nullptr;
   if (s->resid) cudaFree(s->resid), s->resid = nullptr;
   s->n = 0;
 }
@@ -392,45 +349,44 @@ inline int bigsys_prepare(BigSys* s, size_t n) {
     s->levels.push_back(l);
     m = l.m;
   }
-  if (s->levels.empty())
-    for (double*& p : s->small)
-      if ((e = cudaMalloc((void**)&p, n * sizeof(double))) != cudaSuccess) return bigsys_fail(e, "cudaMalloc");
   if ((e = cudaMalloc((void**)&s->resid, n * sizeof(double))) != cudaSuccess) return bigsys_fail(e, "cudaMalloc");
   return 0;
 }
 
-inline int bigsys_mid(double* lo, double* di, double* up, double* f, size_t m, double* out, bool accum, cudaStream_t st,
-                      unsigned long long* launches) {
-  int R0 = (int)((m + BS_MID_THREADS - 1) / BS_MID_THREADS);
-  if (R0 < 3) R0 = 3;
-  constexpr size_t smem = sizeof(Pyramid<BS_MID_THREADS / 4>);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(k_tri_mid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_tri_mid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) return bigsys_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute");
-    attr_set = true;
+template <int P1>
+inline int bigsys_mid_launch(const double* lo, const double* di, const double* up, const double* f, size_t m, double* out,
+                             bool accum, cudaStream_t st) {
+  constexpr size_t smem = sizeof(Pyramid<P1>);
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e1 = cudaFuncSetAttribute(k_tri_mid<P1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e2 = cudaFuncSetAttribute(k_tri_mid<P1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) return bigsys_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute");
+      attr_set = true;
+    }
   }
   if (accum)
-    k_tri_mid<true><<<1, BS_MID_THREADS, smem, st>>>(lo, di, up, f, (int)m, R0, out);
+    k_tri_mid<P1, true><<<1, BS_THREADS, smem, st>>>(lo, di, up, f, (int)m, out);
   else
-    k_tri_mid<false><<<1, BS_MID_THREADS, smem, st>>>(lo, di, up, f, (int)m, R0, out);
-  ++*launches;
+    k_tri_mid<P1, false><<<1, BS_THREADS, smem, st>>>(lo, di, up, f, (int)m, out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : bigsys_fail(e, "k_tri_mid");
+}
+inline int bigsys_mid(const double* lo, const double* di, const double* up, const double* f, size_t m, double* out, bool accum,
+                      cudaStream_t st, unsigned long long* launches) {
+  ++*launches;
+  if (m <= 32) return bigsys_mid_launch<4>(lo, di, up, f, m, out, accum, st);
+  if (m <= 128) return bigsys_mid_launch<16>(lo, di, up, f, m, out, accum, st);
+  if (m <= 512) return bigsys_mid_launch<64>(lo, di, up, f, m, out, accum, st);
+  return bigsys_mid_launch<256>(lo, di, up, f, m, out, accum, st);
 }
 
 // out (+)= A^{-1} f for the n-row system (lo, di, up); inputs are not modified.
 inline int bigsys_solve_once(BigSys* s, const double* lo, const double* di, const double* up, const double* f, double* out,
                              bool accum, cudaStream_t st, unsigned long long* launches) {
   cudaError_t e;
-  if (s->levels.empty()) {
-    const double* src[4] = {lo, di, up, f};
-    for (int k = 0; k < 4; ++k)
-      if ((e = cudaMemcpyAsync(s->small[k], src[k], s->n * sizeof(double), cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
-        return bigsys_fail(e, "cudaMemcpyAsync");
-    return bigsys_mid(s->small[0], s->small[1], s->small[2], s->small[3], s->n, out, accum, st, launches);
-  }
+  if (s->levels.empty()) return bigsys_mid(lo, di, up, f, s->n, out, accum, st, launches);
   const size_t nl = s->levels.size();
   // up-sweeps
   const double *cl = lo, *cd = di, *cu = up, *cf = f;

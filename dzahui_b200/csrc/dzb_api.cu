@@ -230,6 +230,7 @@ struct dzb_ensemble {
   double mu = 0, b = 0, bc0 = 0, bc1 = 0;
   bool fast = false;
   int L = 0;
+  int assembly_mode = 0;
   double* d_mesh = nullptr;
   double *mlo = nullptr, *mdi = nullptr, *mup = nullptr, *slo = nullptr, *sdi = nullptr, *sup = nullptr;  // natural [B][n]
   double *c = nullptr, *den = nullptr;                                                                     // natural [B][n]
@@ -250,6 +251,10 @@ struct dzb_solver {
   bool parallel = false;
   int refine_steps = 0;
   dzb::BigSys big;
+  // what dzb_solver_rebuild needs to assemble again
+  double mu = 0, b = 0, bc0 = 0, bc1 = 0;
+  size_t G = 0;
+  int assembly_mode = 0;
   // time dependent: an ensemble of one bar
   dzb_ensemble* td = nullptr;
 };
@@ -325,6 +330,21 @@ int ensemble_step_once(dzb_ensemble* e, double dt) {
   return DZB_OK;
 }
 
+// assembly of M and S plus the per-matrix Thomas factors, into the buffers the handle already owns
+int ensemble_assemble(dzb_ensemble* e) {
+  dzb::AsmParams P{e->mu, e->b, e->bc0, e->bc1, 0.0, 0.0};
+  dzb::AsmOut o{e->slo, e->sdi, e->sup, nullptr, e->mlo, e->mdi, e->mup};
+  int rc = launch_assembly<dzb::KIND_TD>(e->d_mesh, e->n, e->B, e->G, e->assembly_mode, P, o, nullptr);
+  if (rc) return rc;
+  if (!e->use_big) {
+    dzb::k_thomas_factor<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)e->n,
+                                                                              (long long)e->B);
+    LAUNCHED();
+  }
+  e->prepared = false;
+  return DZB_OK;
+}
+
 int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, double b, double bc0, double bc1, const double* h_ic,
                          size_t n_ic, size_t G, const dzb_options* opt_in, dzb_ensemble** out) {
   if (!out) return fail(DZB_INVALID, "null output handle");
@@ -357,31 +377,24 @@ int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, 
     k_td_init_state<<<blocks_for((long long)tot, 256), 256, 0, g_stream>>>(e->u[1], e->u[0], (long long)n, (long long)B, bc0, bc1);
     ++g_launches;
   }
-  dzb::AsmParams P{mu, b, bc0, bc1, 0.0, 0.0};
-  dzb::AsmOut o{e->slo, e->sdi, e->sup, nullptr, e->mlo, e->mdi, e->mup};
-  if ((rc = launch_assembly<dzb::KIND_TD>(e->d_mesh, n, B, G, opt.assembly_mode, P, o, nullptr))) return bail(rc);
-
   int solve_mode = opt.solve_mode;
   if (solve_mode == DZB_SOLVE_AUTO) solve_mode = tot <= 65536 ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
   if (solve_mode == DZB_SOLVE_PARALLEL && n > 1024 && B != 1)
     return bail(fail(DZB_INVALID, "PARALLEL ensembles support bars of up to 1024 nodes (longer bars: one bar per handle)"));
+  e->assembly_mode = opt.assembly_mode;
   if (solve_mode == DZB_SOLVE_PARALLEL && n > 1024) {
     e->use_big = true;
     if (dzb::bigsys_prepare(&e->big, n)) return bail(fail(DZB_CUDA, dzb::bigsys_error()));
-  } else {
-    dzb::k_thomas_factor<<<blocks_for((long long)B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)n,
-                                                                           (long long)B);
-    ++g_launches;
-    if (solve_mode == DZB_SOLVE_PARALLEL) {
-      int L = 1;
-      while ((size_t)32 * L < n) L <<= 1;
-      e->L = L;
-      e->fast = true;
-      const size_t np = B * 32 * (size_t)L;
-      for (double** p : {&e->a_lo, &e->a_di, &e->a_up, &e->alpha, &e->cc})
-        if ((rc = dalloc(p, np))) return bail(rc);
-    }
+  } else if (solve_mode == DZB_SOLVE_PARALLEL) {
+    int L = 1;
+    while ((size_t)32 * L < n) L <<= 1;
+    e->L = L;
+    e->fast = true;
+    const size_t np = B * 32 * (size_t)L;
+    for (double** p : {&e->a_lo, &e->a_di, &e->a_up, &e->alpha, &e->cc})
+      if ((rc = dalloc(p, np))) return bail(rc);
   }
+  if ((rc = ensemble_assemble(e))) return bail(rc);
   if (cudaStreamSynchronize(g_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
     return bail(fail(DZB_CUDA, std::string("ensemble setup: ") + cudaGetErrorString(cudaGetLastError())));
   *out = e;
@@ -491,6 +504,15 @@ int dzb_mesh_from_nodes(const double* x, size_t n, dzb_mesh** out) {
   *out = m;
   return DZB_OK;
 }
+int dzb_mesh_set_nodes(dzb_mesh* m, const double* x, size_t n) {
+  if (!m || !x) return fail(DZB_INVALID, "null pointer");
+  if (n != m->n) return fail(DZB_WRONG_DIMS, "node count");
+  if (m->from_obj) return fail(DZB_INVALID, "only meshes made by dzb_mesh_from_nodes can be re-pointed");
+  m->h_nodes.assign(x, x + n);
+  m->max_length = -x[0] + x[n - 1];
+  CK(cudaMemcpyAsync(m->d_nodes, x, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  return sync_stream();
+}
 int dzb_mesh_node_count(const dzb_mesh* m, size_t* n) {
   if (!m || !n) return fail(DZB_INVALID, "null pointer");
   *n = m->n;
@@ -559,6 +581,13 @@ static int static_alloc(dzb_solver* s, size_t n) {
     if ((rc = dalloc(p, n))) return rc;
   return DZB_OK;
 }
+static int static_factor(dzb_solver* s) {  // per-matrix work of the serial path (the PARALLEL path has none)
+  if (!s->parallel) {
+    dzb::k_thomas_factor<<<1, 32, 0, g_stream>>>(s->lo, s->di, s->up, s->c, s->den, (long long)s->n, 1);
+    LAUNCHED();
+  }
+  return DZB_OK;
+}
 static int static_finish(dzb_solver* s, const dzb_options& opt) {
   const size_t n = s->n;
   int solve_mode = opt.solve_mode;
@@ -573,8 +602,7 @@ static int static_finish(dzb_solver* s, const dzb_options& opt) {
     int rc;
     if ((rc = dalloc(&s->c, n))) return rc;
     if ((rc = dalloc(&s->den, n))) return rc;
-    dzb::k_thomas_factor<<<1, 32, 0, g_stream>>>(s->lo, s->di, s->up, s->c, s->den, (long long)n, 1);
-    LAUNCHED();
+    if ((rc = static_factor(s))) return rc;
   }
   return sync_stream();
 }
@@ -588,6 +616,7 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
   if (m->n < 3) return fail(DZB_WRONG_DIMS, "a bar needs at least 3 nodes");
   dzb_solver* s = new dzb_solver;
   s->kind = dzb::KIND_TI, s->n = m->n;
+  s->mu = mu, s->b = b, s->bc0 = bc_left, s->bc1 = bc_right, s->G = G, s->assembly_mode = opt.assembly_mode;
   int rc = static_alloc(s, s->n);
   if (!rc) {
     dzb::AsmParams P{mu, b, bc_left, bc_right, 0.0, 0.0};
@@ -661,6 +690,24 @@ int dzb_diffusion_td_create(const dzb_mesh* m, double mu, double b, double bc_le
   s->kind = dzb::KIND_TD, s->n = m->n, s->td = e;
   *out = s;
   return DZB_OK;
+}
+
+int dzb_solver_rebuild(dzb_solver* s, const dzb_mesh* m) {
+  if (!s || !m) return fail(DZB_INVALID, "null pointer");
+  if (m->n != s->n) return fail(DZB_WRONG_DIMS, "rebuild needs a mesh with the solver's node count");
+  if (s->kind == dzb::KIND_TI) {
+    dzb::AsmParams P{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
+    dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
+    int rc = launch_assembly<dzb::KIND_TI>(m->d_nodes, s->n, 1, s->G, s->assembly_mode, P, o, nullptr);
+    if (rc) return rc;
+    return static_factor(s);
+  }
+  if (s->kind == dzb::KIND_TD) {
+    dzb_ensemble* e = s->td;
+    CK(cudaMemcpyAsync(e->d_mesh, m->d_nodes, s->n * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    return ensemble_assemble(e);
+  }
+  return fail(DZB_INVALID, "the Stokes solver samples a host closure: build a new solver instead");
 }
 
 int dzb_solver_solve_device(dzb_solver* s, double dt, const double** dev) {

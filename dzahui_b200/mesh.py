@@ -38,6 +38,12 @@ class Mesh:
         check(lib.dzb_mesh_from_nodes(x.ctypes.data_as(_lib.c_double_p), x.size, C.byref(h)), lib)
         return cls(h, lib)
 
+    def set_nodes(self, nodes):
+        """re-point a from_nodes mesh at new coordinates (same count) without reallocating device memory"""
+        x = np.ascontiguousarray(np.asarray(nodes, dtype=np.float64))
+        check(self._lib.dzb_mesh_set_nodes(self._h, x.ctypes.data_as(_lib.c_double_p), x.size), self._lib)
+        self.max_length = float(-x[0] + x[-1])
+
     def filter_for_solving_1d(self):
         out = np.empty(self.n, dtype=np.float64)
         check(self._lib.dzb_mesh_nodes(self._h, out.ctypes.data_as(_lib.c_double_p), self.n), self._lib)

@@ -67,6 +67,17 @@ class DiffEquationSolver:
         check(self._lib.dzb_solver_solve(self._h, float(time_step), out.ctypes.data_as(_lib.c_double_p), self.n), self._lib)
         return out
 
+    def rebuild(self, mesh=None):
+        """XSolver::new again into the same device buffers (same node count and params): re-assemble for `mesh`"""
+        m = self._mesh if mesh is None else _as_mesh(mesh)
+        check(self._lib.dzb_solver_rebuild(self._h, m._h), self._lib)
+        self._mesh = m
+
+    def solve_into(self, time_step, host_ptr):
+        """solve() into a caller-owned (e.g. pinned) host buffer of n doubles"""
+        check(self._lib.dzb_solver_solve(self._h, float(time_step), C.cast(C.c_void_p(int(host_ptr)), _lib.c_double_p), self.n),
+              self._lib)
+
     def solve_device(self, time_step=0.0):
         """Same step, result left on the device; returns the raw device pointer (valid until the next call)."""
         p = C.c_void_p()

@@ -75,6 +75,8 @@ int dzb_launch_count(unsigned long long* count, int reset);
 int dzb_mesh_ingest_obj_1d(const char* path, int has_height_multiplier, double height_multiplier, dzb_mesh** out);
 /* `mesh: Vec<f64>` handed straight to XSolver::new (time_independent.rs:57): sorted ascending, n >= 3. */
 int dzb_mesh_from_nodes(const double* x, size_t n, dzb_mesh** out);
+/* Re-points an existing from_nodes mesh at new coordinates (same n) without reallocating: a moving / re-meshed bar. */
+int dzb_mesh_set_nodes(dzb_mesh* m, const double* x, size_t n);
 int dzb_mesh_node_count(const dzb_mesh* m, size_t* n);
 int dzb_mesh_nodes(const dzb_mesh* m, double* out, size_t n);         /* Mesh::filter_for_solving_1d (mesh/mod.rs:54-68) */
 int dzb_mesh_vertices(const dzb_mesh* m, double* out, size_t len);    /* Mesh.vertices, len = 12n  (0 for from_nodes meshes) */
@@ -105,6 +107,11 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
 int dzb_diffusion_td_create(const dzb_mesh* m, double mu, double b, double bc_left, double bc_right,
                             const double* initial_conditions, size_t n_ic, size_t gauss_step,
                             const dzb_options* opt, dzb_solver** out);
+
+/* XSolver::new again, into the buffers the handle already owns (same node count, same params): re-assembles K (or M, S;
+ * the time-dependent state is kept) for the mesh's current coordinates.  This is the "assemble" half of one
+ * assemble + solve step without allocator traffic; the Stokes solver (host closure) is not rebuildable. */
+int dzb_solver_rebuild(dzb_solver* s, const dzb_mesh* m);
 
 /* DiffEquationSolver::solve(&mut self, time_step) -> Result<Vec<f64>, Error> (solver_trait.rs:23).
  * Synchronous: `out_host[0..n)` holds the nodal values on return.  Static solvers ignore time_step; the
