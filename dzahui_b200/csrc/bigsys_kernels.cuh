@@ -2,21 +2,31 @@
 //
 // The reference solves K u = b with the serial Thomas recurrence (matrix_solver/mod.rs:17-48), which cannot use a GPU
 // at n = 10^7.  Here every thread runs a *modified Thomas* sweep over R = 8 consecutive rows that eliminates the six
-// interior unknowns and leaves two equations coupling the chunk's first/last unknown with the neighbouring chunks:
-//     s-row:  lo_s u_{s-1} + (di_s - up_s a_1) u_s - up_s c_1 u_e           = f_s - up_s d_1
-//     e-row:               a_7 u_s           +      u_e + c_7 u_{e+1}       = d_7
-// which is again a tridiagonal system, of a quarter of the size, in the order (s_0, e_0, s_1, e_1, ...).  The interior
-// values follow without division, u_j = d_j - a_j u_s - c_j u_e.  The reduction is applied recursively:
+// interior unknowns and leaves two equations coupling the chunk's first/last unknown (u_s, u_e) with the neighbouring
+// chunks — again a tridiagonal system, of a quarter of the size, in the order (s_0, e_0, s_1, e_1, ...).  The reduction
+// is applied recursively:
 //     level 0   registers      2048 rows per CTA (256 threads x 8 rows, 128-bit loads)
 //     level 1-4 shared memory  512 -> 128 -> 32 -> 8 -> 2 rows, chunk-interleaved SoA (conflict-free)
 //     grid      k_tri_tile<REDUCE> writes 2 rows per tile; k_tri_mid (one CTA, shared memory only) solves that system
-//               (recursing through k_tri_tile again while it exceeds 2048 rows); k_tri_tile<SOLVE> redoes the up-sweep on chip and walks back
-//               down.  HBM traffic: 32 B/row (reduce) + 40 B/row (solve) for materialised bands.
-// Pivoting: none, like the reference; chunk-local pivots are the diagonals of the diffusion / mass matrices
-// (M-matrices), not the cancelling diagonal of the Stokes matrix, which therefore stays on the serial kernel.
-// Accuracy: a partitioned elimination loses ~2 digits against serial Thomas on the n = 10^7 stiffness matrix (see
-// DESIGN.md), so static solves refine once with a double-double residual (k_residual_dd), which lands closer to the
-// exact solution of the reference's system than the reference's own f64 Thomas does.
+//               (recursing through k_tri_tile again while it exceeds 2048 rows); k_tri_tile<SOLVE> redoes the forward
+//               sweeps on chip and back-substitutes.  HBM traffic: 32 B/row (reduce) + 40 B/row (solve).
+//
+// Accuracy.  A plain partitioned elimination is ~150x LESS accurate than serial Thomas on the n = 10^7 stiffness matrix
+// (identical chunks make identical rounding errors, which add up coherently in the nearly-cancelling row sums).  Rows are
+// therefore carried in the Grassmann-Taksar-Heyman form (a, c, s, f):  a u_{i-1} + (s - a - c) u_i + c u_{i+1} = f,
+// with the row-sum excess s = lo + di + up obtained once by an error-free TwoSum.  For an M-matrix (a, c <= 0 <= s) every
+// update below adds quantities of one sign, so nothing cancels; for other sign patterns it is ordinary elimination.
+// Measured against a __float128 Thomas of the same system (regular bar, mu = b = 1): n = 10^7 -> 1.4e-10 relative L2,
+// where the reference's own f64 Thomas is at 2.6e-7 (tests/test_gpu_parity.py).
+// Pivoting: none, like the reference.  The Stokes matrix (cancelling ~0 diagonal) stays on the serial kernel.
+//
+// One chunk, rows j = 0..7 (row 0 = s, row 7 = e), forward sweep only:
+//     alpha_j = m alpha_{j-1},  sigma_j = S_j + m sigma_{j-1},  delta_j = F_j + m delta_{j-1},  m = -A_j / beta_{j-1},
+//     beta_j  = sigma_j - alpha_j - C_j                      (row j:  alpha_j u_s + beta_j u_j + C_j u_{j+1} = delta_j)
+//   e-row = (alpha_7, C_7, sigma_7, delta_7);  the s-row needs rows 1..6 folded back into row 0, which is accumulated on
+//   the way with the running product P_j = (-C_0/beta_1) prod_{k<j} (-C_k/beta_{k+1}):
+//   s-row = (A_0, P_6 C_6, S_0 + sum_j P_j sigma_j, F_0 + sum_j P_j delta_j).
+//   Once u_s, u_e are known: u_j = (delta_j - alpha_j u_s - C_j u_{j+1}) / beta_j, j = 6..1.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -32,60 +42,67 @@ constexpr int BS_THREADS = 256;               // tile kernel
 constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
 constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
 
+enum { BS_SRC_BANDS = 0, BS_SRC_ROWS = 1 };   // inputs are (lo, di, up, f) or already (a, c, s, f)
+
+// fl(lo + di + up) with a single rounding (TwoSum twice)
+__device__ __forceinline__ double excess3(double lo, double di, double up) {
+  const double s1 = lo + up, b1 = s1 - lo, e1 = (lo - (s1 - b1)) + (up - b1);
+  const double s2 = s1 + di, b2 = s2 - s1, e2 = (s1 - (s2 - b2)) + (di - b2);
+  return s2 + (e1 + e2);
+}
+
 // Shared-memory level: 8*P rows, SoA, row r of the level at (r % 8) * P + r / 8.
 struct LevelPtr {
-  double *a, *b, *c, *d;
+  double *a, *c, *s, *d;
 };
 __device__ __forceinline__ int lvl_pos(int r, int P) { return (r & 7) * P + (r >> 3); }
 
-// One chunk (thread t of P) of a shared-memory level: modified Thomas in place, reduced rows -> next level (PN chunks;
-// PN == 0: the next level is the final 2-row system stored at index 0/1).
+// One chunk (thread t of P) of a shared-memory level, reduced rows -> next level (PN chunks; PN == 0: the next level is
+// the final 2-row system stored at index 0/1).
 __device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, const LevelPtr& nx, int PN, int t) {
-  const double L0 = lv.a[t], D0 = lv.b[t], U0 = lv.c[t], F0 = lv.d[t];
+  const double A0 = lv.a[t], C0 = lv.c[t], S0 = lv.s[t], F0 = lv.d[t];
   int idx = P + t;
-  double r = __drcp_rn(lv.b[idx]);
-  double aj = lv.a[idx] * r, cj = lv.c[idx] * r, dj = lv.d[idx] * r;
-  lv.a[idx] = aj, lv.c[idx] = cj, lv.d[idx] = dj;
+  double alpha = lv.a[idx], sigma = lv.s[idx], delta = lv.d[idx], gam = lv.c[idx];
+  double r = __drcp_rn((sigma - alpha) - gam);
+  lv.s[idx] = r;
+  double Pr = -C0 * r;
+  double accS = fma(Pr, sigma, S0), accF = fma(Pr, delta, F0), lastG = gam;
 #pragma unroll
   for (int j = 2; j < BS_R; ++j) {
     idx += P;
-    const double l = lv.a[idx];
-    r = __drcp_rn(fma(-l, cj, lv.b[idx]));
-    aj = -l * aj * r;
-    dj = fma(-l, dj, lv.d[idx]) * r;
-    cj = lv.c[idx] * r;
-    lv.a[idx] = aj, lv.c[idx] = cj, lv.d[idx] = dj;
-  }
-  const double ea = aj, ec = cj, ed = dj;
-  idx = 6 * P + t;
-  double a1 = lv.a[idx], c1 = lv.c[idx], d1 = lv.d[idx];
-#pragma unroll
-  for (int j = BS_R - 3; j >= 1; --j) {
-    idx -= P;
-    const double cc = lv.c[idx];
-    d1 = fma(-cc, d1, lv.d[idx]);
-    a1 = fma(-cc, a1, lv.a[idx]);
-    c1 = -cc * c1;
-    lv.a[idx] = a1, lv.c[idx] = c1, lv.d[idx] = d1;
+    const double m = -lv.a[idx] * r;
+    alpha = m * alpha;
+    sigma = fma(m, sigma, lv.s[idx]);
+    delta = fma(m, delta, lv.d[idx]);
+    const double gprev = gam;
+    gam = lv.c[idx];
+    r = __drcp_rn((sigma - alpha) - gam);
+    if (j < BS_R - 1) {
+      lv.a[idx] = alpha, lv.s[idx] = r, lv.d[idx] = delta;
+      Pr *= -gprev * r;
+      accS = fma(Pr, sigma, accS), accF = fma(Pr, delta, accF), lastG = gam;
+    }
   }
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
-  nx.a[p0] = L0, nx.b[p0] = fma(-U0, a1, D0), nx.c[p0] = -U0 * c1, nx.d[p0] = fma(-U0, d1, F0);
-  nx.a[p1] = ea, nx.b[p1] = 1.0, nx.c[p1] = ec, nx.d[p1] = ed;
+  nx.a[p0] = A0, nx.c[p0] = Pr * lastG, nx.s[p0] = accS, nx.d[p0] = accF;
+  nx.a[p1] = alpha, nx.c[p1] = gam, nx.s[p1] = sigma, nx.d[p1] = delta;
 }
-// Down-sweep of the same chunk: the next level's d[] holds the solved u_s / u_e; this level's d[] receives u.
+// Back-substitution of the same chunk: the next level's d[] holds the solved u_s / u_e; this level's d[] receives u.
 __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, const LevelPtr& nx, int PN, int t) {
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
   const double us = nx.d[p0], ue = nx.d[p1];
   lv.d[t] = us;
   lv.d[7 * P + t] = ue;
+  double nxt = ue;
 #pragma unroll
-  for (int j = 1; j < BS_R - 1; ++j) {
+  for (int j = BS_R - 2; j >= 1; --j) {
     const int idx = j * P + t;
-    lv.d[idx] = fma(-lv.c[idx], ue, fma(-lv.a[idx], us, lv.d[idx]));
+    nxt = fma(-lv.c[idx], nxt, fma(-lv.a[idx], us, lv.d[idx])) * lv.s[idx];
+    lv.d[idx] = nxt;
   }
 }
 
-// Shared-memory pyramid below a level-1 system of 8*P1 rows; P1 is a power of 4 (64 for tiles, 256 for k_tri_mid).
+// Shared-memory pyramid below a level-1 system of 8*P1 rows; P1 is a power of 4 (64 for tiles, up to 256 for k_tri_mid).
 template <int P>
 struct PyramidRows {
   static constexpr int value = 8 * P + PyramidRows<P / 4>::value;
@@ -97,9 +114,9 @@ struct PyramidRows<0> {
 template <int P1>
 struct Pyramid {
   static constexpr int ROWS = PyramidRows<P1>::value;
-  double a[ROWS], b[ROWS], c[ROWS], d[ROWS];
-  __device__ __forceinline__ LevelPtr level(int off) { return {a + off, b + off, c + off, d + off}; }
-  // up-sweep from level 1 to the final 2 rows (all threads of the CTA must call; needs >= P1 threads)
+  double a[ROWS], c[ROWS], s[ROWS], d[ROWS];
+  __device__ __forceinline__ LevelPtr level(int off) { return {a + off, c + off, s + off, d + off}; }
+  // forward sweeps from level 1 to the final 2 rows (all threads of the CTA must call; needs >= P1 threads)
   __device__ __forceinline__ void reduce(int t) {
     int off = 0;
 #pragma unroll
@@ -111,7 +128,7 @@ struct Pyramid {
     __syncthreads();
   }
   __device__ __forceinline__ LevelPtr top() { return level(ROWS - 2); }
-  // down-sweep; top().d[0..1] must hold the solved pair
+  // back-substitution; top().d[0..1] must hold the solved pair
   __device__ __forceinline__ void backsolve(int t) {
     int off = ROWS - 2;
 #pragma unroll
@@ -125,80 +142,92 @@ struct Pyramid {
 };
 
 // ---- tile kernel --------------------------------------------------------------------------------------------------
-// SOLVE == false: up-sweep, the tile's two reduced rows -> red_{lo,di,up,f}[2 tile + {0,1}].
-// SOLVE == true : up-sweep again, take (u_s, u_e) of the tile from ured[2 tile + {0,1}], down-sweep, write out[]
+// SOLVE == false: forward sweeps, the tile's two reduced rows -> red_{a,c,s,f}[2 tile + {0,1}].
+// SOLVE == true : forward sweeps again, (u_s, u_e) of the tile from ured[2 tile + {0,1}], back-substitution, out[]
 //                 (ACCUM: out[] += value, the iterative-refinement update).
-template <bool SOLVE, bool ACCUM>
-__global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __restrict__ lo, const double* __restrict__ di,
-                                                         const double* __restrict__ up, const double* __restrict__ f,
-                                                         long long m, double* __restrict__ red_lo,
-                                                         double* __restrict__ red_di, double* __restrict__ red_up,
-                                                         double* __restrict__ red_f, const double* __restrict__ ured,
-                                                         double* __restrict__ out) {
+// SRC: p0..p3 = (lo, di, up, f) of the caller's system, or (a, c, s, f) of a reduced system.
+template <int SRC, bool SOLVE, bool ACCUM>
+__global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __restrict__ p0, const double* __restrict__ p1,
+                                                            const double* __restrict__ p2, const double* __restrict__ p3,
+                                                            long long m, double* __restrict__ red_a,
+                                                            double* __restrict__ red_c, double* __restrict__ red_s,
+                                                            double* __restrict__ red_f, const double* __restrict__ ured,
+                                                            double* __restrict__ out) {
   __shared__ Pyramid<BS_THREADS / 4> pyr;  // level 1: 512 rows = 64 chunks
   const int t = threadIdx.x;
   const long long g0 = (long long)blockIdx.x * BS_TILE + (long long)t * BS_R;
-  double L[BS_R], D[BS_R], U[BS_R], F[BS_R];
+  double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
   if (g0 + BS_R <= m) {
-    const double2* pl = reinterpret_cast<const double2*>(lo + g0);
-    const double2* pd = reinterpret_cast<const double2*>(di + g0);
-    const double2* pu = reinterpret_cast<const double2*>(up + g0);
-    const double2* pf = reinterpret_cast<const double2*>(f + g0);
+    const double2* q0 = reinterpret_cast<const double2*>(p0 + g0);
+    const double2* q1 = reinterpret_cast<const double2*>(p1 + g0);
+    const double2* q2 = reinterpret_cast<const double2*>(p2 + g0);
+    const double2* q3 = reinterpret_cast<const double2*>(p3 + g0);
 #pragma unroll
     for (int j = 0; j < BS_R / 2; ++j) {
-      const double2 vl = __ldcs(pl + j), vd = __ldcs(pd + j), vu = __ldcs(pu + j), vf = __ldcs(pf + j);
-      L[2 * j] = vl.x, L[2 * j + 1] = vl.y, D[2 * j] = vd.x, D[2 * j + 1] = vd.y;
-      U[2 * j] = vu.x, U[2 * j + 1] = vu.y, F[2 * j] = vf.x, F[2 * j + 1] = vf.y;
+      const double2 v0 = __ldcs(q0 + j), v1 = __ldcs(q1 + j), v2 = __ldcs(q2 + j), v3 = __ldcs(q3 + j);
+      if (SRC == BS_SRC_BANDS) {
+        A[2 * j] = v0.x, A[2 * j + 1] = v0.y, S[2 * j] = v1.x, S[2 * j + 1] = v1.y;  // S holds di for now
+        C[2 * j] = v2.x, C[2 * j + 1] = v2.y;
+      } else {
+        A[2 * j] = v0.x, A[2 * j + 1] = v0.y, C[2 * j] = v1.x, C[2 * j + 1] = v1.y;
+        S[2 * j] = v2.x, S[2 * j + 1] = v2.y;
+      }
+      F[2 * j] = v3.x, F[2 * j + 1] = v3.y;
     }
   } else {
 #pragma unroll
     for (int j = 0; j < BS_R; ++j) {
       const long long g = g0 + j;
       const bool in = g < m;
-      L[j] = in ? lo[g] : 0.0, D[j] = in ? di[g] : 1.0, U[j] = in ? up[g] : 0.0, F[j] = in ? f[g] : 0.0;
+      if (SRC == BS_SRC_BANDS) A[j] = in ? p0[g] : 0.0, S[j] = in ? p1[g] : 1.0, C[j] = in ? p2[g] : 0.0;
+      else A[j] = in ? p0[g] : 0.0, C[j] = in ? p1[g] : 0.0, S[j] = in ? p2[g] : 1.0;
+      F[j] = in ? p3[g] : 0.0;
     }
   }
-  if (g0 == 0) L[0] = 0.0;
+  if (g0 == 0) A[0] = 0.0;
   if (m - 1 >= g0 && m - 1 < g0 + BS_R) {
 #pragma unroll
     for (int j = 0; j < BS_R; ++j)
-      if (g0 + j == m - 1) U[j] = 0.0;
+      if (g0 + j == m - 1) C[j] = 0.0;
   }
-  // level 0 in registers: (L, U, F)[1..7] become (a, c, d)
-  const double L0 = L[0], D0 = D[0], U0 = U[0], F0 = F[0];
-  {
-    double r = __drcp_rn(D[1]);
-    L[1] *= r, U[1] *= r, F[1] *= r;
+  if (SRC == BS_SRC_BANDS) {
 #pragma unroll
-    for (int j = 2; j < BS_R; ++j) {
-      const double l = L[j];
-      r = __drcp_rn(fma(-l, U[j - 1], D[j]));
-      L[j] = -l * L[j - 1] * r;
-      F[j] = fma(-l, F[j - 1], F[j]) * r;
-      U[j] *= r;
-    }
+    for (int j = 0; j < BS_R; ++j) S[j] = excess3(A[j], S[j], C[j]);
   }
-  const double ea = L[BS_R - 1], ec = U[BS_R - 1], ed = F[BS_R - 1];
-#pragma unroll
-  for (int j = BS_R - 3; j >= 1; --j) {
-    const double cc = U[j];
-    F[j] = fma(-cc, F[j + 1], F[j]);
-    L[j] = fma(-cc, L[j + 1], L[j]);
-    U[j] = -cc * U[j + 1];
-  }
+  // level 0 in registers; SOLVE keeps (alpha_j, 1/beta_j, delta_j) in (A, S, F)[1..6]
   constexpr int P1 = BS_THREADS / 4;
   {
+    double alpha = A[1], sigma = S[1], delta = F[1], gam = C[1];
+    double r = __drcp_rn((sigma - alpha) - gam);
+    S[1] = r;
+    double Pr = -C[0] * r;
+    double accS = fma(Pr, sigma, S[0]), accF = fma(Pr, delta, F[0]), lastG = gam;
+#pragma unroll
+    for (int j = 2; j < BS_R; ++j) {
+      const double mm = -A[j] * r;
+      alpha = mm * alpha;
+      sigma = fma(mm, sigma, S[j]);
+      delta = fma(mm, delta, F[j]);
+      const double gprev = gam;
+      gam = C[j];
+      r = __drcp_rn((sigma - alpha) - gam);
+      if (j < BS_R - 1) {
+        if (SOLVE) A[j] = alpha, S[j] = r, F[j] = delta;
+        Pr *= -gprev * r;
+        accS = fma(Pr, sigma, accS), accF = fma(Pr, delta, accF), lastG = gam;
+      }
+    }
     LevelPtr l1 = pyr.level(0);
-    const int p0 = lvl_pos(2 * t, P1), p1 = lvl_pos(2 * t + 1, P1);
-    l1.a[p0] = L0, l1.b[p0] = fma(-U0, L[1], D0), l1.c[p0] = -U0 * U[1], l1.d[p0] = fma(-U0, F[1], F0);
-    l1.a[p1] = ea, l1.b[p1] = 1.0, l1.c[p1] = ec, l1.d[p1] = ed;
+    const int i0 = lvl_pos(2 * t, P1), i1 = lvl_pos(2 * t + 1, P1);
+    l1.a[i0] = A[0], l1.c[i0] = Pr * lastG, l1.s[i0] = accS, l1.d[i0] = accF;
+    l1.a[i1] = alpha, l1.c[i1] = gam, l1.s[i1] = sigma, l1.d[i1] = delta;
   }
   pyr.reduce(t);
   LevelPtr top = pyr.top();
   if (!SOLVE) {
     if (t < 2) {
       const long long o = 2LL * blockIdx.x + t;
-      red_lo[o] = top.a[t], red_di[o] = top.b[t], red_up[o] = top.c[t], red_f[o] = top.d[t];
+      red_a[o] = top.a[t], red_c[o] = top.c[t], red_s[o] = top.s[t], red_f[o] = top.d[t];
     }
     return;
   }
@@ -210,7 +239,7 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
     double o[BS_R];
     o[0] = us, o[BS_R - 1] = ue;
 #pragma unroll
-    for (int j = 1; j < BS_R - 1; ++j) o[j] = fma(-U[j], ue, fma(-L[j], us, F[j]));
+    for (int j = BS_R - 2; j >= 1; --j) o[j] = fma(-C[j], o[j + 1], fma(-A[j], us, F[j])) * S[j];
     if (g0 + BS_R <= m) {
       double2* po = reinterpret_cast<double2*>(out + g0);
 #pragma unroll
@@ -233,9 +262,9 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
 // ---- single-CTA kernel: solves an m-row system (m <= 8 P1 <= 2048) entirely in shared memory ------------------------
 // The rows are loaded coalesced straight into level 1 of the pyramid (identity rows pad up to 8 P1); inputs are not
 // modified.  P1 in {4, 16, 64, 256}: 32 / 128 / 512 / 2048 rows.
-template <int P1, bool ACCUM>
-__global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict__ lo, const double* __restrict__ di,
-                                                        const double* __restrict__ up, const double* __restrict__ f, int m,
+template <int P1, int SRC, bool ACCUM>
+__global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict__ p0, const double* __restrict__ p1,
+                                                        const double* __restrict__ p2, const double* __restrict__ p3, int m,
                                                         double* __restrict__ out) {
   extern __shared__ double4 mid_smem[];
   Pyramid<P1>& pyr = *reinterpret_cast<Pyramid<P1>*>(mid_smem);
@@ -243,19 +272,22 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict
   LevelPtr l1 = pyr.level(0);
   for (int r = t; r < 8 * P1; r += BS_THREADS) {
     const int p = lvl_pos(r, P1);
-    const bool in = r < m;
-    l1.a[p] = (in && r > 0) ? lo[r] : 0.0;
-    l1.b[p] = in ? di[r] : 1.0;
-    l1.c[p] = (in && r < m - 1) ? up[r] : 0.0;
-    l1.d[p] = in ? f[r] : 0.0;
+    double a = 0.0, c = 0.0, s = 1.0, f = 0.0;
+    if (r < m) {
+      a = r > 0 ? p0[r] : 0.0;
+      c = r < m - 1 ? (SRC == BS_SRC_BANDS ? p2[r] : p1[r]) : 0.0;
+      s = SRC == BS_SRC_BANDS ? excess3(a, p1[r], c) : p2[r];
+      f = p3[r];
+    }
+    l1.a[p] = a, l1.c[p] = c, l1.s[p] = s, l1.d[p] = f;
   }
   pyr.reduce(t);
   LevelPtr top = pyr.top();
-  if (t == 0) {  // closed 2 x 2 system: [b0 c0; a1 b1] (u_s, u_e) = (f0, f1)
-    const double b0 = top.b[0], c0 = top.c[0], a1 = top.a[1], b1 = top.b[1], f0 = top.d[0], f1 = top.d[1];
-    const double det = fma(b0, b1, -c0 * a1);
-    top.d[0] = fma(f0, b1, -c0 * f1) / det;
-    top.d[1] = fma(b0, f1, -a1 * f0) / det;
+  if (t == 0) {  // closed 2 x 2 system (a_0 = c_1 = 0): [s0 - c0, c0; a1, s1 - a1] (u_s, u_e) = (f0, f1)
+    const double c0 = top.c[0], s0 = top.s[0], f0 = top.d[0], a1 = top.a[1], s1 = top.s[1], f1 = top.d[1];
+    const double det = (s0 * s1 - s0 * a1) - c0 * s1;  // = b0 b1 - c0 a1 without the cancelling c0 a1 terms
+    top.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;
+    top.d[1] = ((s0 - c0) * f1 - a1 * f0) / det;
   }
   pyr.backsolve(t);
   for (int r = t; r < m; r += BS_THREADS) {
@@ -308,7 +340,7 @@ __global__ void k_set_ends(double* __restrict__ u, long long n, double bc0, doub
 // ---- host orchestration --------------------------------------------------------------------------------------------
 struct BigLevel {
   size_t m = 0;  // rows of the reduced system produced at this level
-  double *lo = nullptr, *di = nullptr, *up = nullptr, *f = nullptr, *u = nullptr;
+  double *a = nullptr, *c = nullptr, *s = nullptr, *f = nullptr, *u = nullptr;
 };
 struct BigSys {
   size_t n = 0;
@@ -328,7 +360,7 @@ inline int bigsys_fail(cudaError_t e, const char* what) {
 
 inline void bigsys_free(BigSys* s) {
   for (BigLevel& l : s->levels)
-    for (double** p : {&l.lo, &l.di, &l.up, &l.f, &l.u})
+    for (double** p : {&l.a, &l.c, &l.s, &l.f, &l.u})
       if (*p) cudaFree(*p), *p = nullptr;
   s->levels.clear();
   if (s->resid) cudaFree(s->resid), s->resid = nullptr;
@@ -344,7 +376,7 @@ inline int bigsys_prepare(BigSys* s, size_t n) {
   while (m > (size_t)BS_MID_CAP) {
     BigLevel l;
     l.m = 2 * ((m + BS_TILE - 1) / BS_TILE);
-    for (double** p : {&l.lo, &l.di, &l.up, &l.f, &l.u})
+    for (double** p : {&l.a, &l.c, &l.s, &l.f, &l.u})
       if ((e = cudaMalloc((void**)p, l.m * sizeof(double))) != cudaSuccess) return bigsys_fail(e, "cudaMalloc");
     s->levels.push_back(l);
     m = l.m;
@@ -353,73 +385,74 @@ inline int bigsys_prepare(BigSys* s, size_t n) {
   return 0;
 }
 
-template <int P1>
-inline int bigsys_mid_launch(const double* lo, const double* di, const double* up, const double* f, size_t m, double* out,
+template <int P1, int SRC>
+inline int bigsys_mid_launch(const double* p0, const double* p1, const double* p2, const double* p3, size_t m, double* out,
                              bool accum, cudaStream_t st) {
   constexpr size_t smem = sizeof(Pyramid<P1>);
   if (smem > 48 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e1 = cudaFuncSetAttribute(k_tri_mid<P1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaError_t e2 = cudaFuncSetAttribute(k_tri_mid<P1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e1 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e2 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e1 != cudaSuccess || e2 != cudaSuccess) return bigsys_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute");
       attr_set = true;
     }
   }
   if (accum)
-    k_tri_mid<P1, true><<<1, BS_THREADS, smem, st>>>(lo, di, up, f, (int)m, out);
+    k_tri_mid<P1, SRC, true><<<1, BS_THREADS, smem, st>>>(p0, p1, p2, p3, (int)m, out);
   else
-    k_tri_mid<P1, false><<<1, BS_THREADS, smem, st>>>(lo, di, up, f, (int)m, out);
+    k_tri_mid<P1, SRC, false><<<1, BS_THREADS, smem, st>>>(p0, p1, p2, p3, (int)m, out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : bigsys_fail(e, "k_tri_mid");
 }
-inline int bigsys_mid(const double* lo, const double* di, const double* up, const double* f, size_t m, double* out, bool accum,
+template <int SRC>
+inline int bigsys_mid(const double* p0, const double* p1, const double* p2, const double* p3, size_t m, double* out, bool accum,
                       cudaStream_t st, unsigned long long* launches) {
   ++*launches;
-  if (m <= 32) return bigsys_mid_launch<4>(lo, di, up, f, m, out, accum, st);
-  if (m <= 128) return bigsys_mid_launch<16>(lo, di, up, f, m, out, accum, st);
-  if (m <= 512) return bigsys_mid_launch<64>(lo, di, up, f, m, out, accum, st);
-  return bigsys_mid_launch<256>(lo, di, up, f, m, out, accum, st);
+  if (m <= 32) return bigsys_mid_launch<4, SRC>(p0, p1, p2, p3, m, out, accum, st);
+  if (m <= 128) return bigsys_mid_launch<16, SRC>(p0, p1, p2, p3, m, out, accum, st);
+  if (m <= 512) return bigsys_mid_launch<64, SRC>(p0, p1, p2, p3, m, out, accum, st);
+  return bigsys_mid_launch<256, SRC>(p0, p1, p2, p3, m, out, accum, st);
 }
 
 // out (+)= A^{-1} f for the n-row system (lo, di, up); inputs are not modified.
 inline int bigsys_solve_once(BigSys* s, const double* lo, const double* di, const double* up, const double* f, double* out,
                              bool accum, cudaStream_t st, unsigned long long* launches) {
   cudaError_t e;
-  if (s->levels.empty()) return bigsys_mid(lo, di, up, f, s->n, out, accum, st, launches);
+  if (s->levels.empty()) return bigsys_mid<BS_SRC_BANDS>(lo, di, up, f, s->n, out, accum, st, launches);
   const size_t nl = s->levels.size();
-  // up-sweeps
-  const double *cl = lo, *cd = di, *cu = up, *cf = f;
-  size_t m = s->n;
+  // forward: each application leaves 2 rows per 2048
   for (size_t k = 0; k < nl; ++k) {
     BigLevel& L = s->levels[k];
-    const unsigned tiles = (unsigned)((m + BS_TILE - 1) / BS_TILE);
-    k_tri_tile<false, false><<<tiles, BS_THREADS, 0, st>>>(cl, cd, cu, cf, (long long)m, L.lo, L.di, L.up, L.f, nullptr, nullptr);
+    if (k == 0) {
+      const unsigned tiles = (unsigned)((s->n + BS_TILE - 1) / BS_TILE);
+      k_tri_tile<BS_SRC_BANDS, false, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, L.a, L.c, L.s, L.f, nullptr, nullptr);
+    } else {
+      BigLevel& Q = s->levels[k - 1];
+      const unsigned tiles = (unsigned)((Q.m + BS_TILE - 1) / BS_TILE);
+      k_tri_tile<BS_SRC_ROWS, false, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, L.a, L.c, L.s, L.f, nullptr, nullptr);
+    }
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<reduce>");
-    cl = L.lo, cd = L.di, cu = L.up, cf = L.f, m = L.m;
   }
   {
     BigLevel& L = s->levels[nl - 1];
-    if (bigsys_mid(L.lo, L.di, L.up, L.f, L.m, L.u, false, st, launches)) return 1;
+    if (bigsys_mid<BS_SRC_ROWS>(L.a, L.c, L.s, L.f, L.m, L.u, false, st, launches)) return 1;
   }
-  // down-sweeps
+  // backward
   for (size_t k = nl; k-- > 0;) {
-    const double *sl, *sd, *su, *sf;
-    double* dst;
-    size_t mm;
-    bool acc = false;
-    if (k == 0) sl = lo, sd = di, su = up, sf = f, dst = out, mm = s->n, acc = accum;
-    else {
-      BigLevel& P = s->levels[k - 1];
-      sl = P.lo, sd = P.di, su = P.up, sf = P.f, dst = P.u, mm = P.m;
-    }
-    const unsigned tiles = (unsigned)((mm + BS_TILE - 1) / BS_TILE);
     BigLevel& L = s->levels[k];
-    if (acc)
-      k_tri_tile<true, true><<<tiles, BS_THREADS, 0, st>>>(sl, sd, su, sf, (long long)mm, nullptr, nullptr, nullptr, nullptr, L.u, dst);
-    else
-      k_tri_tile<true, false><<<tiles, BS_THREADS, 0, st>>>(sl, sd, su, sf, (long long)mm, nullptr, nullptr, nullptr, nullptr, L.u, dst);
+    if (k == 0) {
+      const unsigned tiles = (unsigned)((s->n + BS_TILE - 1) / BS_TILE);
+      if (accum)
+        k_tri_tile<BS_SRC_BANDS, true, true><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out);
+      else
+        k_tri_tile<BS_SRC_BANDS, true, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out);
+    } else {
+      BigLevel& Q = s->levels[k - 1];
+      const unsigned tiles = (unsigned)((Q.m + BS_TILE - 1) / BS_TILE);
+      k_tri_tile<BS_SRC_ROWS, true, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, nullptr, nullptr, nullptr, nullptr, L.u, Q.u);
+    }
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<solve>");
   }

@@ -596,7 +596,7 @@ static int static_finish(dzb_solver* s, const dzb_options& opt) {
   if (s->kind == dzb::KIND_STOKES) solve_mode = DZB_SOLVE_FAITHFUL;
   if (solve_mode == DZB_SOLVE_PARALLEL) {
     s->parallel = true;
-    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : (n > (1u << 21) ? 2 : (n > 2048 ? 1 : 0));
+    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : (n > (1u << 22) ? 1 : 0);
     if (dzb::bigsys_prepare(&s->big, n)) return fail(DZB_CUDA, dzb::bigsys_error());
   } else {
     int rc;

@@ -54,7 +54,7 @@ typedef enum dzb_solve_mode {
 typedef struct dzb_options {
   int assembly_mode; /* dzb_assembly_mode */
   int solve_mode;    /* dzb_solve_mode */
-  int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto: 0 up to 2048 rows, 1 up to 2^21, 2 beyond) */
+  int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto: 0 up to 2^22 rows, 1 beyond) */
   int reserved;
 } dzb_options;
 
