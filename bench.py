@@ -32,6 +32,15 @@ ALG_BYTES_TD_STEP = 64       # u in/out 16 B + 3 M bands + 3 S bands 48 B per DO
 ALG_BYTES_STATIC = 80        # assembly 40 B/DOF + solve 40 B/DOF
 
 
+def c5_workload(bars):
+    return (f"C5: ensemble of {bars} x {C5_N}-node bars per GPU, time-dependent diffusion, one solve(dt) per bar per step, "
+            f"dt={C5_DT}, G={G}, mu=b=1, bc=(1,15)")
+
+
+def c4_workload(nodes):
+    return f"C4: one regular bar of {nodes} nodes per GPU, static diffusion assemble + solve per step, G={G}, mu=b=1, bc=(1,15)"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -138,12 +147,19 @@ def cpu_static_sample(n, threads):
     return n / dt, dt
 
 
+def host_threads():
+    """cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the reference arm wants)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, rank):
     """the reference's own CPU algorithm (oracle port; the Rust crate cannot be built in this image) with all host threads"""
     if rank != 0:
         return
-    import oracle_lib as o
-    threads = o.hardware_threads()
+    threads = host_threads()
     vals, secs = [], []
     if args.workload == "c5":
         sample = f"{args.cpu_sample_bars} of {args.bars} bars x {C5_N} nodes, 10 solve(dt) per bench step"
@@ -153,7 +169,7 @@ def run_reference(args, rank):
             if k >= args.warmup:
                 vals.append(v)
                 secs.append(sec)
-        cfg = {"workload": f"C5: ensemble of {args.bars} x {C5_N}-node bars per GPU, time-dependent diffusion, dt={C5_DT}, G={G}"}
+        cfg = {"workload": c5_workload(args.bars)}
     else:
         nn = min(args.nodes, 1_000_000)
         sample = f"{nn}-node regular bar (of {args.nodes}), one assemble + Thomas per bench step"
@@ -162,7 +178,7 @@ def run_reference(args, rank):
             if k >= args.warmup:
                 vals.append(v)
                 secs.append(sec)
-        cfg = {"workload": f"C4: one regular bar of {args.nodes} nodes, static diffusion assemble + solve, G={G}"}
+        cfg = {"workload": c4_workload(args.nodes)}
     value = statistics.mean(vals)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": statistics.mean(secs) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -228,8 +244,7 @@ def main():
         step_e2e = lambda: solver.solve_into(C5_DT, host_out.data_ptr())
         alg_bytes = ALG_BYTES_TD_STEP * dof
         kernel = "k_td_step_fast<32,4>"
-        workload = (f"C5: ensemble of {B} x {n}-node bars per GPU, time-dependent diffusion, one solve(dt) per bar per step, "
-                    f"dt={C5_DT}, G={G}, mu=b=1, bc=(1,15)")
+        workload = c5_workload(B)
         d2h = dof * 8
     else:
         n = args.nodes
@@ -254,7 +269,7 @@ def main():
             solver.solve_into(0.0, host_out.data_ptr())
         alg_bytes = ALG_BYTES_STATIC * dof
         kernel = "assemble + tridiagonal solve kernels"
-        workload = f"C4: one regular bar of {n} nodes per GPU, static diffusion assemble + solve per step, G={G}, mu=b=1, bc=(1,15)"
+        workload = c4_workload(n)
         d2h = dof * 8
 
     # ---- device-resident timing
@@ -310,8 +325,7 @@ def main():
         "extra": extra,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle_lib as o
-        threads = o.hardware_threads()
+        threads = host_threads()
         if args.workload == "c5":
             v_all, t_all = cpu_td_sample(args.cpu_sample_bars, 40, threads)
             v_one, _ = cpu_td_sample(max(args.cpu_sample_bars // 8, 64), 40, 1)

@@ -55,6 +55,14 @@ SIGNATURES = {
     "dzb_solver_bands": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t]),
     "dzb_solver_state": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
     "dzb_solver_destroy": (None, [C.c_void_p]),
+    "dzb_diffusion_ti_create_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                C.c_size_t, C.POINTER(Options), C.POINTER(C.c_void_p)]),
+    "dzb_solver_block_reduce": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "dzb_solver_block_backsolve": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]),
+    "dzb_solver_block_edges": (C.c_int, [C.c_void_p, c_double_p]),
+    "dzb_solver_block_residual": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "dzb_solver_block_read": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
+    "dzb_interface_solve": (C.c_int, [c_double_p, C.c_size_t, c_double_p]),
     "dzb_ensemble_td_create": (C.c_int, [c_double_p, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_double,
                                          C.c_double, c_double_p, C.c_size_t, C.c_size_t, C.POINTER(Options),
                                          C.POINTER(C.c_void_p)]),

@@ -43,6 +43,8 @@ constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
 constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
 
 enum { BS_SRC_BANDS = 0, BS_SRC_ROWS = 1 };   // inputs are (lo, di, up, f) or already (a, c, s, f)
+enum { BS_OPEN_LEFT = 1, BS_OPEN_RIGHT = 2 }; // the system is a block of a longer one: end couplings are kept
+enum { BS_MID_SOLVE = 0, BS_MID_REDUCE = 1, BS_MID_BACKSOLVE = 2 };
 
 // fl(lo + di + up) with a single rounding (TwoSum twice)
 __device__ __forceinline__ double excess3(double lo, double di, double up) {
@@ -57,45 +59,64 @@ struct LevelPtr {
 };
 __device__ __forceinline__ int lvl_pos(int r, int P) { return (r & 7) * P + (r >> 3); }
 
+// Ragged sizes are handled without padding rows: a level holds `rows` rows and its last chunk is simply shorter
+// (len = 2..8; len == 2 has nothing to eliminate, its two rows pass through).  A single left-over row (rows % 8 == 1) is
+// avoided by splitting the last nine rows 7 + 2.  So every unknown of every level is a REAL row — which is what lets
+// a block of a longer bar keep its end couplings (SPIKE split across GPUs): padding rows at an open end would alias the
+// neighbour's unknown instead.
+__device__ __forceinline__ int chunk_len(int rows, int t) {
+  const int T = (rows - 1) >> 3;  // last chunk
+  if ((rows & 7) == 1 && rows > 1) return t == T ? 2 : (t == T - 1 ? 7 : (t < T ? BS_R : 0));
+  return max(0, min(BS_R, rows - BS_R * t));
+}
+// slot (chunk-interleaved position) of row r of a level of `rows` rows with capacity P chunks
+__device__ __forceinline__ int row_slot(int r, int rows, int P) {
+  if ((rows & 7) == 1 && r >= rows - 2 && rows > 1) return (r - (rows - 2)) * P + ((rows - 1) >> 3);
+  return lvl_pos(r, P);
+}
+
 // One chunk (thread t of P) of a shared-memory level, reduced rows -> next level (PN chunks; PN == 0: the next level is
 // the final 2-row system stored at index 0/1).
-__device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, const LevelPtr& nx, int PN, int t) {
+__device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
+  const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
   const double A0 = lv.a[t], C0 = lv.c[t], S0 = lv.s[t], F0 = lv.d[t];
   int idx = P + t;
   double alpha = lv.a[idx], sigma = lv.s[idx], delta = lv.d[idx], gam = lv.c[idx];
-  double r = __drcp_rn((sigma - alpha) - gam);
-  lv.s[idx] = r;
-  double Pr = -C0 * r;
-  double accS = fma(Pr, sigma, S0), accF = fma(Pr, delta, F0), lastG = gam;
-#pragma unroll
-  for (int j = 2; j < BS_R; ++j) {
-    idx += P;
-    const double m = -lv.a[idx] * r;
-    alpha = m * alpha;
-    sigma = fma(m, sigma, lv.s[idx]);
-    delta = fma(m, delta, lv.d[idx]);
-    const double gprev = gam;
-    gam = lv.c[idx];
-    r = __drcp_rn((sigma - alpha) - gam);
-    if (j < BS_R - 1) {
-      lv.a[idx] = alpha, lv.s[idx] = r, lv.d[idx] = delta;
-      Pr *= -gprev * r;
-      accS = fma(Pr, sigma, accS), accF = fma(Pr, delta, accF), lastG = gam;
+  double sc = C0, ss = S0, sf = F0;  // s-row (its a stays A0)
+  if (len >= 3) {
+    double r = __drcp_rn((sigma - alpha) - gam);
+    lv.s[idx] = r;
+    double Pr = -C0 * r;
+    ss = fma(Pr, sigma, S0), sf = fma(Pr, delta, F0);
+    double lastG = gam;
+    for (int j = 2; j < len; ++j) {
+      idx += P;
+      const double m = -lv.a[idx] * r;
+      alpha = m * alpha;
+      sigma = fma(m, sigma, lv.s[idx]);
+      delta = fma(m, delta, lv.d[idx]);
+      const double gprev = gam;
+      gam = lv.c[idx];
+      if (j < len - 1) {
+        r = __drcp_rn((sigma - alpha) - gam);
+        lv.a[idx] = alpha, lv.s[idx] = r, lv.d[idx] = delta;
+        Pr *= -gprev * r;
+        ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
+      }
     }
+    sc = Pr * lastG;
   }
-  const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
-  nx.a[p0] = A0, nx.c[p0] = Pr * lastG, nx.s[p0] = accS, nx.d[p0] = accF;
+  nx.a[p0] = A0, nx.c[p0] = sc, nx.s[p0] = ss, nx.d[p0] = sf;
   nx.a[p1] = alpha, nx.c[p1] = gam, nx.s[p1] = sigma, nx.d[p1] = delta;
 }
 // Back-substitution of the same chunk: the next level's d[] holds the solved u_s / u_e; this level's d[] receives u.
-__device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, const LevelPtr& nx, int PN, int t) {
+__device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
   const double us = nx.d[p0], ue = nx.d[p1];
   lv.d[t] = us;
-  lv.d[7 * P + t] = ue;
+  lv.d[(len - 1) * P + t] = ue;
   double nxt = ue;
-#pragma unroll
-  for (int j = BS_R - 2; j >= 1; --j) {
+  for (int j = len - 2; j >= 1; --j) {
     const int idx = j * P + t;
     nxt = fma(-lv.c[idx], nxt, fma(-lv.a[idx], us, lv.d[idx])) * lv.s[idx];
     lv.d[idx] = nxt;
@@ -116,26 +137,36 @@ struct Pyramid {
   static constexpr int ROWS = PyramidRows<P1>::value;
   double a[ROWS], c[ROWS], s[ROWS], d[ROWS];
   __device__ __forceinline__ LevelPtr level(int off) { return {a + off, c + off, s + off, d + off}; }
-  // forward sweeps from level 1 to the final 2 rows (all threads of the CTA must call; needs >= P1 threads)
-  __device__ __forceinline__ void reduce(int t) {
-    int off = 0;
+  // forward sweeps from level 1 (holding rows1 rows) to the final 2 rows; all threads of the CTA must call
+  __device__ __forceinline__ void reduce(int t, int rows1) {
+    int off = 0, rows = rows1;
 #pragma unroll
     for (int p = P1; p >= 1; p /= 4) {
       __syncthreads();
-      if (t < p) level_reduce(level(off), p, level(off + 8 * p), p / 4, t);
+      if (chunk_len(rows, t) > 0) level_reduce(level(off), p, chunk_len(rows, t), level(off + 8 * p), p / 4, t);
       off += 8 * p;
+      rows = 2 * ((rows + BS_R - 1) / BS_R);
     }
     __syncthreads();
   }
   __device__ __forceinline__ LevelPtr top() { return level(ROWS - 2); }
   // back-substitution; top().d[0..1] must hold the solved pair
-  __device__ __forceinline__ void backsolve(int t) {
-    int off = ROWS - 2;
+  __device__ __forceinline__ void backsolve(int t, int rows1) {
+    int rows_at[8];
+    {
+      int rows = rows1, k = 0;
+#pragma unroll
+      for (int p = P1; p >= 1; p /= 4) rows_at[k++] = rows, rows = 2 * ((rows + BS_R - 1) / BS_R);
+    }
+    int off = ROWS - 2, k = 0;
+#pragma unroll
+    for (int p = 1; p <= P1; p *= 4) ++k;
 #pragma unroll
     for (int p = 1; p <= P1; p *= 4) {
       off -= 8 * p;
+      --k;
       __syncthreads();
-      if (t < p) level_backsolve(level(off), p, level(off + 8 * p), p / 4, t);
+      if (chunk_len(rows_at[k], t) > 0) level_backsolve(level(off), p, chunk_len(rows_at[k], t), level(off + 8 * p), p / 4, t);
     }
     __syncthreads();
   }
@@ -152,12 +183,27 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
                                                             long long m, double* __restrict__ red_a,
                                                             double* __restrict__ red_c, double* __restrict__ red_s,
                                                             double* __restrict__ red_f, const double* __restrict__ ured,
-                                                            double* __restrict__ out) {
-  __shared__ Pyramid<BS_THREADS / 4> pyr;  // level 1: 512 rows = 64 chunks
+                                                            double* __restrict__ out, int flags) {
+  __shared__ Pyramid<BS_THREADS / 4> pyr;  // level 1: up to 512 rows = 64 chunks
   const int t = threadIdx.x;
-  const long long g0 = (long long)blockIdx.x * BS_TILE + (long long)t * BS_R;
+  long long tile0 = (long long)blockIdx.x * BS_TILE;
+  int rows0 = (int)min((long long)BS_TILE, m - tile0);            // rows of this tile
+  {  // never leave a single row to the last tile: split 2047 + 2 instead
+    const long long rem = m - (long long)(gridDim.x - 1) * BS_TILE;
+    if (rem == 1 && gridDim.x > 1) {
+      if (blockIdx.x == gridDim.x - 1) tile0 -= 1, rows0 = 2;
+      else if (blockIdx.x == gridDim.x - 2) rows0 = BS_TILE - 1;
+    }
+  }
+  const int rows1 = 2 * ((rows0 + BS_R - 1) / BS_R);              // rows it leaves at level 1
+  const int len = chunk_len(rows0, t);                            // rows of this thread's chunk (0: idle)
+  const bool shifted = (rows0 & 7) == 1 && rows0 > 1 && t == ((rows0 - 1) >> 3);  // the "2" of a 7 + 2 split
+  const long long g0 = tile0 + (long long)t * BS_R - (shifted ? 1 : 0);
   double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
-  if (g0 + BS_R <= m) {
+  const bool vec = len == BS_R &&  // full chunk whose 128-bit accesses are aligned
+                   !((reinterpret_cast<size_t>(p0 + g0) | reinterpret_cast<size_t>(p1 + g0) | reinterpret_cast<size_t>(p2 + g0) |
+                      reinterpret_cast<size_t>(p3 + g0) | (SOLVE ? reinterpret_cast<size_t>(out + g0) : 0)) & 15);
+  if (vec) {
     const double2* q0 = reinterpret_cast<const double2*>(p0 + g0);
     const double2* q1 = reinterpret_cast<const double2*>(p1 + g0);
     const double2* q2 = reinterpret_cast<const double2*>(p2 + g0);
@@ -178,51 +224,61 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
 #pragma unroll
     for (int j = 0; j < BS_R; ++j) {
       const long long g = g0 + j;
-      const bool in = g < m;
+      const bool in = j < len;
       if (SRC == BS_SRC_BANDS) A[j] = in ? p0[g] : 0.0, S[j] = in ? p1[g] : 1.0, C[j] = in ? p2[g] : 0.0;
       else A[j] = in ? p0[g] : 0.0, C[j] = in ? p1[g] : 0.0, S[j] = in ? p2[g] : 1.0;
       F[j] = in ? p3[g] : 0.0;
     }
   }
-  if (g0 == 0) A[0] = 0.0;
-  if (m - 1 >= g0 && m - 1 < g0 + BS_R) {
+  // closed ends cut the first / last coupling; a block of a longer bar (SPIKE split) keeps them
+  if (g0 == 0 && len > 0 && !(flags & BS_OPEN_LEFT)) A[0] = 0.0;
+  if (!(flags & BS_OPEN_RIGHT) && len > 0 && g0 + len == m) {
 #pragma unroll
     for (int j = 0; j < BS_R; ++j)
-      if (g0 + j == m - 1) C[j] = 0.0;
+      if (j == len - 1) C[j] = 0.0;
   }
   if (SRC == BS_SRC_BANDS) {
 #pragma unroll
     for (int j = 0; j < BS_R; ++j) S[j] = excess3(A[j], S[j], C[j]);
   }
-  // level 0 in registers; SOLVE keeps (alpha_j, 1/beta_j, delta_j) in (A, S, F)[1..6]
+  // level 0 in registers; SOLVE keeps (alpha_j, 1/beta_j, delta_j) in (A, S, F)[1..len-2]
   constexpr int P1 = BS_THREADS / 4;
-  {
-    double alpha = A[1], sigma = S[1], delta = F[1], gam = C[1];
-    double r = __drcp_rn((sigma - alpha) - gam);
-    S[1] = r;
-    double Pr = -C[0] * r;
-    double accS = fma(Pr, sigma, S[0]), accF = fma(Pr, delta, F[0]), lastG = gam;
-#pragma unroll
-    for (int j = 2; j < BS_R; ++j) {
-      const double mm = -A[j] * r;
-      alpha = mm * alpha;
-      sigma = fma(mm, sigma, S[j]);
-      delta = fma(mm, delta, F[j]);
-      const double gprev = gam;
-      gam = C[j];
-      r = __drcp_rn((sigma - alpha) - gam);
-      if (j < BS_R - 1) {
-        if (SOLVE) A[j] = alpha, S[j] = r, F[j] = delta;
-        Pr *= -gprev * r;
-        accS = fma(Pr, sigma, accS), accF = fma(Pr, delta, accF), lastG = gam;
-      }
-    }
+  if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
     const int i0 = lvl_pos(2 * t, P1), i1 = lvl_pos(2 * t + 1, P1);
-    l1.a[i0] = A[0], l1.c[i0] = Pr * lastG, l1.s[i0] = accS, l1.d[i0] = accF;
-    l1.a[i1] = alpha, l1.c[i1] = gam, l1.s[i1] = sigma, l1.d[i1] = delta;
+    {
+      double alpha = A[1], sigma = S[1], delta = F[1], gam = C[1];
+      double sc = C[0], ss = S[0], sf = F[0];
+      if (len >= 3) {
+        double r = __drcp_rn((sigma - alpha) - gam);
+        S[1] = r;
+        double Pr = -C[0] * r;
+        ss = fma(Pr, sigma, S[0]), sf = fma(Pr, delta, F[0]);
+        double lastG = gam;
+#pragma unroll
+        for (int j = 2; j < BS_R; ++j) {
+          if (j < len) {
+            const double mm = -A[j] * r;
+            alpha = mm * alpha;
+            sigma = fma(mm, sigma, S[j]);
+            delta = fma(mm, delta, F[j]);
+            const double gprev = gam;
+            gam = C[j];
+            if (j < len - 1) {
+              r = __drcp_rn((sigma - alpha) - gam);
+              if (SOLVE) A[j] = alpha, S[j] = r, F[j] = delta;
+              Pr *= -gprev * r;
+              ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
+            }
+          }
+        }
+        sc = Pr * lastG;
+      }
+      l1.a[i0] = A[0], l1.c[i0] = sc, l1.s[i0] = ss, l1.d[i0] = sf;
+      l1.a[i1] = alpha, l1.c[i1] = gam, l1.s[i1] = sigma, l1.d[i1] = delta;
+    }
   }
-  pyr.reduce(t);
+  pyr.reduce(t, rows1);
   LevelPtr top = pyr.top();
   if (!SOLVE) {
     if (t < 2) {
@@ -232,15 +288,15 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
     return;
   }
   if (t < 2) top.d[t] = ured[2LL * blockIdx.x + t];
-  pyr.backsolve(t);
-  {
+  pyr.backsolve(t, rows1);
+  if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
     const double us = l1.d[lvl_pos(2 * t, P1)], ue = l1.d[lvl_pos(2 * t + 1, P1)];
     double o[BS_R];
-    o[0] = us, o[BS_R - 1] = ue;
+    if (vec) {
+      o[0] = us, o[BS_R - 1] = ue;
 #pragma unroll
-    for (int j = BS_R - 2; j >= 1; --j) o[j] = fma(-C[j], o[j + 1], fma(-A[j], us, F[j])) * S[j];
-    if (g0 + BS_R <= m) {
+      for (int j = BS_R - 2; j >= 1; --j) o[j] = fma(-C[j], o[j + 1], fma(-A[j], us, F[j])) * S[j];
       double2* po = reinterpret_cast<double2*>(out + g0);
 #pragma unroll
       for (int j = 0; j < BS_R / 2; ++j) {
@@ -252,46 +308,61 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
         po[j] = v;
       }
     } else {
+      double nxt = ue;
+#pragma unroll
+      for (int j = BS_R - 1; j >= 0; --j) {
+        if (j == len - 1) o[j] = ue;
+        else if (j == 0) o[j] = us;
+        else if (j < len - 1) nxt = fma(-C[j], nxt, fma(-A[j], us, F[j])) * S[j], o[j] = nxt;
+        else o[j] = 0.0;
+      }
 #pragma unroll
       for (int j = 0; j < BS_R; ++j)
-        if (g0 + j < m) out[g0 + j] = ACCUM ? out[g0 + j] + o[j] : o[j];
+        if (j < len) out[g0 + j] = ACCUM ? out[g0 + j] + o[j] : o[j];
     }
   }
 }
 
 // ---- single-CTA kernel: solves an m-row system (m <= 8 P1 <= 2048) entirely in shared memory ------------------------
-// The rows are loaded coalesced straight into level 1 of the pyramid (identity rows pad up to 8 P1); inputs are not
-// modified.  P1 in {4, 16, 64, 256}: 32 / 128 / 512 / 2048 rows.
-template <int P1, int SRC, bool ACCUM>
+// The rows are loaded coalesced straight into level 1 of the pyramid; inputs are not modified.  P1 in {4, 16, 64, 256}: 32 / 128 / 512 / 2048 rows.
+// MODE: BS_MID_SOLVE      closed system -> out[0..m)
+//       BS_MID_REDUCE     open block: the two rows left after eliminating everything inside -> top8 = (a,c,s,f) x 2
+//       BS_MID_BACKSOLVE  open block whose end unknowns (us, ue) are now known -> out[0..m)
+template <int P1, int SRC, int MODE, bool ACCUM>
 __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict__ p0, const double* __restrict__ p1,
                                                         const double* __restrict__ p2, const double* __restrict__ p3, int m,
-                                                        double* __restrict__ out) {
+                                                        double* __restrict__ out, int flags, double* __restrict__ top8,
+                                                        double us, double ue) {
   extern __shared__ double4 mid_smem[];
   Pyramid<P1>& pyr = *reinterpret_cast<Pyramid<P1>*>(mid_smem);
   const int t = threadIdx.x;
+  const bool open_left = flags & BS_OPEN_LEFT, open_right = flags & BS_OPEN_RIGHT;
   LevelPtr l1 = pyr.level(0);
-  for (int r = t; r < 8 * P1; r += BS_THREADS) {
-    const int p = lvl_pos(r, P1);
-    double a = 0.0, c = 0.0, s = 1.0, f = 0.0;
-    if (r < m) {
-      a = r > 0 ? p0[r] : 0.0;
-      c = r < m - 1 ? (SRC == BS_SRC_BANDS ? p2[r] : p1[r]) : 0.0;
-      s = SRC == BS_SRC_BANDS ? excess3(a, p1[r], c) : p2[r];
-      f = p3[r];
-    }
-    l1.a[p] = a, l1.c[p] = c, l1.s[p] = s, l1.d[p] = f;
-  }
-  pyr.reduce(t);
-  LevelPtr top = pyr.top();
-  if (t == 0) {  // closed 2 x 2 system (a_0 = c_1 = 0): [s0 - c0, c0; a1, s1 - a1] (u_s, u_e) = (f0, f1)
-    const double c0 = top.c[0], s0 = top.s[0], f0 = top.d[0], a1 = top.a[1], s1 = top.s[1], f1 = top.d[1];
-    const double det = (s0 * s1 - s0 * a1) - c0 * s1;  // = b0 b1 - c0 a1 without the cancelling c0 a1 terms
-    top.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;
-    top.d[1] = ((s0 - c0) * f1 - a1 * f0) / det;
-  }
-  pyr.backsolve(t);
   for (int r = t; r < m; r += BS_THREADS) {
-    const double v = l1.d[lvl_pos(r, P1)];
+    const int p = row_slot(r, m, P1);
+    const double a = (r > 0 || open_left) ? p0[r] : 0.0;
+    const double c = (r < m - 1 || open_right) ? (SRC == BS_SRC_BANDS ? p2[r] : p1[r]) : 0.0;
+    l1.a[p] = a, l1.c[p] = c, l1.s[p] = SRC == BS_SRC_BANDS ? excess3(a, p1[r], c) : p2[r], l1.d[p] = p3[r];
+  }
+  pyr.reduce(t, m);
+  LevelPtr top = pyr.top();
+  if (MODE == BS_MID_REDUCE) {
+    if (t < 2) top8[4 * t + 0] = top.a[t], top8[4 * t + 1] = top.c[t], top8[4 * t + 2] = top.s[t], top8[4 * t + 3] = top.d[t];
+    return;
+  }
+  if (t == 0) {
+    if (MODE == BS_MID_SOLVE) {  // closed 2 x 2 system (a_0 = c_1 = 0): [s0 - c0, c0; a1, s1 - a1] (u_s, u_e) = (f0, f1)
+      const double c0 = top.c[0], s0 = top.s[0], f0 = top.d[0], a1 = top.a[1], s1 = top.s[1], f1 = top.d[1];
+      const double det = (s0 * s1 - s0 * a1) - c0 * s1;  // = b0 b1 - c0 a1 without the cancelling c0 a1 terms
+      top.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;
+      top.d[1] = ((s0 - c0) * f1 - a1 * f0) / det;
+    } else {
+      top.d[0] = us, top.d[1] = ue;
+    }
+  }
+  pyr.backsolve(t, m);
+  for (int r = t; r < m; r += BS_THREADS) {
+    const double v = l1.d[row_slot(r, m, P1)];
     out[r] = ACCUM ? out[r] + v : v;
   }
 }
@@ -308,12 +379,15 @@ __device__ __forceinline__ void dd_sub_prod(double& s, double& comp, double x, d
 }
 __global__ void __launch_bounds__(256) k_residual_dd(const double* __restrict__ lo, const double* __restrict__ di,
                                                      const double* __restrict__ up, const double* __restrict__ f,
-                                                     const double* __restrict__ u, double* __restrict__ r, long long n) {
+                                                     const double* __restrict__ u, double* __restrict__ r, long long n,
+                                                     int flags, double u_left, double u_right) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double s = f[i], comp = 0.0;
     if (i > 0) dd_sub_prod(s, comp, lo[i], u[i - 1]);
+    else if (flags & BS_OPEN_LEFT) dd_sub_prod(s, comp, lo[i], u_left);     // halo value of the previous block
     dd_sub_prod(s, comp, di[i], u[i]);
     if (i + 1 < n) dd_sub_prod(s, comp, up[i], u[i + 1]);
+    else if (flags & BS_OPEN_RIGHT) dd_sub_prod(s, comp, up[i], u_right);   // halo value of the next block
     r[i] = s + comp;
   }
 }
@@ -385,78 +459,107 @@ inline int bigsys_prepare(BigSys* s, size_t n) {
   return 0;
 }
 
-template <int P1, int SRC>
+template <int P1, int SRC, int MODE>
 inline int bigsys_mid_launch(const double* p0, const double* p1, const double* p2, const double* p3, size_t m, double* out,
-                             bool accum, cudaStream_t st) {
+                             bool accum, int flags, double* top8, double us, double ue, cudaStream_t st) {
   constexpr size_t smem = sizeof(Pyramid<P1>);
   if (smem > 48 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e1 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaError_t e2 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e1 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e2 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e1 != cudaSuccess || e2 != cudaSuccess) return bigsys_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute");
       attr_set = true;
     }
   }
   if (accum)
-    k_tri_mid<P1, SRC, true><<<1, BS_THREADS, smem, st>>>(p0, p1, p2, p3, (int)m, out);
+    k_tri_mid<P1, SRC, MODE, true><<<1, BS_THREADS, smem, st>>>(p0, p1, p2, p3, (int)m, out, flags, top8, us, ue);
   else
-    k_tri_mid<P1, SRC, false><<<1, BS_THREADS, smem, st>>>(p0, p1, p2, p3, (int)m, out);
+    k_tri_mid<P1, SRC, MODE, false><<<1, BS_THREADS, smem, st>>>(p0, p1, p2, p3, (int)m, out, flags, top8, us, ue);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : bigsys_fail(e, "k_tri_mid");
 }
-template <int SRC>
+template <int SRC, int MODE>
 inline int bigsys_mid(const double* p0, const double* p1, const double* p2, const double* p3, size_t m, double* out, bool accum,
-                      cudaStream_t st, unsigned long long* launches) {
+                      int flags, double* top8, double us, double ue, cudaStream_t st, unsigned long long* launches) {
   ++*launches;
-  if (m <= 32) return bigsys_mid_launch<4, SRC>(p0, p1, p2, p3, m, out, accum, st);
-  if (m <= 128) return bigsys_mid_launch<16, SRC>(p0, p1, p2, p3, m, out, accum, st);
-  if (m <= 512) return bigsys_mid_launch<64, SRC>(p0, p1, p2, p3, m, out, accum, st);
-  return bigsys_mid_launch<256, SRC>(p0, p1, p2, p3, m, out, accum, st);
+  if (m <= 32) return bigsys_mid_launch<4, SRC, MODE>(p0, p1, p2, p3, m, out, accum, flags, top8, us, ue, st);
+  if (m <= 128) return bigsys_mid_launch<16, SRC, MODE>(p0, p1, p2, p3, m, out, accum, flags, top8, us, ue, st);
+  if (m <= 512) return bigsys_mid_launch<64, SRC, MODE>(p0, p1, p2, p3, m, out, accum, flags, top8, us, ue, st);
+  return bigsys_mid_launch<256, SRC, MODE>(p0, p1, p2, p3, m, out, accum, flags, top8, us, ue, st);
 }
 
-// out (+)= A^{-1} f for the n-row system (lo, di, up); inputs are not modified.
-inline int bigsys_solve_once(BigSys* s, const double* lo, const double* di, const double* up, const double* f, double* out,
-                             bool accum, cudaStream_t st, unsigned long long* launches) {
+// forward sweeps of every grid level: each application of k_tri_tile leaves 2 rows per 2048
+inline int bigsys_forward(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
+                          cudaStream_t st, unsigned long long* launches) {
   cudaError_t e;
-  if (s->levels.empty()) return bigsys_mid<BS_SRC_BANDS>(lo, di, up, f, s->n, out, accum, st, launches);
-  const size_t nl = s->levels.size();
-  // forward: each application leaves 2 rows per 2048
-  for (size_t k = 0; k < nl; ++k) {
+  for (size_t k = 0; k < s->levels.size(); ++k) {
     BigLevel& L = s->levels[k];
     if (k == 0) {
       const unsigned tiles = (unsigned)((s->n + BS_TILE - 1) / BS_TILE);
-      k_tri_tile<BS_SRC_BANDS, false, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, L.a, L.c, L.s, L.f, nullptr, nullptr);
+      k_tri_tile<BS_SRC_BANDS, false, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, L.a, L.c, L.s, L.f, nullptr, nullptr, flags);
     } else {
       BigLevel& Q = s->levels[k - 1];
       const unsigned tiles = (unsigned)((Q.m + BS_TILE - 1) / BS_TILE);
-      k_tri_tile<BS_SRC_ROWS, false, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, L.a, L.c, L.s, L.f, nullptr, nullptr);
+      k_tri_tile<BS_SRC_ROWS, false, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, L.a, L.c, L.s, L.f, nullptr, nullptr, flags);
     }
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<reduce>");
   }
-  {
-    BigLevel& L = s->levels[nl - 1];
-    if (bigsys_mid<BS_SRC_ROWS>(L.a, L.c, L.s, L.f, L.m, L.u, false, st, launches)) return 1;
-  }
-  // backward
-  for (size_t k = nl; k-- > 0;) {
+  return 0;
+}
+// back-substitution of every grid level; levels.back().u must hold the solved top-level unknowns
+inline int bigsys_backward(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
+                           double* out, bool accum, cudaStream_t st, unsigned long long* launches) {
+  cudaError_t e;
+  for (size_t k = s->levels.size(); k-- > 0;) {
     BigLevel& L = s->levels[k];
     if (k == 0) {
       const unsigned tiles = (unsigned)((s->n + BS_TILE - 1) / BS_TILE);
       if (accum)
-        k_tri_tile<BS_SRC_BANDS, true, true><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out);
+        k_tri_tile<BS_SRC_BANDS, true, true><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out, flags);
       else
-        k_tri_tile<BS_SRC_BANDS, true, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out);
+        k_tri_tile<BS_SRC_BANDS, true, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out, flags);
     } else {
       BigLevel& Q = s->levels[k - 1];
       const unsigned tiles = (unsigned)((Q.m + BS_TILE - 1) / BS_TILE);
-      k_tri_tile<BS_SRC_ROWS, true, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, nullptr, nullptr, nullptr, nullptr, L.u, Q.u);
+      k_tri_tile<BS_SRC_ROWS, true, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, nullptr, nullptr, nullptr, nullptr, L.u, Q.u, flags);
     }
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<solve>");
   }
   return 0;
+}
+
+// out (+)= A^{-1} f for the closed n-row system (lo, di, up); inputs are not modified.
+inline int bigsys_solve_once(BigSys* s, const double* lo, const double* di, const double* up, const double* f, double* out,
+                             bool accum, cudaStream_t st, unsigned long long* launches) {
+  if (s->levels.empty())
+    return bigsys_mid<BS_SRC_BANDS, BS_MID_SOLVE>(lo, di, up, f, s->n, out, accum, 0, nullptr, 0.0, 0.0, st, launches);
+  if (bigsys_forward(s, lo, di, up, f, 0, st, launches)) return 1;
+  BigLevel& L = s->levels.back();
+  if (bigsys_mid<BS_SRC_ROWS, BS_MID_SOLVE>(L.a, L.c, L.s, L.f, L.m, L.u, false, 0, nullptr, 0.0, 0.0, st, launches)) return 1;
+  return bigsys_backward(s, lo, di, up, f, 0, out, accum, st, launches);
+}
+
+// SPIKE split, first half: eliminate everything inside this block; top8 (device, 8 doubles) receives its two interface
+// rows (a, c, s, f) x 2: a couples the block's first unknown to the previous block's last, c the last to the next's first.
+inline int bigsys_block_reduce(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
+                               double* top8, cudaStream_t st, unsigned long long* launches) {
+  if (s->levels.empty())
+    return bigsys_mid<BS_SRC_BANDS, BS_MID_REDUCE>(lo, di, up, f, s->n, nullptr, false, flags, top8, 0.0, 0.0, st, launches);
+  if (bigsys_forward(s, lo, di, up, f, flags, st, launches)) return 1;
+  BigLevel& L = s->levels.back();
+  return bigsys_mid<BS_SRC_ROWS, BS_MID_REDUCE>(L.a, L.c, L.s, L.f, L.m, nullptr, false, flags, top8, 0.0, 0.0, st, launches);
+}
+// SPIKE split, second half: the interface solve gave this block's end unknowns (us, ue); back-substitute.
+inline int bigsys_block_backsolve(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
+                                  double us, double ue, double* out, bool accum, cudaStream_t st, unsigned long long* launches) {
+  if (s->levels.empty())
+    return bigsys_mid<BS_SRC_BANDS, BS_MID_BACKSOLVE>(lo, di, up, f, s->n, out, accum, flags, nullptr, us, ue, st, launches);
+  BigLevel& L = s->levels.back();
+  if (bigsys_mid<BS_SRC_ROWS, BS_MID_BACKSOLVE>(L.a, L.c, L.s, L.f, L.m, L.u, false, flags, nullptr, us, ue, st, launches)) return 1;
+  return bigsys_backward(s, lo, di, up, f, flags, out, accum, st, launches);
 }
 
 inline unsigned bigsys_grid(size_t n) {
@@ -470,7 +573,7 @@ inline int bigsys_solve(BigSys* s, const double* lo, const double* di, const dou
                         int refine_steps, cudaStream_t st, unsigned long long* launches) {
   if (bigsys_solve_once(s, lo, di, up, rhs, out, false, st, launches)) return 1;
   for (int k = 0; k < refine_steps; ++k) {
-    k_residual_dd<<<bigsys_grid(s->n), 256, 0, st>>>(lo, di, up, rhs, out, s->resid, (long long)s->n);
+    k_residual_dd<<<bigsys_grid(s->n), 256, 0, st>>>(lo, di, up, rhs, out, s->resid, (long long)s->n, 0, 0.0, 0.0);
     ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bigsys_fail(e, "k_residual_dd");

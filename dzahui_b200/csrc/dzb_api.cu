@@ -251,6 +251,12 @@ struct dzb_solver {
   bool parallel = false;
   int refine_steps = 0;
   dzb::BigSys big;
+  // block of a longer bar (SPIKE split across GPUs): the arrays above are views shifted by `off` into allocations that
+  // also hold the halo rows; block_flags = BS_OPEN_LEFT | BS_OPEN_RIGHT
+  size_t off = 0, n_alloc = 0;
+  int block_flags = 0;
+  bool is_block = false;
+  double* d_top8 = nullptr;
   // what dzb_solver_rebuild needs to assemble again
   double mu = 0, b = 0, bc0 = 0, bc1 = 0;
   size_t G = 0;
@@ -695,6 +701,7 @@ int dzb_diffusion_td_create(const dzb_mesh* m, double mu, double b, double bc_le
 int dzb_solver_rebuild(dzb_solver* s, const dzb_mesh* m) {
   if (!s || !m) return fail(DZB_INVALID, "null pointer");
   if (m->n != s->n) return fail(DZB_WRONG_DIMS, "rebuild needs a mesh with the solver's node count");
+  if (s->is_block) return fail(DZB_INVALID, "block solvers are not rebuildable");
   if (s->kind == dzb::KIND_TI) {
     dzb::AsmParams P{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
     dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
@@ -718,6 +725,7 @@ int dzb_solver_solve_device(dzb_solver* s, double dt, const double** dev) {
     *dev = s->td->u[s->td->cur];
     return DZB_OK;
   }
+  if (s->is_block) return fail(DZB_INVALID, "a block solver is driven through dzb_solver_block_* (it needs its neighbours)");
   if (s->parallel) {
     if (dzb::bigsys_solve(&s->big, s->lo, s->di, s->up, s->rhs, s->out, s->refine_steps, g_stream, &g_launches))
       return fail(DZB_CUDA, dzb::bigsys_error());
@@ -770,10 +778,118 @@ int dzb_solver_state(const dzb_solver* s, double* out, size_t n) {
 }
 void dzb_solver_destroy(dzb_solver* s) {
   if (!s) return;
-  for (double** p : {&s->lo, &s->di, &s->up, &s->rhs, &s->c, &s->den, &s->out}) dfree(*p);
+  for (double** p : {&s->lo, &s->di, &s->up, &s->rhs}) {
+    if (*p) *p -= s->off;
+    dfree(*p);
+  }
+  for (double** p : {&s->c, &s->den, &s->out, &s->d_top8}) dfree(*p);
   dzb::bigsys_free(&s->big);
   ensemble_free(s->td);
   delete s;
+}
+
+// ------------------------------------------------------------------------------------------------- SPIKE blocks
+int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right, double mu, double b, double bc_left,
+                                  double bc_right, size_t G, const dzb_options* opt_in, dzb_solver** out) {
+  if (!out || !m) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  const dzb_options opt = resolve_options(opt_in);
+  if (!options_valid(opt)) return fail(DZB_INVALID, "bad dzb_options");
+  const size_t halo = (has_left ? 1 : 0) + (has_right ? 1 : 0);
+  if (m->n < 3 || m->n < halo + 2) return fail(DZB_WRONG_DIMS, "a block needs at least 2 own nodes besides its halo nodes");
+  dzb_solver* s = new dzb_solver;
+  s->kind = dzb::KIND_TI, s->n_alloc = m->n, s->n = m->n - halo;
+  s->mu = mu, s->b = b, s->bc0 = bc_left, s->bc1 = bc_right, s->G = G, s->assembly_mode = opt.assembly_mode;
+  s->is_block = true, s->parallel = true;
+  s->block_flags = (has_left ? dzb::BS_OPEN_LEFT : 0) | (has_right ? dzb::BS_OPEN_RIGHT : 0);
+  s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : 0;
+  // assemble over own + halo nodes: the halo rows come out as (discarded) boundary rows, every own row is exact
+  // one spare element in front so that the block's own rows start 16-byte aligned (128-bit loads in k_tri_tile)
+  const size_t lead = has_left ? 1 : 0;
+  int rc = static_alloc(s, s->n_alloc + lead);
+  if (!rc) rc = dalloc(&s->d_top8, 8);
+  if (!rc) {
+    dzb::AsmParams P{mu, b, bc_left, bc_right, 0.0, 0.0};
+    dzb::AsmOut o{s->lo + lead, s->di + lead, s->up + lead, s->rhs + lead, nullptr, nullptr, nullptr};
+    rc = launch_assembly<dzb::KIND_TI>(m->d_nodes, s->n_alloc, 1, G, opt.assembly_mode, P, o, nullptr);
+  }
+  if (!rc) {
+    s->off = 2 * lead;
+    s->lo += s->off, s->di += s->off, s->up += s->off, s->rhs += s->off;
+    if (dzb::bigsys_prepare(&s->big, s->n)) rc = fail(DZB_CUDA, dzb::bigsys_error());
+  }
+  if (!rc) rc = sync_stream();
+  if (rc) {
+    dzb_solver_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return DZB_OK;
+}
+int dzb_solver_block_reduce(dzb_solver* s, int which_rhs, double top8[8]) {
+  if (!s || !top8) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  const double* f = which_rhs ? s->big.resid : s->rhs;
+  if (dzb::bigsys_block_reduce(&s->big, s->lo, s->di, s->up, f, s->block_flags, s->d_top8, g_stream, &g_launches))
+    return fail(DZB_CUDA, dzb::bigsys_error());
+  CK(cudaMemcpyAsync(top8, s->d_top8, 8 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_solver_block_backsolve(dzb_solver* s, int which_rhs, double us, double ue, int accumulate) {
+  if (!s) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  const double* f = which_rhs ? s->big.resid : s->rhs;
+  if (dzb::bigsys_block_backsolve(&s->big, s->lo, s->di, s->up, f, s->block_flags, us, ue, s->out, accumulate != 0, g_stream,
+                                  &g_launches))
+    return fail(DZB_CUDA, dzb::bigsys_error());
+  return DZB_OK;
+}
+int dzb_solver_block_edges(const dzb_solver* s, double edges[2]) {
+  if (!s || !edges) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  CK(cudaMemcpyAsync(edges, s->out, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(edges + 1, s->out + s->n - 1, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_solver_block_residual(dzb_solver* s, double u_left, double u_right) {
+  if (!s) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  dzb::k_residual_dd<<<dzb::bigsys_grid(s->n), 256, 0, g_stream>>>(s->lo, s->di, s->up, s->rhs, s->out, s->big.resid,
+                                                                    (long long)s->n, s->block_flags, u_left, u_right);
+  LAUNCHED();
+  return DZB_OK;
+}
+int dzb_solver_block_read(const dzb_solver* s, double* out_host, size_t n) {
+  if (!s || !out_host) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  if (n != s->n) return fail(DZB_WRONG_DIMS, "output length != rows owned by the block");
+  CK(cudaMemcpyAsync(out_host, s->out, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+// Host-side interface system of the SPIKE split: rows[8 r .. 8 r + 8) = block r's (a,c,s,f) s-row then e-row; unknowns
+// in the order (s_0, e_0, s_1, e_1, ...) form a tridiagonal system of 2 n_blocks rows, solved here in long double.
+int dzb_interface_solve(const double* rows, size_t n_blocks, double* ends) {
+  if (!rows || !ends) return fail(DZB_INVALID, "null pointer");
+  if (n_blocks == 0) return fail(DZB_WRONG_DIMS, "no blocks");
+  const size_t m = 2 * n_blocks;
+  std::vector<long double> a(m), bb(m), c(m), f(m), cp(m), dp(m);
+  for (size_t i = 0; i < m; ++i) {
+    a[i] = rows[4 * i], c[i] = rows[4 * i + 1], f[i] = rows[4 * i + 3];
+    bb[i] = (long double)rows[4 * i + 2] - a[i] - c[i];  // diagonal = s - a - c
+  }
+  a[0] = 0.0L, c[m - 1] = 0.0L;  // closed ends of the whole bar (already 0 when the end blocks were created as such)
+  cp[0] = c[0] / bb[0], dp[0] = f[0] / bb[0];
+  for (size_t i = 1; i < m; ++i) {
+    const long double den = bb[i] - a[i] * cp[i - 1];
+    cp[i] = c[i] / den, dp[i] = (f[i] - a[i] * dp[i - 1]) / den;
+  }
+  long double x = dp[m - 1];
+  ends[m - 1] = (double)x;
+  for (size_t i = m - 1; i-- > 0;) {
+    x = dp[i] - cp[i] * x;
+    ends[i] = (double)x;
+  }
+  return DZB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- ensembles

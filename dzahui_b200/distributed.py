@@ -1,0 +1,192 @@
+"""Multi-GPU paths of the hot path, one process per GPU.
+
+* Ensembles shard by bars: `shard_bars` gives a rank its contiguous slice; nothing is exchanged while stepping.
+* One long bar (BASELINE config 4) is split SPIKE-style into contiguous row blocks, one per rank.  Each rank
+  eliminates everything inside its block on its own GPU (the same chunk-reduction kernels as the single-GPU solver,
+  with the block's end couplings kept), ONE all-gather moves 8 doubles per rank (the two interface rows), every rank
+  solves the 2P-row interface system redundantly on the host, and back-substitutes locally.  Optional refinement sweeps
+  add one all-gather of the block edge values (the residual's halo) and one more of interface rows per sweep.
+
+Collectives go through `torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests).  `LocalComm` runs
+all blocks in one process — what a single-GPU test uses to exercise the block kernels."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .errors import check
+from .mesh import Mesh
+
+
+# ---------------------------------------------------------------------------------------------- partitioning
+def shard_bars(n_bars, rank, world):
+    """contiguous slice [first, last) of an ensemble's bars owned by `rank`; sizes differ by at most one"""
+    base, rem = divmod(int(n_bars), int(world))
+    first = rank * base + min(rank, rem)
+    return first, first + base + (1 if rank < rem else 0)
+
+
+def partition_rows(n, world):
+    """row blocks [(first, last), ...] of one bar; every block keeps at least 2 rows"""
+    world = int(world)
+    if n < 2 * world:
+        raise ValueError("a bar of %d nodes cannot be split into %d blocks of at least 2 rows" % (n, world))
+    return [shard_bars(n, r, world) for r in range(world)]
+
+
+def block_nodes(mesh, first, last):
+    """the node coordinates block [first, last) needs: its own plus one halo node per existing neighbour"""
+    n = len(mesh)
+    has_left, has_right = first > 0, last < n
+    return np.ascontiguousarray(mesh[first - (1 if has_left else 0): last + (1 if has_right else 0)]), has_left, has_right
+
+
+# ---------------------------------------------------------------------------------------------- communicators
+class LocalComm:
+    """all blocks live in this process (single-GPU emulation of P ranks, run one after another)"""
+    rank, world = 0, 1
+
+    def all_gather(self, local):            # local: [k_local, width] -> [k_total, width]
+        return np.asarray(local, dtype=np.float64)
+
+
+class TorchComm:
+    """torch.distributed process group: NCCL (CUDA staging tensors) or gloo (CPU tensors)"""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist, self._group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        self._device = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                          if backend == "nccl" else torch.device("cpu"))
+
+    def all_gather(self, local):
+        torch = self._torch
+        loc = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(self._device)
+        out = torch.empty((self.world,) + tuple(loc.shape), dtype=torch.float64, device=self._device)
+        self._dist.all_gather_into_tensor(out.view(-1), loc.view(-1), group=self._group)
+        return out.cpu().numpy().reshape(self.world * loc.shape[0], *loc.shape[1:])
+
+
+# ---------------------------------------------------------------------------------------------- one block on one GPU
+class BarBlock:
+    """DiffussionSolverTimeIndependent for the rows of one block (dzb_diffusion_ti_create_block)."""
+
+    def __init__(self, params, nodes_with_halo, has_left, has_right, gauss_step, options=None):
+        self._lib = _lib.load()
+        self._h = None
+        self._mesh = Mesh.from_nodes(nodes_with_halo)
+        h = C.c_void_p()
+        check(self._lib.dzb_diffusion_ti_create_block(self._mesh._h, int(bool(has_left)), int(bool(has_right)), params.mu, params.b,
+                                                      params.boundary_conditions[0], params.boundary_conditions[1],
+                                                      int(gauss_step), C.byref(options) if options is not None else None,
+                                                      C.byref(h)), self._lib)
+        self._h = h
+        self.n = len(nodes_with_halo) - int(bool(has_left)) - int(bool(has_right))
+
+    def block_reduce(self, which_rhs=0):
+        top = np.empty(8)
+        check(self._lib.dzb_solver_block_reduce(self._h, int(which_rhs), top.ctypes.data_as(_lib.c_double_p)), self._lib)
+        return top
+
+    def block_backsolve(self, which_rhs, us, ue, accumulate=False):
+        check(self._lib.dzb_solver_block_backsolve(self._h, int(which_rhs), float(us), float(ue), int(bool(accumulate))), self._lib)
+
+    def block_edges(self):
+        e = np.empty(2)
+        check(self._lib.dzb_solver_block_edges(self._h, e.ctypes.data_as(_lib.c_double_p)), self._lib)
+        return e
+
+    def block_residual(self, u_left, u_right):
+        check(self._lib.dzb_solver_block_residual(self._h, float(u_left), float(u_right)), self._lib)
+
+    def block_read(self):
+        out = np.empty(self.n)
+        check(self._lib.dzb_solver_block_read(self._h, out.ctypes.data_as(_lib.c_double_p), self.n), self._lib)
+        return out
+
+    def bands(self):
+        lo, di, up, rhs = (np.empty(self.n) for _ in range(4))
+        check(self._lib.dzb_solver_bands(self._h, 0, lo.ctypes.data_as(_lib.c_double_p), di.ctypes.data_as(_lib.c_double_p),
+                                         up.ctypes.data_as(_lib.c_double_p), rhs.ctypes.data_as(_lib.c_double_p), self.n), self._lib)
+        return lo, di, up, rhs
+
+    def close(self):
+        if self._h:
+            self._lib.dzb_solver_destroy(self._h)
+            self._h = None
+        if self._mesh is not None:
+            self._mesh.close()
+            self._mesh = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def interface_solve(rows):
+    """rows [P, 8] (block r's s-row and e-row as (a, c, s, f)) -> ends [P, 2]; host side, long double (C ABI)"""
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 8)
+    ends = np.empty((rows.shape[0], 2))
+    check(lib.dzb_interface_solve(rows.ctypes.data_as(_lib.c_double_p), rows.shape[0], ends.ctypes.data_as(_lib.c_double_p)), lib)
+    return ends
+
+
+# ---------------------------------------------------------------------------------------------- the SPIKE driver
+def spike_solve(blocks, comm, refine_steps=0, solve_interface=interface_solve):
+    """Solves the bar whose consecutive row blocks are `blocks` on this process (one in production) and the other ranks
+    of `comm`.  Returns the list of this process' block solutions.  Exactly one all-gather of 8 doubles per block per
+    solve, plus one of 2 doubles per refinement sweep."""
+    k = len(blocks)
+    first_global = comm.rank * k  # every process owns the same number of consecutive blocks
+
+    def one_solve(which_rhs, accumulate):
+        rows = comm.all_gather(np.stack([b.block_reduce(which_rhs) for b in blocks]))
+        ends = solve_interface(rows)
+        for j, b in enumerate(blocks):
+            us, ue = ends[first_global + j]
+            b.block_backsolve(which_rhs, us, ue, accumulate)
+        return rows.shape[0]
+
+    total = one_solve(0, False)
+    for _ in range(int(refine_steps)):
+        edges = comm.all_gather(np.stack([b.block_edges() for b in blocks]))
+        for j, b in enumerate(blocks):
+            g = first_global + j
+            b.block_residual(edges[g - 1][1] if g > 0 else 0.0, edges[g + 1][0] if g + 1 < total else 0.0)
+        one_solve(1, True)
+    return [b.block_read() for b in blocks]
+
+
+class DistributedBarTimeIndependent:
+    """`DiffussionSolverTimeIndependent` (time_independent.rs:46-53) for one bar split across the ranks of `comm`.
+    `mesh` is the whole bar's node array (every rank slices its own block + halo from it) or, with `local=True`,
+    already this rank's `block_nodes`."""
+
+    def __init__(self, params, mesh, gauss_step, comm=None, options=None, refine_steps=0, blocks_per_process=1):
+        self.comm = comm if comm is not None else LocalComm()
+        mesh = np.asarray(mesh, dtype=np.float64)
+        total_blocks = self.comm.world * blocks_per_process
+        self.partition = partition_rows(len(mesh), total_blocks)
+        self.refine_steps = int(refine_steps)
+        self.blocks = []
+        for j in range(blocks_per_process):
+            first, last = self.partition[self.comm.rank * blocks_per_process + j]
+            nodes, hl, hr = block_nodes(mesh, first, last)
+            self.blocks.append(BarBlock(params, nodes, hl, hr, gauss_step, options))
+        self.rows = (self.partition[self.comm.rank * blocks_per_process][0],
+                     self.partition[(self.comm.rank + 1) * blocks_per_process - 1][1])
+
+    def solve(self, _time_step=0.0):
+        """nodal values of this process' rows [self.rows[0], self.rows[1])"""
+        return np.concatenate(spike_solve(self.blocks, self.comm, self.refine_steps))
+
+    def close(self):
+        for b in self.blocks:
+            b.close()
+        self.blocks = []

@@ -128,6 +128,24 @@ int dzb_solver_bands(const dzb_solver* s, int which, double* lo, double* di, dou
 int dzb_solver_state(const dzb_solver* s, double* out, size_t n);  /* `state` (time_dependent.rs:55) */
 void dzb_solver_destroy(dzb_solver* s);
 
+/* ---- one bar split across GPUs (SPIKE): every rank owns a contiguous block of rows ---------------------------- */
+/* DiffussionSolverTimeIndependent::new (time_independent.rs:57-71) for the rows of one block.  `m` holds the block's own
+ * nodes plus one halo node on each side that has a neighbour (has_left / has_right): assembly of an interior row needs
+ * x_{i-1}, x_i, x_{i+1} only.  The first block carries the left Dirichlet row, the last block the right one. */
+int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right, double mu, double b, double bc_left,
+                                  double bc_right, size_t gauss_step, const dzb_options* opt, dzb_solver** out);
+/* Eliminates everything inside the block; top8 = its two interface rows (a, c, s, f) x 2 in row-excess form
+ * (diagonal = s - a - c).  which_rhs: 0 = b_vector, 1 = the residual left by dzb_solver_block_residual. */
+int dzb_solver_block_reduce(dzb_solver* s, int which_rhs, double top8[8]);
+/* After the ranks exchanged their rows (ONE all-gather of 8 doubles per rank) and solved the interface system:
+ * back-substitute with this block's end unknowns; accumulate != 0 adds to the stored solution (refinement). */
+int dzb_solver_block_backsolve(dzb_solver* s, int which_rhs, double us, double ue, int accumulate);
+int dzb_solver_block_edges(const dzb_solver* s, double edges[2]);              /* first / last value of the block's solution */
+int dzb_solver_block_residual(dzb_solver* s, double u_left, double u_right);   /* r = b - K u (double-double) with halo values */
+int dzb_solver_block_read(const dzb_solver* s, double* out_host, size_t n);
+/* rows[8 r ..] = block r's top8; ends[2 r], ends[2 r + 1] = the values to hand to block r's back-substitution */
+int dzb_interface_solve(const double* rows, size_t n_blocks, double* ends);
+
 /* ---- ensembles: B independent time-dependent bars, one solve() each per step ------------------------------- */
 /* meshes: host, bar-major [n_bars][n]; initial_conditions: host, [n_bars][n-2] (n_ic = n-2 per bar). */
 int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double mu, double b, double bc_left,
