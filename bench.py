@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 100)")
     ap.add_argument("--cpu-sample-bars", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--assembly", default="auto", choices=["auto", "faithful", "fast"],
+                    help="c4: auto = the reference's arithmetic (bit-identical bands); fast = closed form (HBM-bound)")
     return ap.parse_args()
 
 
@@ -252,7 +254,9 @@ def main():
         params = dz.DiffussionParams.time_independent().mu(MU).b(BADV).boundary_conditions(*BC).build()
         dmesh = dz.Mesh.from_nodes(mesh)
         t0 = time.perf_counter()
-        solver = dz.DiffussionSolverTimeIndependent(params, dmesh, G)
+        amode = {"auto": dz.ASSEMBLY_AUTO, "faithful": dz.ASSEMBLY_FAITHFUL, "fast": dz.ASSEMBLY_FAST}[args.assembly]
+        solver = dz.DiffussionSolverTimeIndependent(params, dmesh, G, dz.make_options(amode, dz.SOLVE_AUTO))
+        extra["assembly"] = args.assembly
         dz.synchronize()
         extra["create_s"] = time.perf_counter() - t0
         dof = n

@@ -149,6 +149,61 @@ __device__ __forceinline__ void faithful_row(const double* __restrict__ mesh, lo
   }
 }
 
+// ---- FAITHFUL row, lean: the same operations in the same order, with everything that does not depend on the
+// quadrature node hoisted out of the loop.  Valid when every node image stays inside the element(s) it is meant for
+// (checked with the reference's own two-rounding predicate at the two extreme nodes; fl(fl(cs*x)+ms) is monotone in x),
+// so that the piecewise selects of `Hat::eval/deriv` are known per loop: then deriv() returns the piece's coefficient
+// exactly (0.0*x + c == c) and eval() is one `c*x + t`.  Bands are bit-identical to faithful_row<KIND_TI>; rows that fail
+// the check (degenerate or unsorted spacing) take the generic loop.  time_independent.rs:132-165.
+__device__ __forceinline__ bool faithful_row_lean_ti(const double* __restrict__ mesh, long long n, long long i,
+                                                     const double* __restrict__ qx, const double* __restrict__ qw, int m,
+                                                     const AsmParams& P, double out[7]) {
+  const double a = mesh[i - 1], c = mesh[i], e = mesh[i + 1];
+  const Affine tp = from_m1_p1(a, c), tn = from_m1_p1(c, e), ts = from_m1_p1(a, e);
+  bool ok = m > 0 && (a < c) && (c < e);
+  if (ok) {
+    const double x_hi = qx[0], x_lo = qx[m - 1];
+    ok = (tp(x_hi) < c) && !(tp(x_lo) < a) && (tn(x_hi) < e) && !(tn(x_lo) < c) && (ts(x_hi) < e) && !(ts(x_lo) < a);
+    if (i >= 2) ok = ok && !(a < mesh[i - 2]);
+    if (i + 2 < n) ok = ok && !(mesh[i + 2] < e);
+  }
+  if (!ok) return false;
+  const Affine phi1 = {1.0, 0.0}, phi2 = {-1.0, 1.0};
+  const Affine pl = compose(phi1, to_0_1(a, c));   // phi_i   on [a, c)
+  const Affine pr = compose(phi2, to_0_1(c, e));   // phi_i   on [c, e)
+  const Affine ql = compose(phi2, to_0_1(a, c));   // phi_i-1 on [a, c)
+  const Affine qr = compose(phi1, to_0_1(c, e));   // phi_i+1 on [c, e)
+  // (mu * phi_i' * phi_j') and (b * phi_j'), evaluated as the reference does for every node (same value every time)
+  const double k1p = P.mu * pl.c * ql.c, k2p = P.b * ql.c;
+  const double k1n = P.mu * pr.c * qr.c, k2n = P.b * qr.c;
+  const double k1l = P.mu * pl.c * pl.c, k2l = P.b * pl.c;
+  const double k1r = P.mu * pr.c * pr.c, k2r = P.b * pr.c;
+  int lo = 0, hi = m;  // first node whose image under t_square is left of the kink (x_j decreases with j)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ts(qx[mid]) < c) hi = mid; else lo = mid + 1;
+  }
+  const int split = lo;
+  double a_prev = 0.0, a_next = 0.0, a_sq = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < split; ++j) {  // t_square(x_j) in [c, e): right piece
+    const double x = qx[j], w = qw[j];
+    a_prev += (k1p + k2p * pl(tp(x))) * tp.c * w;
+    a_next += (k1n + k2n * pr(tn(x))) * tn.c * w;
+    a_sq += (k1r + k2r * pr(ts(x))) * ts.c * w;
+  }
+#pragma unroll 4
+  for (int j = split; j < m; ++j) {  // t_square(x_j) in [a, c): left piece
+    const double x = qx[j], w = qw[j];
+    a_prev += (k1p + k2p * pl(tp(x))) * tp.c * w;
+    a_next += (k1n + k2n * pr(tn(x))) * tn.c * w;
+    a_sq += (k1l + k2l * pl(ts(x))) * ts.c * w;
+  }
+  out[0] = a_prev, out[1] = a_sq, out[2] = a_next, out[3] = 0.0;
+  out[4] = out[5] = out[6] = 0.0;
+  return true;
+}
+
 // Stokes row 0 (dim1.rs:195-236)
 __device__ __forceinline__ void faithful_stokes_row0(const double* __restrict__ mesh, long long n,
                                                      const double* __restrict__ qx, const double* __restrict__ qw,
@@ -208,7 +263,7 @@ __global__ void __launch_bounds__(128) k_assemble_faithful(const double* __restr
     boundary_row<KIND>(i == 0, P, v);
   else if (i == 0)
     faithful_stokes_row0(bm, n, qx, qw, rule.m, P, force, n, v);
-  else
+  else if (KIND != KIND_TI || !faithful_row_lean_ti(bm, n, i, qx, qw, rule.m, P, v))
     faithful_row<KIND>(bm, n, i, qx, qw, rule.m, P, force ? force + i : nullptr, n, v);
   store_row<KIND>(o, g, v);
 }

@@ -39,7 +39,7 @@ typedef struct dzb_ensemble dzb_ensemble; /* many independent DiffussionSolverTi
 
 /* How the element integrals are evaluated on the device. */
 typedef enum dzb_assembly_mode {
-  DZB_ASSEMBLY_AUTO = 0,     /* FAITHFUL while nodes*gauss_step <= 2^24, FAST beyond */
+  DZB_ASSEMBLY_AUTO = 0,     /* static solvers: FAITHFUL (nodal parity on long bars needs the reference's bands bit for bit); time dependent: FAITHFUL while nodes*gauss_step <= 2^24, FAST beyond */
   DZB_ASSEMBLY_FAITHFUL = 1, /* the reference's quadrature loop, same operation order, no FMA: bands bit-identical to the reference arithmetic */
   DZB_ASSEMBLY_FAST = 2      /* closed form over prefix moments of the same rule (incl. the dropped node and the split at the kink): O(log G) per node, differs by rounding only */
 } dzb_assembly_mode;
