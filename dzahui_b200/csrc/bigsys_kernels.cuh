@@ -77,37 +77,45 @@ __device__ __forceinline__ int row_slot(int r, int rows, int P) {
 
 // One chunk (thread t of P) of a shared-memory level, reduced rows -> next level (PN chunks; PN == 0: the next level is
 // the final 2-row system stored at index 0/1).
-__device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
+template <bool FULL>  // FULL: len == 8, loops unrolled
+__device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
   const double A0 = lv.a[t], C0 = lv.c[t], S0 = lv.s[t], F0 = lv.d[t];
   int idx = P + t;
   double alpha = lv.a[idx], sigma = lv.s[idx], delta = lv.d[idx], gam = lv.c[idx];
   double sc = C0, ss = S0, sf = F0;  // s-row (its a stays A0)
-  if (len >= 3) {
+  if (FULL || len >= 3) {
     double r = __drcp_rn((sigma - alpha) - gam);
     lv.s[idx] = r;
     double Pr = -C0 * r;
     ss = fma(Pr, sigma, S0), sf = fma(Pr, delta, F0);
     double lastG = gam;
-    for (int j = 2; j < len; ++j) {
-      idx += P;
-      const double m = -lv.a[idx] * r;
-      alpha = m * alpha;
-      sigma = fma(m, sigma, lv.s[idx]);
-      delta = fma(m, delta, lv.d[idx]);
-      const double gprev = gam;
-      gam = lv.c[idx];
-      if (j < len - 1) {
-        r = __drcp_rn((sigma - alpha) - gam);
-        lv.a[idx] = alpha, lv.s[idx] = r, lv.d[idx] = delta;
-        Pr *= -gprev * r;
-        ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
+#pragma unroll
+    for (int j = 2; j < BS_R; ++j) {
+      if (FULL || j < len) {
+        idx += P;
+        const double m = -lv.a[idx] * r;
+        alpha = m * alpha;
+        sigma = fma(m, sigma, lv.s[idx]);
+        delta = fma(m, delta, lv.d[idx]);
+        const double gprev = gam;
+        gam = lv.c[idx];
+        if (FULL ? j < BS_R - 1 : j < len - 1) {
+          r = __drcp_rn((sigma - alpha) - gam);
+          lv.a[idx] = alpha, lv.s[idx] = r, lv.d[idx] = delta;
+          Pr *= -gprev * r;
+          ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
+        }
       }
     }
     sc = Pr * lastG;
   }
   nx.a[p0] = A0, nx.c[p0] = sc, nx.s[p0] = ss, nx.d[p0] = sf;
   nx.a[p1] = alpha, nx.c[p1] = gam, nx.s[p1] = sigma, nx.d[p1] = delta;
+}
+__device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
+  if (len == BS_R) level_reduce_impl<true>(lv, P, len, nx, PN, t);
+  else level_reduce_impl<false>(lv, P, len, nx, PN, t);
 }
 // Back-substitution of the same chunk: the next level's d[] holds the solved u_s / u_e; this level's d[] receives u.
 __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
@@ -116,10 +124,19 @@ __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int l
   lv.d[t] = us;
   lv.d[(len - 1) * P + t] = ue;
   double nxt = ue;
-  for (int j = len - 2; j >= 1; --j) {
-    const int idx = j * P + t;
-    nxt = fma(-lv.c[idx], nxt, fma(-lv.a[idx], us, lv.d[idx])) * lv.s[idx];
-    lv.d[idx] = nxt;
+  if (len == BS_R) {
+#pragma unroll
+    for (int j = BS_R - 2; j >= 1; --j) {
+      const int idx = j * P + t;
+      nxt = fma(-lv.c[idx], nxt, fma(-lv.a[idx], us, lv.d[idx])) * lv.s[idx];
+      lv.d[idx] = nxt;
+    }
+  } else {
+    for (int j = len - 2; j >= 1; --j) {
+      const int idx = j * P + t;
+      nxt = fma(-lv.c[idx], nxt, fma(-lv.a[idx], us, lv.d[idx])) * lv.s[idx];
+      lv.d[idx] = nxt;
+    }
   }
 }
 
@@ -171,6 +188,42 @@ struct Pyramid {
     __syncthreads();
   }
 };
+
+// Level 0: the forward sweep over a chunk held in registers; KEEP stores (alpha_j, 1/beta_j, delta_j) over
+// (A, S, F)[1..len-2] for the back-substitution.  FULL: len == 8.
+template <bool KEEP, bool FULL>
+__device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R],
+                                               int len, const LevelPtr& l1, int i0, int i1) {
+  double alpha = A[1], sigma = S[1], delta = F[1], gam = C[1];
+  double sc = C[0], ss = S[0], sf = F[0];
+  if (FULL || len >= 3) {
+    double r = __drcp_rn((sigma - alpha) - gam);
+    S[1] = r;
+    double Pr = -C[0] * r;
+    ss = fma(Pr, sigma, S[0]), sf = fma(Pr, delta, F[0]);
+    double lastG = gam;
+#pragma unroll
+    for (int j = 2; j < BS_R; ++j) {
+      if (FULL || j < len) {
+        const double mm = -A[j] * r;
+        alpha = mm * alpha;
+        sigma = fma(mm, sigma, S[j]);
+        delta = fma(mm, delta, F[j]);
+        const double gprev = gam;
+        gam = C[j];
+        if (FULL ? j < BS_R - 1 : j < len - 1) {
+          r = __drcp_rn((sigma - alpha) - gam);
+          if (KEEP) A[j] = alpha, S[j] = r, F[j] = delta;
+          Pr *= -gprev * r;
+          ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
+        }
+      }
+    }
+    sc = Pr * lastG;
+  }
+  l1.a[i0] = A[0], l1.c[i0] = sc, l1.s[i0] = ss, l1.d[i0] = sf;
+  l1.a[i1] = alpha, l1.c[i1] = gam, l1.s[i1] = sigma, l1.d[i1] = delta;
+}
 
 // ---- tile kernel --------------------------------------------------------------------------------------------------
 // SOLVE == false: forward sweeps, the tile's two reduced rows -> red_{a,c,s,f}[2 tile + {0,1}].
@@ -246,37 +299,8 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
     const int i0 = lvl_pos(2 * t, P1), i1 = lvl_pos(2 * t + 1, P1);
-    {
-      double alpha = A[1], sigma = S[1], delta = F[1], gam = C[1];
-      double sc = C[0], ss = S[0], sf = F[0];
-      if (len >= 3) {
-        double r = __drcp_rn((sigma - alpha) - gam);
-        S[1] = r;
-        double Pr = -C[0] * r;
-        ss = fma(Pr, sigma, S[0]), sf = fma(Pr, delta, F[0]);
-        double lastG = gam;
-#pragma unroll
-        for (int j = 2; j < BS_R; ++j) {
-          if (j < len) {
-            const double mm = -A[j] * r;
-            alpha = mm * alpha;
-            sigma = fma(mm, sigma, S[j]);
-            delta = fma(mm, delta, F[j]);
-            const double gprev = gam;
-            gam = C[j];
-            if (j < len - 1) {
-              r = __drcp_rn((sigma - alpha) - gam);
-              if (SOLVE) A[j] = alpha, S[j] = r, F[j] = delta;
-              Pr *= -gprev * r;
-              ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
-            }
-          }
-        }
-        sc = Pr * lastG;
-      }
-      l1.a[i0] = A[0], l1.c[i0] = sc, l1.s[i0] = ss, l1.d[i0] = sf;
-      l1.a[i1] = alpha, l1.c[i1] = gam, l1.s[i1] = sigma, l1.d[i1] = delta;
-    }
+    if (len == BS_R) chunk0_forward<SOLVE, true>(A, C, S, F, len, l1, i0, i1);
+    else chunk0_forward<SOLVE, false>(A, C, S, F, len, l1, i0, i1);
   }
   pyr.reduce(t, rows1);
   LevelPtr top = pyr.top();
