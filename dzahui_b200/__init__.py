@@ -9,6 +9,7 @@ from .errors import CudaError, Error, Integration, Invalid, Io, MeshParse, Piece
 from .mesh import Mesh, MeshBuilder
 from .params import (BuilderPanic, DiffussionParams, DiffussionParamsTimeDependent, DiffussionParamsTimeIndependent,
                      StaticPressureParams, StaticPressureParamsBuilder, StokesParams, StokesParams1D, StokesParams1DBuilder)
+from .writer import Writer, format_f64
 from .solvers import (ASSEMBLY_AUTO, ASSEMBLY_FAITHFUL, ASSEMBLY_FAST, SOLVE_AUTO, SOLVE_FAITHFUL, SOLVE_PARALLEL,
                       DiffEquationSolver, DiffussionSolverTimeDependent, DiffussionSolverTimeIndependent, NoSolver, Solver,
                       StaticPressureSolver, StokesSolver1D, TriDiag, make_options)

@@ -146,6 +146,15 @@ int dzb_solver_block_read(const dzb_solver* s, double* out_host, size_t n);
 /* rows[8 r ..] = block r's top8; ends[2 r], ends[2 r + 1] = the values to hand to block r's back-substitution */
 int dzb_interface_solve(const double* rows, size_t n_blocks, double* ends);
 
+/* ---- CSV snapshots: Writer (writer.rs:47-146), host code ------------------------------------------------------- */
+/* `f64::to_string()` of Rust: shortest round-trip digits, never an exponent, "1" for 1.0, "-0", "NaN", "inf". */
+int dzb_format_f64(double v, char* buf, size_t cap);
+/* Writer::new: DZB_IO unless `dir` exists; erase_prev_dir != 0 removes the plain files directly inside it. */
+int dzb_csv_prepare_dir(const char* dir, int erase_prev_dir);
+/* Writer::write: <dir>/<prefix><id>.csv, header = names joined by ',', then n_vars values per line. */
+int dzb_csv_write(const char* dir, const char* prefix, double id, const char* const* variable_names, size_t n_vars,
+                  const double* vals, size_t n_vals);
+
 /* ---- ensembles: B independent time-dependent bars, one solve() each per step ------------------------------- */
 /* meshes: host, bar-major [n_bars][n]; initial_conditions: host, [n_bars][n-2] (n_ic = n-2 per bar). */
 int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double mu, double b, double bc_left,

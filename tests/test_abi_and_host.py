@@ -136,3 +136,29 @@ def test_synthetic_workloads_are_deterministic(dz):
     assert ic.shape == (3, 1022)
     x = synthetic.regular_bar(11)
     assert x[0] == 0.0 and x[-1] == 1.0 and x[3] == 3 / 10
+
+
+def test_csv_writer_matches_rust_formatting(dz, tmp_path):
+    """Writer::write (writer.rs:99-146): header, one value per line for 1 variable, Rust Display for f64"""
+    cases = [(1.0, "1"), (-2.0, "-2"), (0.5, "0.5"), (0.1 + 0.2, "0.30000000000000004"), (1e21, "1000000000000000000000"),
+             (1e-7, "0.0000001"), (-0.0, "-0"), (0.0, "0"), (100.9937043619243, "100.9937043619243"),
+             (123456789.125, "123456789.125"), (5e-324, "0." + "0" * 323 + "5"), (float("inf"), "inf"), (float("-inf"), "-inf"),
+             (1.7976931348623157e308, "17976931348623157" + "0" * 292), (15.0, "15"),
+             (0.9485126528155906, "0.9485126528155906"), (2.5e-5, "0.000025"), (1234.5, "1234.5")]
+    for v, want in cases:
+        assert dz.format_f64(v) == want, (v, dz.format_f64(v))
+    assert dz.format_f64(float("nan")) == "NaN"
+    for v in np.random.default_rng(0).normal(size=200) * 10.0 ** np.random.default_rng(1).integers(-12, 12, 200):
+        s = dz.format_f64(v)
+        assert "e" not in s and float(s) == v                         # positional and round-trips
+    (tmp_path / "old.csv").write_text("x")
+    (tmp_path / "sub").mkdir()
+    w = dz.Writer(str(tmp_path), "pressure_", ["p"], erase_prev_dir=True)
+    assert not (tmp_path / "old.csv").exists() and (tmp_path / "sub").exists()
+    path = w.write(12.5, [109.96852572142232, 100.0, -0.0])
+    assert path.endswith("pressure_12.5.csv")
+    assert open(path).read() == "p\n109.96852572142232\n100\n-0\n"
+    w2 = dz.Writer(str(tmp_path), "v", ["v_x", "v_y"])
+    assert open(w2.write(3.0, [1.0, 2.0, 3.0, 4.0, 5.0])).read() == "v_x,v_y\n1,2\n3,4\n5\n"   # chunks(): short last line
+    with pytest.raises(dz.Io):
+        dz.Writer(str(tmp_path / "missing"), "a", ["p"])
