@@ -111,7 +111,7 @@ dzb_options resolve_options(const dzb_options* opt) {
 }
 bool options_valid(const dzb_options& o) {
   return o.assembly_mode >= 0 && o.assembly_mode <= 2 && o.solve_mode >= 0 && o.solve_mode <= 2 && o.refine_steps >= -1 &&
-         o.refine_steps <= 8;
+         o.refine_steps <= 8 && (o.reserved == 0 || o.reserved == 1);
 }
 
 // ---- assembly launcher -----------------------------------------------------------------------------------------
@@ -221,7 +221,8 @@ __global__ void k_gradient(const double* __restrict__ u, long long n, const doub
 struct dzb_mesh {
   size_t n = 0;
   bool from_obj = false;
-  std::vector<double> h_nodes;
+  std::vector<double> h_nodes;  // host copy of the coordinates (may be stale after dzb_mesh_set_nodes: see host_nodes())
+  bool h_stale = false;
   double* d_nodes = nullptr;
   double* d_vertices = nullptr;   // 12 n
   uint32_t* d_indices = nullptr;  // 6 n - 6
@@ -242,6 +243,11 @@ struct dzb_ensemble {
   double *mlo = nullptr, *mdi = nullptr, *mup = nullptr, *slo = nullptr, *sdi = nullptr, *sup = nullptr;  // natural [B][n]
   double *c = nullptr, *den = nullptr;                                                                     // natural [B][n]
   double *a_lo = nullptr, *a_di = nullptr, *a_up = nullptr, *alpha = nullptr, *cc = nullptr;               // interleaved [B][32 L]
+  double *bdi = nullptr, *idn = nullptr, *hh = nullptr;  // lean step: unscaled diagonal, 1/den, element lengths (interleaved)
+  int* d_bad = nullptr;
+  int lean_L = 0, lean_wpb = 1;  // rows per lane / warps per bar of the lean layout
+  bool lean_ok = false;   // the lean step applies (no row needed the quadrature-loop fallback); decided at prepare time
+  dzb::LeanConsts lean_k{};
   double* u[2] = {nullptr, nullptr};
   int cur = 0;
   bool prepared = false;
@@ -274,11 +280,24 @@ struct dzb_solver {
 
 namespace {
 
+int host_nodes(const dzb_mesh* cm, const std::vector<double>** out) {
+  dzb_mesh* m = const_cast<dzb_mesh*>(cm);
+  if (m->h_stale) {
+    m->h_nodes.resize(m->n);
+    CK(cudaMemcpyAsync(m->h_nodes.data(), m->d_nodes, m->n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    m->h_stale = false;
+  }
+  *out = &m->h_nodes;
+  return DZB_OK;
+}
+
 void ensemble_free(dzb_ensemble* e) {
   if (!e) return;
   for (double** p : {&e->d_mesh, &e->mlo, &e->mdi, &e->mup, &e->slo, &e->sdi, &e->sup, &e->c, &e->den, &e->a_lo, &e->a_di, &e->a_up,
-                     &e->alpha, &e->cc, &e->u[0], &e->u[1]})
+                     &e->alpha, &e->cc, &e->u[0], &e->u[1], &e->bdi, &e->idn, &e->hh})
     dfree(*p);
+  if (e->d_bad) cudaFree(e->d_bad), e->d_bad = nullptr;
   dzb::bigsys_free(&e->big);
   delete e;
 }
@@ -307,6 +326,33 @@ int launch_step_fast(dzb_ensemble* e) {
   LAUNCHED();
   return DZB_OK;
 }
+template <int L, int WPB>
+int launch_prepare_lean(dzb_ensemble* e, double dt, double x_hi, double x_lo) {
+  long long blocks = (long long)e->B;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  dzb::k_td_prepare_lean<L, WPB><<<(unsigned)blocks, 256, 0, g_stream>>>(e->d_mesh, e->mdi, e->sdi, e->den, e->bdi, e->idn, e->hh,
+                                                                         (int)e->n, (long long)e->B, dt, x_hi, x_lo, e->d_bad);
+  LAUNCHED();
+  return DZB_OK;
+}
+template <int L, int WPB>
+int launch_step_lean(dzb_ensemble* e) {
+  dzb::k_td_step_lean<L, WPB><<<(unsigned)e->B, 32 * WPB, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->bdi, e->idn, e->hh, (int)e->n,
+                                                                          e->bc0, e->bc1, e->lean_k);
+  LAUNCHED();
+  return DZB_OK;
+}
+// lean layout: one warp per bar up to 512 nodes, two warps (16 rows per lane) for 513..1024
+#define DISPATCH_LEAN(E_, FN, ...)                                \
+  switch ((E_)->lean_L * 8 + (E_)->lean_wpb) {                    \
+    case 1 * 8 + 1: rc = FN<1, 1>(__VA_ARGS__); break;            \
+    case 2 * 8 + 1: rc = FN<2, 1>(__VA_ARGS__); break;            \
+    case 4 * 8 + 1: rc = FN<4, 1>(__VA_ARGS__); break;            \
+    case 8 * 8 + 1: rc = FN<8, 1>(__VA_ARGS__); break;            \
+    case 16 * 8 + 1: rc = FN<16, 1>(__VA_ARGS__); break;          \
+    case 16 * 8 + 2: rc = FN<16, 2>(__VA_ARGS__); break;          \
+    default: rc = fail(DZB_INVALID, "bad lean layout");           \
+  }
 #define DISPATCH_L(L_, FN, ...)                  \
   switch (L_) {                                  \
     case 1: rc = FN<1>(__VA_ARGS__); break;      \
@@ -326,12 +372,39 @@ int ensemble_step_once(dzb_ensemble* e, double dt) {
     if (rc) return fail(DZB_CUDA, dzb::bigsys_error());
   } else if (e->fast) {
     if (!e->prepared || e->prepared_dt != dt) {
-      DISPATCH_L(e->L, launch_prepare, e, dt);
-      if (rc) return rc;
+      if (e->lean_ok) {  // operator rebuilt on chip from (h, 1/den, unscaled diagonal): 40 B per DOF-step
+        const size_t np = e->B * 32 * (size_t)e->lean_wpb * (size_t)e->lean_L;
+        for (double** p : {&e->bdi, &e->idn, &e->hh})
+          if (!*p && (rc = dalloc(p, np))) return rc;
+        if (!e->d_bad) CK(cudaMalloc((void**)&e->d_bad, sizeof(int)));
+        CK(cudaMemsetAsync(e->d_bad, 0, sizeof(int), g_stream));
+        dzb::QuadRule rule;
+        if (!dzb::gl_build_rule(e->G, &rule) || rule.m == 0) e->lean_ok = false;
+        else {
+          DISPATCH_LEAN(e, launch_prepare_lean, e, dt, rule.x[0], rule.x[rule.m - 1]);
+          if (rc) return rc;
+          int bad = 0;
+          CK(cudaMemcpyAsync(&bad, e->d_bad, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+          CK(cudaStreamSynchronize(g_stream));
+          if (bad) e->lean_ok = false;  // some row needed the quadrature-loop fallback: use the stored operators
+          e->lean_k = dzb::LeanConsts{dt * e->mu * rule.t0 / 2.0, rule.q / 8.0, dt * e->b * rule.t1p / 4.0, dt * e->b * rule.t1m / 4.0};
+        }
+      }
+      if (!e->lean_ok) {
+        const size_t np = e->B * 32 * (size_t)e->L;
+        for (double** p : {&e->a_lo, &e->a_di, &e->a_up, &e->alpha, &e->cc})
+          if (!*p && (rc = dalloc(p, np))) return rc;
+        DISPATCH_L(e->L, launch_prepare, e, dt);
+        if (rc) return rc;
+      }
       e->prepared = true;
       e->prepared_dt = dt;
     }
-    DISPATCH_L(e->L, launch_step_fast, e);
+    if (e->lean_ok) {
+      DISPATCH_LEAN(e, launch_step_lean, e);
+    } else {
+      DISPATCH_L(e->L, launch_step_fast, e);
+    }
     if (rc) return rc;
   } else {
     dzb::k_td_step_faithful<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->mlo, e->mdi, e->mup,
@@ -403,9 +476,10 @@ int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, 
     while ((size_t)32 * L < n) L <<= 1;
     e->L = L;
     e->fast = true;
-    const size_t np = B * 32 * (size_t)L;
-    for (double** p : {&e->a_lo, &e->a_di, &e->a_up, &e->alpha, &e->cc})
-      if ((rc = dalloc(p, np))) return bail(rc);
+    e->lean_ok = opt.reserved == 0;  // dzb_options.reserved = 1 keeps the pre-scaled operator arrays (k_td_step_fast)
+    e->lean_wpb = n > 512 ? 2 : 1;
+    e->lean_L = 1;
+    while ((size_t)32 * e->lean_wpb * e->lean_L < n) e->lean_L <<= 1;
   }
   if ((rc = ensemble_assemble(e))) return bail(rc);
   if (cudaStreamSynchronize(g_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
@@ -521,7 +595,7 @@ int dzb_mesh_set_nodes(dzb_mesh* m, const double* x, size_t n) {
   if (!m || !x) return fail(DZB_INVALID, "null pointer");
   if (n != m->n) return fail(DZB_WRONG_DIMS, "node count");
   if (m->from_obj) return fail(DZB_INVALID, "only meshes made by dzb_mesh_from_nodes can be re-pointed");
-  m->h_nodes.assign(x, x + n);
+  m->h_stale = true;  // refreshed from the device only if a later call needs host coordinates
   m->max_length = -x[0] + x[n - 1];
   CK(cudaMemcpyAsync(m->d_nodes, x, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   return sync_stream();
@@ -659,7 +733,9 @@ int dzb_stokes1d_create(const dzb_mesh* m, double rho, double pressure, double (
   // T(x) = ((end-beg)/2)*x + (end+beg)/2, two roundings (host code is built with -ffp-contract=off).
   const size_t mq = rule.m;
   std::vector<double> F(mq * n, 0.0);
-  const std::vector<double>& x = m->h_nodes;
+  const std::vector<double>* xp = nullptr;
+  if (int hrc = host_nodes(m, &xp)) return hrc;
+  const std::vector<double>& x = *xp;
   for (size_t i = 1; i + 1 < n; ++i) {
     const double cs = (x[i + 1] - x[i - 1]) / 2.0, ms = (x[i + 1] + x[i - 1]) / 2.0;
     for (size_t k = 0; k < mq; ++k) F[k * n + i] = force(cs * rule.x[k] + ms, ctx);
@@ -697,7 +773,9 @@ int dzb_diffusion_td_create(const dzb_mesh* m, double mu, double b, double bc_le
   if (!out || !m) return fail(DZB_INVALID, "null pointer");
   *out = nullptr;
   dzb_ensemble* e = nullptr;
-  int rc = ensemble_create_impl(m->h_nodes.data(), 1, m->n, mu, b, bc_left, bc_right, ic, n_ic, G, opt, &e);
+  const std::vector<double>* xp = nullptr;
+  if (int hrc = host_nodes(m, &xp)) return hrc;
+  int rc = ensemble_create_impl(xp->data(), 1, m->n, mu, b, bc_left, bc_right, ic, n_ic, G, opt, &e);
   if (rc) return rc;
   dzb_solver* s = new dzb_solver;
   s->kind = dzb::KIND_TD, s->n = m->n, s->td = e;

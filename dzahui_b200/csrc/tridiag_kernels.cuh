@@ -254,4 +254,192 @@ __global__ void __launch_bounds__(32 * WARPS) k_td_step_fast(const double* __res
   }
 }
 
+// ---- LEAN step: the same algorithm with the operator rebuilt on chip ---------------------------------------------
+// For linear hats the off-diagonal entries of M and S depend on ONE number per element, its length h:
+//     M_lo,r = M_up,r-1 = h q / 8,        S_lo,r = mu t0 / (2 h) + b t1p / 4,     S_up,r-1 = mu t0 / (2 h) - b t1m / 4
+// (q = sum w (1 - x^2), t0 = sum w, t1p/m = sum w (1 +- x) over the rule's used nodes; closed form of
+// time_dependent.rs:180-233, see fast_row in assembly_kernels.cuh).  So instead of five pre-scaled operator arrays
+// (40 B per row and step) the kernel streams three: h, 1/den and the unscaled diagonal dt S_di + M_di (24 B), and forms
+//     A'_lo = (dt S_lo + M_lo)/den,  A'_up = (dt S_up + M_up)/den,  alpha = -M_lo/den,  c = M_up/den
+// in registers: one reciprocal and a dozen flops per row on an fp64 pipe that is ~6 % busy in k_td_step_fast.
+// HBM traffic 40 B per DOF-step instead of 56.  Rows 0 and n-1 are identity rows (time_dependent.rs:236-239).
+// Valid while every interior row passes fast_row's interval checks; k_td_prepare_lean verifies that and raises *bad.
+template <int L, int WPB>
+__global__ void __launch_bounds__(256) k_td_prepare_lean(const double* __restrict__ mesh, const double* __restrict__ mdi,
+                                                         const double* __restrict__ sdi, const double* __restrict__ den,
+                                                         double* __restrict__ bdi, double* __restrict__ idn,
+                                                         double* __restrict__ hh, int n, long long n_bars, double dt,
+                                                         double x_hi, double x_lo, int* __restrict__ bad) {
+  constexpr int LANES = 32 * WPB;  // lanes that share one bar; lane g owns rows g L .. g L + L - 1
+  constexpr int NP = LANES * L;
+  constexpr int SP = NP + NP / 32;
+  __shared__ double sm[3][SP];
+  for (long long bar = blockIdx.x; bar < n_bars; bar += gridDim.x) {
+    const long long o = bar * (long long)n;
+    for (int r = threadIdx.x; r < NP; r += blockDim.x) {
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      if (r < n) {
+        v0 = dt * sdi[o + r] + mdi[o + r];
+        v1 = 1.0 / den[o + r];
+        if (r + 1 < n) v2 = mesh[o + r + 1] - mesh[o + r];
+        if (r >= 1 && r + 1 < n) {  // the interval checks of fast_row (assembly_kernels.cuh)
+          const double a = mesh[o + r - 1], c = mesh[o + r], e = mesh[o + r + 1];
+          const double cp = (c - a) / 2.0, mp = (c + a) / 2.0, cn = (e - c) / 2.0, mn = (e + c) / 2.0, cs = (e - a) / 2.0,
+                       ms = (e + a) / 2.0;
+          bool ok = (a < c) && (c < e);
+          ok = ok && (cp * x_hi + mp < c) && !(cp * x_lo + mp < a) && (cn * x_hi + mn < e) && !(cn * x_lo + mn < c) &&
+               (cs * x_hi + ms < e) && !(cs * x_lo + ms < a);
+          if (r >= 2) ok = ok && !(a < mesh[o + r - 2]);
+          if (r + 2 < n) ok = ok && !(mesh[o + r + 2] < e);
+          if (!ok) *bad = 1;
+        }
+      }
+      const int p = (r % L) * LANES + r / L;
+      const int q = p + p / 32;
+      sm[0][q] = v0, sm[1][q] = v1, sm[2][q] = v2;
+    }
+    __syncthreads();
+    const long long oo = bar * (long long)NP;
+    for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+      const int q = p + p / 32;
+      bdi[oo + p] = sm[0][q], idn[oo + p] = sm[1][q], hh[oo + p] = sm[2][q];
+    }
+    __syncthreads();
+  }
+}
+
+struct LeanConsts {
+  double dtmu;  // dt * mu * t0 / 2
+  double q8;    // q / 8
+  double kp;    // dt * b * t1p / 4
+  double km;    // dt * b * t1m / 4
+};
+
+// One CTA of WPB warps per bar, lane g owns L consecutive rows (n <= 32 WPB L).  All three operator streams are
+// loaded into registers before any arithmetic (3 L independent coalesced loads in flight per lane); as row j's
+// (1/den, diagonal) die, its (alpha, beta) take their registers, so the recurrence state stays in the register file.
+// Two warps per 1024-node bar (L = 16) instead of one (L = 32) halves the registers per thread and doubles the warps
+// an SM keeps in flight.  The 32 WPB affine maps are scanned with warp shuffles plus one shared-memory hop per warp.
+template <int L, int WPB>
+__global__ void __launch_bounds__(32 * WPB) k_td_step_lean(const double* __restrict__ u_old, double* __restrict__ u_new,
+                                                           const double* __restrict__ bdi, const double* __restrict__ idn,
+                                                           const double* __restrict__ hh, int n, double bc0, double bc1,
+                                                           LeanConsts K) {
+  constexpr int LANES = 32 * WPB;
+  constexpr int NP = LANES * L;
+  constexpr int SW = NP + LANES + 2;  // one pad per chunk (r + r/L), +1 guard on each side
+  __shared__ double s_u[SW];
+  __shared__ double xh[WPB], fe[WPB], fp[WPB], ge[WPB], gp[WPB];  // cross-warp hand-overs
+  const int g = threadIdx.x, lane = g & 31, w = g >> 5;
+  const long long bar = blockIdx.x;
+  double* su = s_u + 1;  // su[-1] and su[pad(NP-1)+1] are the zero guards
+
+  const long long ob = bar * (long long)NP + g;
+  double cc[L], al[L], be[L];  // cc: h, then c_r = M_up/den;  al: 1/den, then alpha;  be: diagonal, then beta, d, s
+#pragma unroll
+  for (int j = 0; j < L; ++j) cc[j] = __ldcs(hh + ob + j * LANES);
+#pragma unroll
+  for (int j = 0; j < L; ++j) al[j] = __ldcs(idn + ob + j * LANES);
+#pragma unroll
+  for (int j = 0; j < L; ++j) be[j] = __ldcs(bdi + ob + j * LANES);
+
+  const double* ub = u_old + bar * (long long)n;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const int r = k * LANES + g;
+    su[r + r / L] = r < n ? __ldcs(ub + r) : 0.0;
+  }
+  if (g == 0) su[-1] = 0.0, su[NP + LANES] = 0.0;
+  if (WPB > 1 && lane == 31) xh[w] = cc[L - 1];
+  if (WPB > 1) __syncthreads(); else __syncwarp();
+
+  const int r0 = g * L, s0 = r0 + g;  // my first row and its padded position
+  {
+    double um = g == 0 ? 0.0 : su[(r0 - 1) + (r0 - 1) / L];
+    double u0 = su[s0];
+    double hl = shfl_up_d(cc[L - 1], 1);  // element to the left of my first row
+    if (WPB > 1 && lane == 0 && w > 0) hl = xh[w - 1];
+    if (g == 0 || hl == 0.0) hl = 1.0;    // no such element (row 0, padding): its coupling is cut below
+    double ml = hl * K.q8;
+    double El = fma(K.dtmu, __drcp_rn(hl), ml);
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const int r = r0 + j, rn = r + 1;
+      const double up1 = (j == L - 1) ? (g == LANES - 1 ? 0.0 : su[rn + rn / L]) : su[rn + g];
+      const bool interior = r >= 1 && r <= n - 2;
+      const double hr = r <= n - 2 ? cc[j] : 1.0;  // element to the right of row r (row 0 hands it on to row 1)
+      const double mr = hr * K.q8;
+      const double Er = fma(K.dtmu, __drcp_rn(hr), mr);
+      const double blo = interior ? El + K.kp : 0.0, bup = interior ? Er - K.km : 0.0;
+      const double id = al[j];
+      be[j] = fma(bup, up1, fma(be[j], u0, blo * um)) * id;
+      al[j] = interior ? -ml * id : 0.0;
+      cc[j] = interior ? mr * id : 0.0;
+      um = u0, u0 = up1, ml = mr, El = Er;
+    }
+  }
+
+  // forward: chunk-local sweep from a zero carry, scan of the affine maps over all lanes of the bar, sweep with the carry
+  {
+    double e = 0.0, p = 1.0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) e = fma(al[j], e, be[j]), p *= al[j];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double pe = shfl_up_d(e, d), pp = shfl_up_d(p, d);
+      if (lane >= d) e = fma(p, pe, e), p *= pp;
+    }
+    double carry = shfl_up_d(e, 1);
+    if (lane == 0) carry = 0.0;
+    if (WPB > 1) {
+      if (lane == 31) fe[w] = e, fp[w] = p;
+      __syncthreads();
+      double E = 0.0;  // value entering this warp = composition of the earlier warps applied to 0
+      for (int v = 0; v < w; ++v) E = fma(fp[v], E, fe[v]);
+      const double pin = shfl_up_d(p, 1);  // product of the maps of the earlier lanes of this warp
+      carry = lane == 0 ? E : fma(pin, E, carry);
+    }
+#pragma unroll
+    for (int j = 0; j < L; ++j) carry = fma(al[j], carry, be[j]), be[j] = carry;  // d
+  }
+
+  // backward: s_r = d_r - c_r s_{r+1}; the result goes straight into the transpose buffer
+  {
+    double e = 0.0, p = 1.0;
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) e = fma(-cc[j], e, be[j]), p *= -cc[j];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double pe = shfl_down_d(e, d), pp = shfl_down_d(p, d);
+      if (lane + d < 32) e = fma(p, pe, e), p *= pp;
+    }
+    double carry = shfl_down_d(e, 1);
+    if (lane == 31) carry = 0.0;
+    if (WPB > 1) {
+      if (lane == 0) ge[w] = e, gp[w] = p;
+      __syncthreads();
+      double E = 0.0;  // value entering this warp from the later warps
+      for (int v = WPB - 1; v > w; --v) E = fma(gp[v], E, ge[v]);
+      const double pin = shfl_down_d(p, 1);
+      carry = lane == 31 ? E : fma(pin, E, carry);
+    } else {
+      __syncwarp();  // every lane is done reading u
+    }
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) carry = fma(-cc[j], carry, be[j]), su[s0 + j] = carry;
+  }
+  if (WPB > 1) __syncthreads(); else __syncwarp();
+  double* un = u_new + bar * (long long)n;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const int r = k * LANES + g;
+    if (r < n) {
+      double v = su[r + r / L];
+      if (r == 0) v = bc0;
+      if (r == n - 1) v = bc1;
+      __stcs(un + r, v);
+    }
+  }
+}
+
 }  // namespace dzb

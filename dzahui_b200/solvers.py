@@ -18,8 +18,10 @@ ASSEMBLY_AUTO, ASSEMBLY_FAITHFUL, ASSEMBLY_FAST = 0, 1, 2
 SOLVE_AUTO, SOLVE_FAITHFUL, SOLVE_PARALLEL = 0, 1, 2
 
 
-def make_options(assembly_mode=ASSEMBLY_AUTO, solve_mode=SOLVE_AUTO, refine_steps=-1):
-    return _lib.Options(int(assembly_mode), int(solve_mode), int(refine_steps), 0)
+def make_options(assembly_mode=ASSEMBLY_AUTO, solve_mode=SOLVE_AUTO, refine_steps=-1, stored_operators=False):
+    """stored_operators: ensembles step from pre-scaled operator arrays (56 B per DOF-step) instead of rebuilding the
+    operator on chip (40 B)"""
+    return _lib.Options(int(assembly_mode), int(solve_mode), int(refine_steps), 1 if stored_operators else 0)
 
 
 def _as_mesh(mesh):

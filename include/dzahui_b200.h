@@ -55,7 +55,7 @@ typedef struct dzb_options {
   int assembly_mode; /* dzb_assembly_mode */
   int solve_mode;    /* dzb_solve_mode */
   int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto: 0 up to 2^22 rows, 1 beyond) */
-  int reserved;
+  int reserved;      /* ensembles, PARALLEL mode: 0 = operator rebuilt on chip (k_td_step_lean, 40 B per DOF-step), 1 = pre-scaled operator arrays (k_td_step_fast, 56 B) */
 } dzb_options;
 
 /* ---- library / device ------------------------------------------------------------------------------------ */
