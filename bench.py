@@ -28,7 +28,7 @@ METRIC = "FEM DOF-steps/sec (assemble+tridiag solve)"
 UNIT = "DOF-steps/s"
 MU, BADV, BC, G = 1.0, 1.0, (1.0, 15.0), 150
 C5_N, C5_DT = 1024, 1e-8
-ALG_BYTES_TD_STEP = 64       # u in/out 16 B + 3 M bands + 3 S bands 48 B per DOF-step
+ALG_BYTES_TD_STEP = 64       # u in/out 16 B + 3 M bands + 3 S bands 48 B per DOF-step; k_td_step_lean moves 40
 ALG_BYTES_STATIC = 80        # assembly 40 B/DOF + solve 40 B/DOF
 
 
@@ -248,7 +248,7 @@ def main():
         host_out = torch.empty(dof, dtype=torch.float64, pin_memory=True)
         step_e2e = lambda: solver.solve_into(C5_DT, host_out.data_ptr())
         alg_bytes = ALG_BYTES_TD_STEP * dof
-        kernel = "k_td_step_fast<32,4>" if args.stored_operators else "k_td_step_lean<32,4>"
+        kernel = "k_td_step_fast<32,4>" if args.stored_operators else "k_td_step_lean<16,2>"
         workload = c5_workload(B)
         d2h = dof * 8
     else:
@@ -317,6 +317,11 @@ def main():
         extra["e2e_including_create"] = {"value": dof * world * e2e_steps / (e2e_s + extra["create_s"]), "unit": UNIT,
                                          "steps": e2e_steps, "create_s": extra["create_s"]}
 
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+    # (profiles/r01_c5_td_step_lean_full.txt), per launch; None where no capture of this exact kernel/size exists
+    traffic = None
+    if args.workload == "c5" and args.bars == 65536:
+        traffic = 3.735e9 if args.stored_operators else 2.655e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -331,15 +336,16 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src},
+                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src},
         "extra": extra,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         if args.workload == "c5":
-            v_all, t_all = cpu_td_sample(args.cpu_sample_bars, 40, threads)
-            v_one, _ = cpu_td_sample(max(args.cpu_sample_bars // 8, 64), 40, 1)
-            sample = f"{args.cpu_sample_bars} of {B} bars x {n} nodes, 40 solve(dt) ({t_all:.1f} s); 1-thread figure on {max(args.cpu_sample_bars // 8, 64)} bars"
+            v_all, t_all = cpu_td_sample(args.cpu_sample_bars, 2000, threads)
+            v_one, t_one = cpu_td_sample(max(args.cpu_sample_bars // 8, 64), 1000, 1)
+            sample = (f"{args.cpu_sample_bars} of {B} bars x {n} nodes, 2000 solve(dt) on {threads} threads ({t_all:.1f} s); "
+                      f"1-thread figure: {max(args.cpu_sample_bars // 8, 64)} bars, 1000 solve(dt) ({t_one:.1f} s)")
         else:
             nn = min(n, 1_000_000)
             v_all, t_all = cpu_static_sample(nn, threads)
