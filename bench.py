@@ -248,7 +248,7 @@ def main():
         host_out = torch.empty(dof, dtype=torch.float64, pin_memory=True)
         step_e2e = lambda: solver.solve_into(C5_DT, host_out.data_ptr())
         alg_bytes = ALG_BYTES_TD_STEP * dof
-        kernel = "k_td_step_fast<32,4>" if args.stored_operators else "k_td_step_lean<16,2>"
+        kernel = "k_td_step_fast<32,4>" if args.stored_operators else "k_td_step_lean<8,4>"
         workload = c5_workload(B)
         d2h = dof * 8
     else:

@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -342,14 +343,15 @@ int launch_step_lean(dzb_ensemble* e) {
   LAUNCHED();
   return DZB_OK;
 }
-// lean layout: one warp per bar up to 512 nodes, two warps (16 rows per lane) for 513..1024
+// lean layout: (rows per lane, warps per bar)
 #define DISPATCH_LEAN(E_, FN, ...)                                \
   switch ((E_)->lean_L * 8 + (E_)->lean_wpb) {                    \
     case 1 * 8 + 1: rc = FN<1, 1>(__VA_ARGS__); break;            \
     case 2 * 8 + 1: rc = FN<2, 1>(__VA_ARGS__); break;            \
     case 4 * 8 + 1: rc = FN<4, 1>(__VA_ARGS__); break;            \
     case 8 * 8 + 1: rc = FN<8, 1>(__VA_ARGS__); break;            \
-    case 16 * 8 + 1: rc = FN<16, 1>(__VA_ARGS__); break;          \
+    case 8 * 8 + 2: rc = FN<8, 2>(__VA_ARGS__); break;            \
+    case 8 * 8 + 4: rc = FN<8, 4>(__VA_ARGS__); break;            \
     case 16 * 8 + 2: rc = FN<16, 2>(__VA_ARGS__); break;          \
     default: rc = fail(DZB_INVALID, "bad lean layout");           \
   }
@@ -477,7 +479,11 @@ int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, 
     e->L = L;
     e->fast = true;
     e->lean_ok = opt.reserved == 0;  // dzb_options.reserved = 1 keeps the pre-scaled operator arrays (k_td_step_fast)
-    e->lean_wpb = n > 512 ? 2 : 1;
+    // at most 8 rows per lane (~100 registers): 1 warp per bar up to 256 nodes, 2 up to 512, 4 up to 1024
+    e->lean_wpb = n > 512 ? 4 : (n > 256 ? 2 : 1);
+    if (const char* w = std::getenv("DZB_LEAN_WPB")) {  // tuning knob: 2 warps x 16 rows for 513..1024 nodes
+      if (std::atoi(w) == 2 && n > 512) e->lean_wpb = 2;
+    }
     e->lean_L = 1;
     while ((size_t)32 * e->lean_wpb * e->lean_L < n) e->lean_L <<= 1;
   }
