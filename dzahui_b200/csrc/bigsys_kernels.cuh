@@ -20,13 +20,17 @@
 // where the reference's own f64 Thomas is at 2.6e-7 (tests/test_gpu_parity.py).
 // Pivoting: none, like the reference.  The Stokes matrix (cancelling ~0 diagonal) stays on the serial kernel.
 //
-// One chunk, rows j = 0..7 (row 0 = s, row 7 = e), forward sweep only:
-//     alpha_j = m alpha_{j-1},  sigma_j = S_j + m sigma_{j-1},  delta_j = F_j + m delta_{j-1},  m = -A_j / beta_{j-1},
-//     beta_j  = sigma_j - alpha_j - C_j                      (row j:  alpha_j u_s + beta_j u_j + C_j u_{j+1} = delta_j)
-//   e-row = (alpha_7, C_7, sigma_7, delta_7);  the s-row needs rows 1..6 folded back into row 0, which is accumulated on
-//   the way with the running product P_j = (-C_0/beta_1) prod_{k<j} (-C_k/beta_{k+1}):
-//   s-row = (A_0, P_6 C_6, S_0 + sum_j P_j sigma_j, F_0 + sum_j P_j delta_j).
-//   Once u_s, u_e are known: u_j = (delta_j - alpha_j u_s - C_j u_{j+1}) / beta_j, j = 6..1.
+// One chunk, rows j = 0..7 (row 0 = s, row 7 = e), ONE forward sweep, and no division on its critical path: instead of
+// the pivots beta_j the sweep carries the leading minors P_j = beta_1 ... beta_j (three-term recurrence) and rows scaled
+// by P_{j-1},
+//     sigma~_j = S_j P_{j-1} - A_j sigma~_{j-1},   alpha~_j = -A_j alpha~_{j-1},   delta~_j = F_j P_{j-1} - A_j delta~_{j-1},
+//     g~_j = C_j P_{j-1},   P_j = sigma~_j - alpha~_j - g~_j          (row j:  alpha~_j u_s + P_j u_j + g~_j u_{j+1} = delta~_j)
+// so a step is 3 dependent fp64 operations instead of ~14 (the reciprocals 1/P_j are off the chain and pipeline).  The
+// chunk is first scaled by the power of two nearest 1/beta_1, which keeps P_j ~ O(1) for any magnitude of the entries.
+//   e-row = (alpha~_7, g~_7, sigma~_7, delta~_7) / P_6;  the s-row needs rows 1..6 folded back into row 0, accumulated on
+//   the way with G_j = (-C_0)(-C_1)...(-C_{j-1}):  s-row = (A_0, G_6 C_6 / P_6, S_0 + sum_j G_j sigma~_j / (P_j P_{j-1}),
+//   F_0 + sum_j G_j delta~_j / (P_j P_{j-1})).   For an M-matrix every term of every sum has the same sign.
+//   Once u_s, u_e are known: u_j = (delta~_j - alpha~_j u_s - g~_j u_{j+1}) / P_j, j = 6..1.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -51,6 +55,12 @@ __device__ __forceinline__ double excess3(double lo, double di, double up) {
   const double s1 = lo + up, b1 = s1 - lo, e1 = (lo - (s1 - b1)) + (up - b1);
   const double s2 = s1 + di, b2 = s2 - s1, e2 = (s1 - (s2 - b2)) + (di - b2);
   return s2 + (e1 + e2);
+}
+
+// 2^-e for x = 1.f * 2^e (1 for zero, subnormal, inf, nan): an exact row scaling
+__device__ __forceinline__ double pow2_inv(double x) {
+  const int E = (__double2hiint(x) >> 20) & 0x7ff;
+  return (E == 0 || E == 0x7ff) ? 1.0 : __hiloint2double((2046 - E) << 20, 0);
 }
 
 // Shared-memory level: 8*P rows, SoA, row r of the level at (r % 8) * P + r / 8.
@@ -80,38 +90,46 @@ __device__ __forceinline__ int row_slot(int r, int rows, int P) {
 template <bool FULL>  // FULL: len == 8, loops unrolled
 __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
-  const double A0 = lv.a[t], C0 = lv.c[t], S0 = lv.s[t], F0 = lv.d[t];
   int idx = P + t;
-  double alpha = lv.a[idx], sigma = lv.s[idx], delta = lv.d[idx], gam = lv.c[idx];
-  double sc = C0, ss = S0, sf = F0;  // s-row (its a stays A0)
+  double alp = lv.a[idx], sig = lv.s[idx], dlt = lv.d[idx], g = lv.c[idx];
+  const double sc = (FULL || len >= 3) ? pow2_inv((sig - alp) - g) : 1.0;
+  const double A0 = lv.a[t] * sc, C0 = lv.c[t] * sc, S0 = lv.s[t] * sc, F0 = lv.d[t] * sc;
+  alp *= sc, sig *= sc, dlt *= sc, g *= sc;
+  double s_c = C0, s_s = S0, s_f = F0;  // s-row (its a stays A0)
+  double rn = 1.0;                      // normalisation of the e-row
   if (FULL || len >= 3) {
-    double r = __drcp_rn((sigma - alpha) - gam);
-    lv.s[idx] = r;
-    double Pr = -C0 * r;
-    ss = fma(Pr, sigma, S0), sf = fma(Pr, delta, F0);
-    double lastG = gam;
+    double Pm = (sig - alp) - g;        // P_1
+    double rP = __drcp_rn(Pm);
+    lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rP, lv.d[idx] = dlt;
+    double G = -C0;
+    s_s = fma(G * rP, sig, S0), s_f = fma(G * rP, dlt, F0);
+    double lastC = g, Cprev = g;
 #pragma unroll
     for (int j = 2; j < BS_R; ++j) {
       if (FULL || j < len) {
         idx += P;
-        const double m = -lv.a[idx] * r;
-        alpha = m * alpha;
-        sigma = fma(m, sigma, lv.s[idx]);
-        delta = fma(m, delta, lv.d[idx]);
-        const double gprev = gam;
-        gam = lv.c[idx];
+        const double Aj = lv.a[idx] * sc, Cj = lv.c[idx] * sc;
+        sig = fma(lv.s[idx] * sc, Pm, -Aj * sig);
+        dlt = fma(lv.d[idx] * sc, Pm, -Aj * dlt);
+        alp = -Aj * alp;
+        g = Cj * Pm;
         if (FULL ? j < BS_R - 1 : j < len - 1) {
-          r = __drcp_rn((sigma - alpha) - gam);
-          lv.a[idx] = alpha, lv.s[idx] = r, lv.d[idx] = delta;
-          Pr *= -gprev * r;
-          ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
+          Pm = (sig - alp) - g;
+          const double rPn = __drcp_rn(Pm);
+          lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rPn, lv.d[idx] = dlt;
+          G *= -Cprev;
+          const double w = G * rPn * rP;
+          s_s = fma(w, sig, s_s), s_f = fma(w, dlt, s_f);
+          lastC = Cj, rP = rPn;
         }
+        Cprev = Cj;
       }
     }
-    sc = Pr * lastG;
+    s_c = G * lastC * rP;
+    rn = rP;
   }
-  nx.a[p0] = A0, nx.c[p0] = sc, nx.s[p0] = ss, nx.d[p0] = sf;
-  nx.a[p1] = alpha, nx.c[p1] = gam, nx.s[p1] = sigma, nx.d[p1] = delta;
+  nx.a[p0] = A0, nx.c[p0] = s_c, nx.s[p0] = s_s, nx.d[p0] = s_f;
+  nx.a[p1] = alp * rn, nx.c[p1] = g * rn, nx.s[p1] = sig * rn, nx.d[p1] = dlt * rn;
 }
 __device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
   if (len == BS_R) level_reduce_impl<true>(lv, P, len, nx, PN, t);
@@ -189,40 +207,49 @@ struct Pyramid {
   }
 };
 
-// Level 0: the forward sweep over a chunk held in registers; KEEP stores (alpha_j, 1/beta_j, delta_j) over
-// (A, S, F)[1..len-2] for the back-substitution.  FULL: len == 8.
+// Level 0: the forward sweep over a chunk held in registers; KEEP stores (alpha~_j, g~_j, 1/P_j, delta~_j) over
+// (A, C, S, F)[1..len-2] for the back-substitution.  FULL: len == 8.
 template <bool KEEP, bool FULL>
 __device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R],
                                                int len, const LevelPtr& l1, int i0, int i1) {
-  double alpha = A[1], sigma = S[1], delta = F[1], gam = C[1];
-  double sc = C[0], ss = S[0], sf = F[0];
+  double alp = A[1], sig = S[1], dlt = F[1], g = C[1];
+  const double sc = (FULL || len >= 3) ? pow2_inv((sig - alp) - g) : 1.0;
+  const double A0 = A[0] * sc, C0 = C[0] * sc, S0 = S[0] * sc, F0 = F[0] * sc;
+  alp *= sc, sig *= sc, dlt *= sc, g *= sc;
+  double s_c = C0, s_s = S0, s_f = F0;
+  double rn = 1.0;
   if (FULL || len >= 3) {
-    double r = __drcp_rn((sigma - alpha) - gam);
-    S[1] = r;
-    double Pr = -C[0] * r;
-    ss = fma(Pr, sigma, S[0]), sf = fma(Pr, delta, F[0]);
-    double lastG = gam;
+    double Pm = (sig - alp) - g;  // P_1
+    double rP = __drcp_rn(Pm);
+    if (KEEP) A[1] = alp, C[1] = g, S[1] = rP, F[1] = dlt;
+    double G = -C0;
+    s_s = fma(G * rP, sig, S0), s_f = fma(G * rP, dlt, F0);
+    double lastC = g, Cprev = g;
 #pragma unroll
     for (int j = 2; j < BS_R; ++j) {
       if (FULL || j < len) {
-        const double mm = -A[j] * r;
-        alpha = mm * alpha;
-        sigma = fma(mm, sigma, S[j]);
-        delta = fma(mm, delta, F[j]);
-        const double gprev = gam;
-        gam = C[j];
+        const double Aj = A[j] * sc, Cj = C[j] * sc;
+        sig = fma(S[j] * sc, Pm, -Aj * sig);
+        dlt = fma(F[j] * sc, Pm, -Aj * dlt);
+        alp = -Aj * alp;
+        g = Cj * Pm;
         if (FULL ? j < BS_R - 1 : j < len - 1) {
-          r = __drcp_rn((sigma - alpha) - gam);
-          if (KEEP) A[j] = alpha, S[j] = r, F[j] = delta;
-          Pr *= -gprev * r;
-          ss = fma(Pr, sigma, ss), sf = fma(Pr, delta, sf), lastG = gam;
+          Pm = (sig - alp) - g;
+          const double rPn = __drcp_rn(Pm);
+          if (KEEP) A[j] = alp, C[j] = g, S[j] = rPn, F[j] = dlt;
+          G *= -Cprev;
+          const double w = G * rPn * rP;
+          s_s = fma(w, sig, s_s), s_f = fma(w, dlt, s_f);
+          lastC = Cj, rP = rPn;
         }
+        Cprev = Cj;
       }
     }
-    sc = Pr * lastG;
+    s_c = G * lastC * rP;
+    rn = rP;
   }
-  l1.a[i0] = A[0], l1.c[i0] = sc, l1.s[i0] = ss, l1.d[i0] = sf;
-  l1.a[i1] = alpha, l1.c[i1] = gam, l1.s[i1] = sigma, l1.d[i1] = delta;
+  l1.a[i0] = A0, l1.c[i0] = s_c, l1.s[i0] = s_s, l1.d[i0] = s_f;
+  l1.a[i1] = alp * rn, l1.c[i1] = g * rn, l1.s[i1] = sig * rn, l1.d[i1] = dlt * rn;
 }
 
 // ---- tile kernel --------------------------------------------------------------------------------------------------
@@ -287,8 +314,7 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
   if (g0 == 0 && len > 0 && !(flags & BS_OPEN_LEFT)) A[0] = 0.0;
   if (!(flags & BS_OPEN_RIGHT) && len > 0 && g0 + len == m) {
 #pragma unroll
-    for (int j = 0; j < BS_R; ++j)
-      if (j == len - 1) C[j] = 0.0;
+    for (int j = 0; j < BS_R; ++j) C[j] = (g0 + j == m - 1) ? 0.0 : C[j];  // selects, not a dynamically indexed store
   }
   if (SRC == BS_SRC_BANDS) {
 #pragma unroll
@@ -317,10 +343,16 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
     LevelPtr l1 = pyr.level(0);
     const double us = l1.d[lvl_pos(2 * t, P1)], ue = l1.d[lvl_pos(2 * t + 1, P1)];
     double o[BS_R];
+    // A decoupled end row of the caller's system (a Dirichlet row: lo = up = 0) is returned exactly as Thomas returns it,
+    // f / di (matrix_solver/mod.rs:36-39 with a zero coupling); the scaled sweeps would be off by an ulp.
+    const bool fix_first = SRC == BS_SRC_BANDS && g0 == 0 && !(flags & BS_OPEN_LEFT) && p2[0] == 0.0;
+    const bool fix_last = SRC == BS_SRC_BANDS && g0 + len == m && !(flags & BS_OPEN_RIGHT) && p0[m - 1] == 0.0;
     if (vec) {
       o[0] = us, o[BS_R - 1] = ue;
 #pragma unroll
       for (int j = BS_R - 2; j >= 1; --j) o[j] = fma(-C[j], o[j + 1], fma(-A[j], us, F[j])) * S[j];
+      if (fix_first) o[0] = p3[0] / p1[0];
+      if (fix_last) o[BS_R - 1] = p3[m - 1] / p1[m - 1];
       double2* po = reinterpret_cast<double2*>(out + g0);
 #pragma unroll
       for (int j = 0; j < BS_R / 2; ++j) {
@@ -340,9 +372,12 @@ __global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __rest
         else if (j < len - 1) nxt = fma(-C[j], nxt, fma(-A[j], us, F[j])) * S[j], o[j] = nxt;
         else o[j] = 0.0;
       }
+      if (fix_first) o[0] = p3[0] / p1[0];
 #pragma unroll
-      for (int j = 0; j < BS_R; ++j)
+      for (int j = 0; j < BS_R; ++j) {
+        if (fix_last && j == len - 1) o[j] = p3[m - 1] / p1[m - 1];
         if (j < len) out[g0 + j] = ACCUM ? out[g0 + j] + o[j] : o[j];
+      }
     }
   }
 }
@@ -386,7 +421,11 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict
   }
   pyr.backsolve(t, m);
   for (int r = t; r < m; r += BS_THREADS) {
-    const double v = l1.d[row_slot(r, m, P1)];
+    double v = l1.d[row_slot(r, m, P1)];
+    if (SRC == BS_SRC_BANDS) {  // exact Dirichlet end rows, as in k_tri_tile
+      if (r == 0 && !open_left && p2[0] == 0.0) v = p3[0] / p1[0];
+      if (r == m - 1 && !open_right && p0[m - 1] == 0.0) v = p3[m - 1] / p1[m - 1];
+    }
     out[r] = ACCUM ? out[r] + v : v;
   }
 }

@@ -466,7 +466,8 @@ int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, 
     ++g_launches;
   }
   int solve_mode = opt.solve_mode;
-  if (solve_mode == DZB_SOLVE_AUTO) solve_mode = tot <= 65536 ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
+  if (solve_mode == DZB_SOLVE_AUTO)  // many long bars: the per-bar kernels only cover 1024 nodes, the serial one covers anything
+    solve_mode = (tot <= 65536 || (n > 1024 && B != 1)) ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
   if (solve_mode == DZB_SOLVE_PARALLEL && n > 1024 && B != 1)
     return bail(fail(DZB_INVALID, "PARALLEL ensembles support bars of up to 1024 nodes (longer bars: one bar per handle)"));
   e->assembly_mode = opt.assembly_mode;
