@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdzahui_b200.so")
+SO_PATH = os.environ.get("DZB_LIB") or os.path.join(_HERE, "libdzahui_b200.so")  # DZB_LIB: an alternative build of the same library
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)

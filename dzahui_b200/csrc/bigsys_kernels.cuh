@@ -45,6 +45,9 @@ constexpr int BS_R = 8;                       // rows per chunk at every level
 constexpr int BS_THREADS = 256;               // tile kernel
 constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
 constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
+#ifndef BS_MIN_CTAS
+#define BS_MIN_CTAS 3
+#endif
 
 enum { BS_SRC_BANDS = 0, BS_SRC_ROWS = 1 };   // inputs are (lo, di, up, f) or already (a, c, s, f)
 enum { BS_OPEN_LEFT = 1, BS_OPEN_RIGHT = 2 }; // the system is a block of a longer one: end couplings are kept
@@ -258,7 +261,7 @@ __device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS
 //                 (ACCUM: out[] += value, the iterative-refinement update).
 // SRC: p0..p3 = (lo, di, up, f) of the caller's system, or (a, c, s, f) of a reduced system.
 template <int SRC, bool SOLVE, bool ACCUM>
-__global__ void __launch_bounds__(BS_THREADS, 3) k_tri_tile(const double* __restrict__ p0, const double* __restrict__ p1,
+__global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const double* __restrict__ p0, const double* __restrict__ p1,
                                                             const double* __restrict__ p2, const double* __restrict__ p3,
                                                             long long m, double* __restrict__ red_a,
                                                             double* __restrict__ red_c, double* __restrict__ red_s,
