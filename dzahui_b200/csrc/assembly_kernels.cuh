@@ -303,9 +303,10 @@ __device__ __forceinline__ void fast_row(const double* __restrict__ mesh, long l
   }
   const int s = lo;
   const double h1 = c - a, h2 = e - c, H = e - a;
-  const double ih1sq = 1.0 / (h1 * h1), ih2sq = 1.0 / (h2 * h2);
+  const double r1 = __drcp_rn(h1), r2 = __drcp_rn(h2);  // two reciprocals instead of four divisions
+  const double ih1sq = r1 * r1, ih2sq = r2 * r2;
   const double U0 = R.u0[s], U1 = R.u1[s], V0 = R.v0[s], V1 = R.v1[s];
-  const double prime_prev = -R.t0 / (2.0 * h1), prime_next = -R.t0 / (2.0 * h2);
+  const double prime_prev = -0.5 * R.t0 * r1, prime_next = -0.5 * R.t0 * r2;
   const double prime_sq = (H / 2.0) * (U0 * ih1sq + V0 * ih2sq);
   const double half_prev = -R.t1p / 4.0, half_next = R.t1m / 4.0;
   const double half_sq = (H * H / 4.0) * (U1 * ih1sq - V1 * ih2sq);
