@@ -4,6 +4,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device and reports DZB_CUDA otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -340,6 +341,13 @@ template <int L, int WPB>
 int launch_step_lean(dzb_ensemble* e) {
   dzb::k_td_step_lean<L, WPB><<<(unsigned)e->B, 32 * WPB, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->bdi, e->idn, e->hh, (int)e->n,
                                                                           e->bc0, e->bc1, e->lean_k);
+  LAUNCHED();
+  return DZB_OK;
+}
+template <int L, int WPB>
+int launch_step_lean_multi(dzb_ensemble* e, int steps) {
+  dzb::k_td_step_lean_multi<L, WPB><<<(unsigned)e->B, 32 * WPB, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->bdi, e->idn, e->hh,
+                                                                                (int)e->n, e->bc0, e->bc1, e->lean_k, steps);
   LAUNCHED();
   return DZB_OK;
 }
@@ -991,7 +999,23 @@ int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double
 }
 int dzb_ensemble_step(dzb_ensemble* e, double dt, size_t steps) {
   if (!e) return fail(DZB_INVALID, "null pointer");
-  for (size_t s = 0; s < steps; ++s) {
+  size_t s = 0;
+  if (steps > 1) {  // the first step also (re)builds the per-dt operators and decides whether the lean path applies
+    int rc = ensemble_step_once(e, dt);
+    if (rc) return rc;
+    s = 1;
+    // nobody can observe the intermediate states: keep operator and state on chip for blocks of steps (8 rows per lane only)
+    if (e->fast && e->lean_ok && !e->use_big && e->lean_L <= 8 && !std::getenv("DZB_NO_MULTI_STEP")) {
+      while (s < steps) {
+        const int blk = (int)std::min<size_t>(steps - s, 1024);
+        DISPATCH_LEAN(e, launch_step_lean_multi, e, blk);
+        if (rc) return rc;
+        e->cur ^= 1;
+        s += (size_t)blk;
+      }
+    }
+  }
+  for (; s < steps; ++s) {
     int rc = ensemble_step_once(e, dt);
     if (rc) return rc;
   }

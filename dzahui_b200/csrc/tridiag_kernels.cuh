@@ -442,4 +442,140 @@ __global__ void __launch_bounds__(32 * WPB) k_td_step_lean(const double* __restr
   }
 }
 
+// ---- temporal blocking: `steps` solve(dt) per launch ---------------------------------------------------------------
+// dzb_ensemble_step(e, dt, steps) with steps > 1 never shows the intermediate states to anyone, so the bar's operator
+// (A' pre-scaled by 1/den, alpha, c: five values per row, 8 rows per lane) and its state stay on chip for the whole
+// launch: HBM traffic is 40 B per DOF for ALL the steps together instead of per step.  The per-step work is the same
+// arithmetic as k_td_step_lean (beta from the neighbours in shared memory, two scans, Dirichlet ends).  Reported
+// separately by bench.py ("multi_step"): the reference-facing solve(dt) contract returns u after every step.
+template <int L, int WPB>
+__global__ void __launch_bounds__(32 * WPB) k_td_step_lean_multi(const double* __restrict__ u_old, double* __restrict__ u_new,
+                                                                 const double* __restrict__ bdi,
+                                                                 const double* __restrict__ idn,
+                                                                 const double* __restrict__ hh, int n, double bc0,
+                                                                 double bc1, LeanConsts K, int steps) {
+  constexpr int LANES = 32 * WPB;
+  constexpr int NP = LANES * L;
+  constexpr int SW = NP + LANES + 2;
+  __shared__ double s_u[SW];
+  __shared__ double xh[WPB], fe[2][WPB], fp[2][WPB], ge[2][WPB], gp[2][WPB];
+  const int g = threadIdx.x, lane = g & 31, w = g >> 5;
+  const long long bar = blockIdx.x;
+  double* su = s_u + 1;
+
+  const long long ob = bar * (long long)NP + g;
+  double cc[L], al[L], blo[L], bdd[L], bup[L], be[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) cc[j] = __ldcs(hh + ob + j * LANES);
+#pragma unroll
+  for (int j = 0; j < L; ++j) al[j] = __ldcs(idn + ob + j * LANES);
+#pragma unroll
+  for (int j = 0; j < L; ++j) bdd[j] = __ldcs(bdi + ob + j * LANES);
+  const double* ub = u_old + bar * (long long)n;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const int r = k * LANES + g;
+    su[r + r / L] = r < n ? __ldcs(ub + r) : 0.0;
+  }
+  if (g == 0) su[-1] = 0.0, su[NP + LANES] = 0.0;
+  if (WPB > 1 && lane == 31) xh[w] = cc[L - 1];
+  __syncthreads();
+
+  const int r0 = g * L, s0 = r0 + g;
+  {  // the operator, once
+    double hl = shfl_up_d(cc[L - 1], 1);
+    if (WPB > 1 && lane == 0 && w > 0) hl = xh[w - 1];
+    if (g == 0 || hl == 0.0) hl = 1.0;
+    double ml = hl * K.q8;
+    double El = fma(K.dtmu, __drcp_rn(hl), ml);
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const int r = r0 + j;
+      const bool interior = r >= 1 && r <= n - 2;
+      const double hr = r <= n - 2 ? cc[j] : 1.0;
+      const double mr = hr * K.q8;
+      const double Er = fma(K.dtmu, __drcp_rn(hr), mr);
+      const double id = al[j];
+      blo[j] = interior ? (El + K.kp) * id : 0.0;
+      bup[j] = interior ? (Er - K.km) * id : 0.0;
+      bdd[j] = bdd[j] * id;
+      al[j] = interior ? -ml * id : 0.0;
+      cc[j] = interior ? mr * id : 0.0;
+      ml = mr, El = Er;
+    }
+  }
+
+  for (int it = 0; it < steps; ++it) {
+    const int ph = it & 1;  // alternate the hand-over slots so that a fast warp cannot overwrite what a slow one still reads
+    {
+      double um = g == 0 ? 0.0 : su[(r0 - 1) + (r0 - 1) / L];
+      double u0 = su[s0];
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        const int rn = r0 + j + 1;
+        const double up1 = (j == L - 1) ? (g == LANES - 1 ? 0.0 : su[rn + rn / L]) : su[rn + g];
+        be[j] = fma(bup[j], up1, fma(bdd[j], u0, blo[j] * um));
+        um = u0, u0 = up1;
+      }
+    }
+    {
+      double e = 0.0, p = 1.0;
+#pragma unroll
+      for (int j = 0; j < L; ++j) e = fma(al[j], e, be[j]), p *= al[j];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double pe = shfl_up_d(e, d), pp = shfl_up_d(p, d);
+        if (lane >= d) e = fma(p, pe, e), p *= pp;
+      }
+      double carry = shfl_up_d(e, 1);
+      if (lane == 0) carry = 0.0;
+      if (WPB > 1) {
+        if (lane == 31) fe[ph][w] = e, fp[ph][w] = p;
+        __syncthreads();  // also: every lane has read its neighbours' u
+        double E = 0.0;
+        for (int v = 0; v < w; ++v) E = fma(fp[ph][v], E, fe[ph][v]);
+        const double pin = shfl_up_d(p, 1);
+        carry = lane == 0 ? E : fma(pin, E, carry);
+      }
+#pragma unroll
+      for (int j = 0; j < L; ++j) carry = fma(al[j], carry, be[j]), be[j] = carry;
+    }
+    {
+      double e = 0.0, p = 1.0;
+#pragma unroll
+      for (int j = L - 1; j >= 0; --j) e = fma(-cc[j], e, be[j]), p *= -cc[j];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double pe = shfl_down_d(e, d), pp = shfl_down_d(p, d);
+        if (lane + d < 32) e = fma(p, pe, e), p *= pp;
+      }
+      double carry = shfl_down_d(e, 1);
+      if (lane == 31) carry = 0.0;
+      if (WPB > 1) {
+        if (lane == 0) ge[ph][w] = e, gp[ph][w] = p;
+        __syncthreads();
+        double E = 0.0;
+        for (int v = WPB - 1; v > w; --v) E = fma(gp[ph][v], E, ge[ph][v]);
+        const double pin = shfl_down_d(p, 1);
+        carry = lane == 31 ? E : fma(pin, E, carry);
+      } else {
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = L - 1; j >= 0; --j) {
+        carry = fma(-cc[j], carry, be[j]);
+        const int r = r0 + j;
+        su[s0 + j] = r == 0 ? bc0 : (r == n - 1 ? bc1 : carry);  // time_dependent.rs:273-274
+      }
+    }
+    if (WPB > 1) __syncthreads(); else __syncwarp();
+  }
+  double* un = u_new + bar * (long long)n;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const int r = k * LANES + g;
+    if (r < n) __stcs(un + r, su[r + r / L]);
+  }
+}
+
 }  // namespace dzb
