@@ -214,6 +214,8 @@ def main():
     dz.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
