@@ -212,6 +212,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: dzahui_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dz.set_device(local_rank)
+    try:  # run (and first-touch the pinned result buffer) on the CPUs next to this GPU: the e2e leg is a 0.5 GB D2H per step
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
