@@ -240,6 +240,18 @@ __device__ __forceinline__ void store_row(const AsmOut& o, long long g, const do
   if (KIND == KIND_TD) o.mlo[g] = v[4], o.mdi[g] = v[5], o.mup[g] = v[6];
 }
 
+// row index -> (bar, row in bar) without a 64-bit division on the common paths
+__device__ __forceinline__ void split_index(long long g, long long n, long long n_bars, long long* bar, long long* i) {
+  if (n_bars == 1) {
+    *bar = 0, *i = g;
+  } else if ((g | n) >> 31 == 0) {
+    const unsigned b = (unsigned)g / (unsigned)n;
+    *bar = b, *i = (unsigned)g - b * (unsigned)n;
+  } else {
+    *bar = g / n, *i = g - *bar * n;
+  }
+}
+
 // One thread per matrix row; the rule table is staged in shared memory when it fits (smem_rule != 0).
 // Stokes: `force` holds rho-free samples f(T_square,i(x_k)) k-major: force[(k-1)*n + i], row 0 at i = 0.
 template <int KIND>
@@ -256,7 +268,8 @@ __global__ void __launch_bounds__(128) k_assemble_faithful(const double* __restr
   }
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n * n_bars) return;
-  const long long bar = g / n, i = g - bar * n;
+  long long bar, i;
+  split_index(g, n, n_bars, &bar, &i);
   const double* bm = mesh + bar * n;
   double v[7];
   if (i == n - 1 || (i == 0 && KIND != KIND_STOKES))
@@ -341,7 +354,8 @@ __global__ void __launch_bounds__(256) k_assemble_fast(const double* __restrict_
   }
   const long long total = n * n_bars;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-    const long long bar = g / n, i = g - bar * n;
+    long long bar, i;
+    split_index(g, n, n_bars, &bar, &i);
     double v[7];
     if (i == 0 || i == n - 1)
       boundary_row<KIND>(i == 0, P, v);
