@@ -63,6 +63,12 @@ SIGNATURES = {
     "dzb_solver_block_residual": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "dzb_solver_block_read": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
     "dzb_interface_solve": (C.c_int, [c_double_p, C.c_size_t, c_double_p]),
+    "dzb_solver_block_reduce_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "dzb_interface_solve_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "dzb_solver_block_backsolve_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "dzb_solver_block_edges_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dzb_solver_block_residual_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dzb_solver_block_device_solution": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "dzb_format_f64": (C.c_int, [C.c_double, C.c_char_p, C.c_size_t]),
     "dzb_csv_prepare_dir": (C.c_int, [C.c_char_p, C.c_int]),
     "dzb_csv_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_char_p), C.c_size_t, c_double_p, C.c_size_t]),

@@ -418,6 +418,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict
       const double det = (s0 * s1 - s0 * a1) - c0 * s1;  // = b0 b1 - c0 a1 without the cancelling c0 a1 terms
       top.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;
       top.d[1] = ((s0 - c0) * f1 - a1 * f0) / det;
+    } else if (top8) {  // the pair the interface solve left in device memory
+      top.d[0] = top8[0], top.d[1] = top8[1];
     } else {
       top.d[0] = us, top.d[1] = ue;
     }
@@ -446,7 +448,11 @@ __device__ __forceinline__ void dd_sub_prod(double& s, double& comp, double x, d
 __global__ void __launch_bounds__(256) k_residual_dd(const double* __restrict__ lo, const double* __restrict__ di,
                                                      const double* __restrict__ up, const double* __restrict__ f,
                                                      const double* __restrict__ u, double* __restrict__ r, long long n,
-                                                     int flags, double u_left, double u_right) {
+                                                     int flags, double u_left, double u_right,
+                                                     const double* __restrict__ d_left,
+                                                     const double* __restrict__ d_right) {
+  if (d_left) u_left = *d_left;     // halo values left in device memory by the edge exchange
+  if (d_right) u_right = *d_right;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double s = f[i], comp = 0.0;
     if (i > 0) dd_sub_prod(s, comp, lo[i], u[i - 1]);
@@ -455,6 +461,31 @@ __global__ void __launch_bounds__(256) k_residual_dd(const double* __restrict__ 
     if (i + 1 < n) dd_sub_prod(s, comp, up[i], u[i + 1]);
     else if (flags & BS_OPEN_RIGHT) dd_sub_prod(s, comp, up[i], u_right);   // halo value of the next block
     r[i] = s + comp;
+  }
+}
+
+// ---- SPIKE interface system on the device: rows[8 r ..] = block r's (a, c, s, f) x 2, 2 n_blocks unknowns ----------
+// Serial Thomas in row-excess form (sigma'_i = s_i + m sigma'_{i-1}, beta_i = sigma'_i - c_i: same-signed sums for an
+// M-matrix); every rank runs it redundantly on the gathered rows, so nothing but the all-gather crosses NVLink.
+__global__ void k_interface_solve(const double* __restrict__ rows, int m, double* __restrict__ ends, double* __restrict__ work) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sig = rows[2] - rows[0];  // row 0: the (zero) outer coupling of the closed end leaves the excess
+  double beta = sig - rows[1], fp = rows[3];
+  work[0] = beta, work[m] = fp;
+  for (int i = 1; i < m; ++i) {
+    const double a = rows[4 * i], c = i == m - 1 ? 0.0 : rows[4 * i + 1], s = rows[4 * i + 2], f = rows[4 * i + 3];
+    const double mm = -a / beta;
+    const double s_eff = i == m - 1 ? s - rows[4 * i + 1] : s;  // drop the stored (zero) outer coupling from the excess
+    sig = fma(mm, sig, s_eff);
+    fp = fma(mm, fp, f);
+    beta = sig - c;
+    work[i] = beta, work[m + i] = fp;
+  }
+  double x = work[2 * m - 1] / work[m - 1];
+  ends[m - 1] = x;
+  for (int i = m - 2; i >= 0; --i) {
+    x = (work[m + i] - rows[4 * i + 1] * x) / work[i];
+    ends[i] = x;
   }
 }
 
@@ -620,11 +651,13 @@ inline int bigsys_block_reduce(BigSys* s, const double* lo, const double* di, co
 }
 // SPIKE split, second half: the interface solve gave this block's end unknowns (us, ue); back-substitute.
 inline int bigsys_block_backsolve(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
-                                  double us, double ue, double* out, bool accum, cudaStream_t st, unsigned long long* launches) {
+                                  double us, double ue, const double* d_ends, double* out, bool accum, cudaStream_t st,
+                                  unsigned long long* launches) {
+  double* de = const_cast<double*>(d_ends);  // device pair (us, ue); takes precedence over the host values when non-null
   if (s->levels.empty())
-    return bigsys_mid<BS_SRC_BANDS, BS_MID_BACKSOLVE>(lo, di, up, f, s->n, out, accum, flags, nullptr, us, ue, st, launches);
+    return bigsys_mid<BS_SRC_BANDS, BS_MID_BACKSOLVE>(lo, di, up, f, s->n, out, accum, flags, de, us, ue, st, launches);
   BigLevel& L = s->levels.back();
-  if (bigsys_mid<BS_SRC_ROWS, BS_MID_BACKSOLVE>(L.a, L.c, L.s, L.f, L.m, L.u, false, flags, nullptr, us, ue, st, launches)) return 1;
+  if (bigsys_mid<BS_SRC_ROWS, BS_MID_BACKSOLVE>(L.a, L.c, L.s, L.f, L.m, L.u, false, flags, de, us, ue, st, launches)) return 1;
   return bigsys_backward(s, lo, di, up, f, flags, out, accum, st, launches);
 }
 
@@ -639,7 +672,7 @@ inline int bigsys_solve(BigSys* s, const double* lo, const double* di, const dou
                         int refine_steps, cudaStream_t st, unsigned long long* launches) {
   if (bigsys_solve_once(s, lo, di, up, rhs, out, false, st, launches)) return 1;
   for (int k = 0; k < refine_steps; ++k) {
-    k_residual_dd<<<bigsys_grid(s->n), 256, 0, st>>>(lo, di, up, rhs, out, s->resid, (long long)s->n, 0, 0.0, 0.0);
+    k_residual_dd<<<bigsys_grid(s->n), 256, 0, st>>>(lo, di, up, rhs, out, s->resid, (long long)s->n, 0, 0.0, 0.0, nullptr, nullptr);
     ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bigsys_fail(e, "k_residual_dd");

@@ -698,7 +698,7 @@ static int static_finish(dzb_solver* s, const dzb_options& opt) {
   if (s->kind == dzb::KIND_STOKES) solve_mode = DZB_SOLVE_FAITHFUL;
   if (solve_mode == DZB_SOLVE_PARALLEL) {
     s->parallel = true;
-    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : (n > (1u << 22) ? 1 : 0);
+    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : 0;  // 1e-11 of the exact solution at 10^7 rows without any
     if (dzb::bigsys_prepare(&s->big, n)) return fail(DZB_CUDA, dzb::bigsys_error());
   } else {
     int rc;
@@ -939,8 +939,8 @@ int dzb_solver_block_backsolve(dzb_solver* s, int which_rhs, double us, double u
   if (!s) return fail(DZB_INVALID, "null pointer");
   if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
   const double* f = which_rhs ? s->big.resid : s->rhs;
-  if (dzb::bigsys_block_backsolve(&s->big, s->lo, s->di, s->up, f, s->block_flags, us, ue, s->out, accumulate != 0, g_stream,
-                                  &g_launches))
+  if (dzb::bigsys_block_backsolve(&s->big, s->lo, s->di, s->up, f, s->block_flags, us, ue, nullptr, s->out, accumulate != 0,
+                                  g_stream, &g_launches))
     return fail(DZB_CUDA, dzb::bigsys_error());
   return DZB_OK;
 }
@@ -955,8 +955,55 @@ int dzb_solver_block_residual(dzb_solver* s, double u_left, double u_right) {
   if (!s) return fail(DZB_INVALID, "null pointer");
   if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
   dzb::k_residual_dd<<<dzb::bigsys_grid(s->n), 256, 0, g_stream>>>(s->lo, s->di, s->up, s->rhs, s->out, s->big.resid,
-                                                                    (long long)s->n, s->block_flags, u_left, u_right);
+                                                                    (long long)s->n, s->block_flags, u_left, u_right, nullptr, nullptr);
   LAUNCHED();
+  return DZB_OK;
+}
+// ---- the same five steps with every operand in DEVICE memory: nothing synchronises with the host, so reduce ->
+// all-gather (NCCL, on the caller's stream) -> interface solve -> back-substitution queue up behind one another.
+int dzb_solver_block_reduce_device(dzb_solver* s, int which_rhs, double* d_top8) {
+  if (!s || !d_top8) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  const double* f = which_rhs ? s->big.resid : s->rhs;
+  if (dzb::bigsys_block_reduce(&s->big, s->lo, s->di, s->up, f, s->block_flags, d_top8, g_stream, &g_launches))
+    return fail(DZB_CUDA, dzb::bigsys_error());
+  return DZB_OK;
+}
+int dzb_interface_solve_device(const double* d_rows, size_t n_blocks, double* d_ends, double* d_work) {
+  if (!d_rows || !d_ends || !d_work) return fail(DZB_INVALID, "null pointer");
+  if (n_blocks == 0 || n_blocks > 4096) return fail(DZB_WRONG_DIMS, "number of blocks");
+  dzb::k_interface_solve<<<1, 32, 0, g_stream>>>(d_rows, (int)(2 * n_blocks), d_ends, d_work);
+  LAUNCHED();
+  return DZB_OK;
+}
+int dzb_solver_block_backsolve_device(dzb_solver* s, int which_rhs, const double* d_ends2, int accumulate) {
+  if (!s || !d_ends2) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  const double* f = which_rhs ? s->big.resid : s->rhs;
+  if (dzb::bigsys_block_backsolve(&s->big, s->lo, s->di, s->up, f, s->block_flags, 0.0, 0.0, d_ends2, s->out, accumulate != 0,
+                                  g_stream, &g_launches))
+    return fail(DZB_CUDA, dzb::bigsys_error());
+  return DZB_OK;
+}
+int dzb_solver_block_edges_device(const dzb_solver* s, double* d_edges2) {
+  if (!s || !d_edges2) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  CK(cudaMemcpyAsync(d_edges2, s->out, sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  CK(cudaMemcpyAsync(d_edges2 + 1, s->out + s->n - 1, sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  return DZB_OK;
+}
+int dzb_solver_block_residual_device(dzb_solver* s, const double* d_left, const double* d_right) {
+  if (!s) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  dzb::k_residual_dd<<<dzb::bigsys_grid(s->n), 256, 0, g_stream>>>(s->lo, s->di, s->up, s->rhs, s->out, s->big.resid,
+                                                                    (long long)s->n, s->block_flags, 0.0, 0.0, d_left, d_right);
+  LAUNCHED();
+  return DZB_OK;
+}
+int dzb_solver_block_device_solution(const dzb_solver* s, const double** device_ptr) {
+  if (!s || !device_ptr) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  *device_ptr = s->out;
   return DZB_OK;
 }
 int dzb_solver_block_read(const dzb_solver* s, double* out_host, size_t n) {

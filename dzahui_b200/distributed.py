@@ -102,6 +102,26 @@ class BarBlock:
     def block_residual(self, u_left, u_right):
         check(self._lib.dzb_solver_block_residual(self._h, float(u_left), float(u_right)), self._lib)
 
+    # -- the same steps on device buffers (raw pointers, e.g. torch tensors' data_ptr()), no host synchronisation
+    def block_reduce_device(self, which_rhs, d_top8):
+        check(self._lib.dzb_solver_block_reduce_device(self._h, int(which_rhs), C.c_void_p(int(d_top8))), self._lib)
+
+    def block_backsolve_device(self, which_rhs, d_ends2, accumulate=False):
+        check(self._lib.dzb_solver_block_backsolve_device(self._h, int(which_rhs), C.c_void_p(int(d_ends2)), int(bool(accumulate))),
+              self._lib)
+
+    def block_edges_device(self, d_edges2):
+        check(self._lib.dzb_solver_block_edges_device(self._h, C.c_void_p(int(d_edges2))), self._lib)
+
+    def block_residual_device(self, d_left, d_right):
+        check(self._lib.dzb_solver_block_residual_device(self._h, C.c_void_p(int(d_left)) if d_left else None,
+                                                         C.c_void_p(int(d_right)) if d_right else None), self._lib)
+
+    def device_solution_ptr(self):
+        p = C.c_void_p()
+        check(self._lib.dzb_solver_block_device_solution(self._h, C.byref(p)), self._lib)
+        return p.value
+
     def block_read(self):
         out = np.empty(self.n)
         check(self._lib.dzb_solver_block_read(self._h, out.ctypes.data_as(_lib.c_double_p), self.n), self._lib)
@@ -163,6 +183,61 @@ def spike_solve(blocks, comm, refine_steps=0, solve_interface=interface_solve):
     return [b.block_read() for b in blocks]
 
 
+class DeviceSpike:
+    """The SPIKE solve with every operand in device memory (torch CUDA tensors as buffers): block reductions, ONE
+    `all_gather_into_tensor` of 8 doubles per block over NCCL, the interface solve as a one-thread kernel run redundantly
+    on every rank, back-substitution — all queued on the current stream, nothing waits for the host."""
+
+    def __init__(self, blocks, group=None, world=None, rank=None):
+        import torch
+        self._torch, self.blocks, self.group = torch, blocks, group
+        if world is None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world, self.rank, self.k = world, rank, len(blocks)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        P = world * self.k
+        self.top = torch.zeros((self.k, 8), dtype=torch.float64, device=dev)
+        self.rows = torch.zeros((P, 8), dtype=torch.float64, device=dev)
+        self.ends = torch.zeros((P, 2), dtype=torch.float64, device=dev)
+        self.work = torch.zeros((P, 4), dtype=torch.float64, device=dev)
+        self.edges = torch.zeros((self.k, 2), dtype=torch.float64, device=dev)
+        self.alledges = torch.zeros((P, 2), dtype=torch.float64, device=dev)
+        self._lib = _lib.load()
+
+    def _gather(self, dst, src):
+        if self.world == 1:
+            dst.copy_(src)
+        else:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(dst.view(-1), src.view(-1), group=self.group)
+
+    def _one(self, which_rhs, accumulate):
+        for j, b in enumerate(self.blocks):
+            b.block_reduce_device(which_rhs, self.top[j].data_ptr())
+        self._gather(self.rows, self.top)
+        check(self._lib.dzb_interface_solve_device(C.c_void_p(self.rows.data_ptr()), self.rows.shape[0],
+                                                   C.c_void_p(self.ends.data_ptr()), C.c_void_p(self.work.data_ptr())), self._lib)
+        for j, b in enumerate(self.blocks):
+            b.block_backsolve_device(which_rhs, self.ends[self.rank * self.k + j].data_ptr(), accumulate)
+
+    def solve(self, refine_steps=0):
+        """leaves every block's solution in its device buffer (BarBlock.device_solution_ptr / block_read)"""
+        self._one(0, False)
+        P = self.world * self.k
+        for _ in range(int(refine_steps)):
+            for j, b in enumerate(self.blocks):
+                b.block_edges_device(self.edges[j].data_ptr())
+            self._gather(self.alledges, self.edges)
+            for j, b in enumerate(self.blocks):
+                g = self.rank * self.k + j
+                left = self.alledges[g - 1, 1:].data_ptr() if g > 0 else 0
+                right = self.alledges[g + 1, 0:].data_ptr() if g + 1 < P else 0
+                b.block_residual_device(left, right)
+            self._one(1, True)
+
+
 class DistributedBarTimeIndependent:
     """`DiffussionSolverTimeIndependent` (time_independent.rs:46-53) for one bar split across the ranks of `comm`.
     `mesh` is the whole bar's node array (every rank slices its own block + halo from it) or, with `local=True`,
@@ -185,6 +260,15 @@ class DistributedBarTimeIndependent:
     def solve(self, _time_step=0.0):
         """nodal values of this process' rows [self.rows[0], self.rows[1])"""
         return np.concatenate(spike_solve(self.blocks, self.comm, self.refine_steps))
+
+    def solve_device(self, group=None):
+        """the same solve with device-resident operands (DeviceSpike); results stay on the device until block_read()"""
+        if getattr(self, "_dev", None) is None:
+            self._dev = DeviceSpike(self.blocks, group, self.comm.world, self.comm.rank)
+        self._dev.solve(self.refine_steps)
+
+    def read(self):
+        return np.concatenate([b.block_read() for b in self.blocks])
 
     def close(self):
         for b in self.blocks:

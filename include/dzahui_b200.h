@@ -54,7 +54,7 @@ typedef enum dzb_solve_mode {
 typedef struct dzb_options {
   int assembly_mode; /* dzb_assembly_mode */
   int solve_mode;    /* dzb_solve_mode */
-  int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto: 0 up to 2^22 rows, 1 beyond) */
+  int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto = 0: the unrefined solve is within 1e-11 of the exact solution of the system at 10^7 rows; one sweep reaches 1e-18) */
   int reserved;      /* ensembles, PARALLEL mode: 0 = operator rebuilt on chip (k_td_step_lean, 40 B per DOF-step), 1 = pre-scaled operator arrays (k_td_step_fast, 56 B) */
 } dzb_options;
 
@@ -145,6 +145,16 @@ int dzb_solver_block_residual(dzb_solver* s, double u_left, double u_right);   /
 int dzb_solver_block_read(const dzb_solver* s, double* out_host, size_t n);
 /* rows[8 r ..] = block r's top8; ends[2 r], ends[2 r + 1] = the values to hand to block r's back-substitution */
 int dzb_interface_solve(const double* rows, size_t n_blocks, double* ends);
+/* The same steps with every operand in DEVICE memory and no host synchronisation, so that reduce -> ncclAllGather (on the
+ * stream given to dzb_set_stream) -> interface solve -> back-substitution queue up behind one another:
+ * d_top8: 8 doubles; d_rows: 8 per block (all ranks, gathered); d_ends: 2 per block; d_work: 4 per block of scratch;
+ * d_ends2: this block's pair inside d_ends; d_left / d_right: the neighbours' edge values (NULL where there is none). */
+int dzb_solver_block_reduce_device(dzb_solver* s, int which_rhs, double* d_top8);
+int dzb_interface_solve_device(const double* d_rows, size_t n_blocks, double* d_ends, double* d_work);
+int dzb_solver_block_backsolve_device(dzb_solver* s, int which_rhs, const double* d_ends2, int accumulate);
+int dzb_solver_block_edges_device(const dzb_solver* s, double* d_edges2);
+int dzb_solver_block_residual_device(dzb_solver* s, const double* d_left, const double* d_right);
+int dzb_solver_block_device_solution(const dzb_solver* s, const double** device_ptr);
 
 /* ---- CSV snapshots: Writer (writer.rs:47-146), host code ------------------------------------------------------- */
 /* `f64::to_string()` of Rust: shortest round-trip digits, never an exponent, "1" for 1.0, "-0", "NaN", "inf". */
