@@ -34,6 +34,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -161,52 +162,62 @@ __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int l
   }
 }
 
-// Shared-memory pyramid below a level-1 system of 8*P1 rows; P1 is a power of 4 (64 for tiles, up to 256 for k_tri_mid).
+// Shared-memory pyramid below a level-1 system of up to 8*P1 rows: level capacities P1, ceil(P1/4), ... , 1 chunks, then the
+// final 2 rows.  WARP: the pyramid belongs to one warp (tile of 256 rows) and synchronises with __syncwarp, so the warps
+// of a CTA run their tiles independently; otherwise it belongs to the CTA (__syncthreads).
 template <int P>
 struct PyramidRows {
-  static constexpr int value = 8 * P + PyramidRows<P / 4>::value;
+  static constexpr int value = 8 * P + PyramidRows<(P + 3) / 4>::value;
 };
 template <>
-struct PyramidRows<0> {
-  static constexpr int value = 2;
+struct PyramidRows<1> {
+  static constexpr int value = 8 + 2;
 };
-template <int P1>
+template <int P1, bool WARP = false>
 struct Pyramid {
   static constexpr int ROWS = PyramidRows<P1>::value;
   double a[ROWS], c[ROWS], s[ROWS], d[ROWS];
   __device__ __forceinline__ LevelPtr level(int off) { return {a + off, c + off, s + off, d + off}; }
-  // forward sweeps from level 1 (holding rows1 rows) to the final 2 rows; all threads of the CTA must call
+  __device__ __forceinline__ static void sync() {
+    if (WARP) __syncwarp(); else __syncthreads();
+  }
+  // forward sweeps from level 1 (holding rows1 rows) to the final 2 rows; every thread of the tile must call
   __device__ __forceinline__ void reduce(int t, int rows1) {
     int off = 0, rows = rows1;
 #pragma unroll
-    for (int p = P1; p >= 1; p /= 4) {
-      __syncthreads();
-      if (chunk_len(rows, t) > 0) level_reduce(level(off), p, chunk_len(rows, t), level(off + 8 * p), p / 4, t);
+    for (int p = P1;; p = (p + 3) / 4) {
+      sync();
+      if (chunk_len(rows, t) > 0) level_reduce(level(off), p, chunk_len(rows, t), level(off + 8 * p), p == 1 ? 0 : (p + 3) / 4, t);
       off += 8 * p;
       rows = 2 * ((rows + BS_R - 1) / BS_R);
+      if (p == 1) break;
     }
-    __syncthreads();
+    sync();
   }
   __device__ __forceinline__ LevelPtr top() { return level(ROWS - 2); }
   // back-substitution; top().d[0..1] must hold the solved pair
   __device__ __forceinline__ void backsolve(int t, int rows1) {
-    int rows_at[8];
+    int rows_at[8], cap[8], offs[8], nl = 0;
     {
-      int rows = rows1, k = 0;
+      int rows = rows1, off = 0;
 #pragma unroll
-      for (int p = P1; p >= 1; p /= 4) rows_at[k++] = rows, rows = 2 * ((rows + BS_R - 1) / BS_R);
+      for (int p = P1;; p = (p + 3) / 4) {
+        rows_at[nl] = rows, cap[nl] = p, offs[nl] = off, ++nl;
+        off += 8 * p;
+        rows = 2 * ((rows + BS_R - 1) / BS_R);
+        if (p == 1) break;
+      }
     }
-    int off = ROWS - 2, k = 0;
 #pragma unroll
-    for (int p = 1; p <= P1; p *= 4) ++k;
-#pragma unroll
-    for (int p = 1; p <= P1; p *= 4) {
-      off -= 8 * p;
-      --k;
-      __syncthreads();
-      if (chunk_len(rows_at[k], t) > 0) level_backsolve(level(off), p, chunk_len(rows_at[k], t), level(off + 8 * p), p / 4, t);
+    for (int k = 7; k >= 0; --k) {
+      if (k < nl) {
+        const int p = cap[k];
+        sync();
+        if (chunk_len(rows_at[k], t) > 0)
+          level_backsolve(level(offs[k]), p, chunk_len(rows_at[k], t), level(offs[k] + 8 * p), p == 1 ? 0 : (p + 3) / 4, t);
+      }
     }
-    __syncthreads();
+    sync();
   }
 };
 
@@ -260,22 +271,32 @@ __device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS
 // SOLVE == true : forward sweeps again, (u_s, u_e) of the tile from ured[2 tile + {0,1}], back-substitution, out[]
 //                 (ACCUM: out[] += value, the iterative-refinement update).
 // SRC: p0..p3 = (lo, di, up, f) of the caller's system, or (a, c, s, f) of a reduced system.
-template <int SRC, bool SOLVE, bool ACCUM>
+// TT: threads that share a tile.  256: the CTA (2048 rows, __syncthreads between the pyramid levels).  32: one warp (256
+// rows, __syncwarp only), so that while one warp is inside its latency-bound pyramid the other warps of the SM keep
+// streaming; a tile then leaves 2 rows per 256.
+template <int SRC, bool SOLVE, bool ACCUM, int TT>
 __global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const double* __restrict__ p0, const double* __restrict__ p1,
                                                             const double* __restrict__ p2, const double* __restrict__ p3,
                                                             long long m, double* __restrict__ red_a,
                                                             double* __restrict__ red_c, double* __restrict__ red_s,
                                                             double* __restrict__ red_f, const double* __restrict__ ured,
                                                             double* __restrict__ out, int flags) {
-  __shared__ Pyramid<BS_THREADS / 4> pyr;  // level 1: up to 512 rows = 64 chunks
-  const int t = threadIdx.x;
-  long long tile0 = (long long)blockIdx.x * BS_TILE;
-  int rows0 = (int)min((long long)BS_TILE, m - tile0);            // rows of this tile
-  {  // never leave a single row to the last tile: split 2047 + 2 instead
-    const long long rem = m - (long long)(gridDim.x - 1) * BS_TILE;
-    if (rem == 1 && gridDim.x > 1) {
-      if (blockIdx.x == gridDim.x - 1) tile0 -= 1, rows0 = 2;
-      else if (blockIdx.x == gridDim.x - 2) rows0 = BS_TILE - 1;
+  constexpr bool WARP = TT == 32;
+  constexpr int TILE = BS_R * TT;
+  constexpr int P1 = TT / 4;  // chunks of level 1
+  __shared__ Pyramid<P1, WARP> pyrs[BS_THREADS / TT];
+  Pyramid<P1, WARP>& pyr = pyrs[WARP ? threadIdx.x / 32 : 0];
+  const int t = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  const long long tile = WARP ? (long long)blockIdx.x * (BS_THREADS / 32) + threadIdx.x / 32 : (long long)blockIdx.x;
+  const long long ntiles = (m + TILE - 1) / TILE;
+  if (tile >= ntiles) return;  // whole warps only (warp scope); never taken in CTA scope
+  long long tile0 = tile * TILE;
+  int rows0 = (int)min((long long)TILE, m - tile0);               // rows of this tile
+  {  // never leave a single row to the last tile: split (TILE - 1) + 2 instead
+    const long long rem = m - (ntiles - 1) * TILE;
+    if (rem == 1 && ntiles > 1) {
+      if (tile == ntiles - 1) tile0 -= 1, rows0 = 2;
+      else if (tile == ntiles - 2) rows0 = TILE - 1;
     }
   }
   const int rows1 = 2 * ((rows0 + BS_R - 1) / BS_R);              // rows it leaves at level 1
@@ -323,8 +344,7 @@ __global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const doub
 #pragma unroll
     for (int j = 0; j < BS_R; ++j) S[j] = excess3(A[j], S[j], C[j]);
   }
-  // level 0 in registers; SOLVE keeps (alpha_j, 1/beta_j, delta_j) in (A, S, F)[1..len-2]
-  constexpr int P1 = BS_THREADS / 4;
+  // level 0 in registers; SOLVE keeps (alpha~_j, g~_j, 1/P_j, delta~_j) in (A, C, S, F)[1..len-2]
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
     const int i0 = lvl_pos(2 * t, P1), i1 = lvl_pos(2 * t + 1, P1);
@@ -335,12 +355,12 @@ __global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const doub
   LevelPtr top = pyr.top();
   if (!SOLVE) {
     if (t < 2) {
-      const long long o = 2LL * blockIdx.x + t;
+      const long long o = 2LL * tile + t;
       red_a[o] = top.a[t], red_c[o] = top.c[t], red_s[o] = top.s[t], red_f[o] = top.d[t];
     }
     return;
   }
-  if (t < 2) top.d[t] = ured[2LL * blockIdx.x + t];
+  if (t < 2) top.d[t] = ured[2LL * tile + t];
   pyr.backsolve(t, rows1);
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
@@ -515,6 +535,7 @@ struct BigLevel {
 };
 struct BigSys {
   size_t n = 0;
+  int tt = 256;  // threads per tile of k_tri_tile: 256 (CTA tiles of 2048 rows; measured 4 % faster) or 32 (warp tiles of 256 rows)
   std::vector<BigLevel> levels;  // levels[k]: reduced system of the k-th application of the tile kernel
   double* resid = nullptr;       // refinement residual / explicit-Euler right-hand side
 };
@@ -542,11 +563,13 @@ inline void bigsys_free(BigSys* s) {
 inline int bigsys_prepare(BigSys* s, size_t n) {
   bigsys_free(s);
   s->n = n;
+  if (const char* v = std::getenv("DZB_TILE_THREADS")) s->tt = std::atoi(v) == 32 ? 32 : 256;  // tuning knob
   cudaError_t e;
   size_t m = n;
   while (m > (size_t)BS_MID_CAP) {
     BigLevel l;
-    l.m = 2 * ((m + BS_TILE - 1) / BS_TILE);
+    const size_t tile = (size_t)BS_R * (size_t)s->tt;
+    l.m = 2 * ((m + tile - 1) / tile);
     for (double** p : {&l.a, &l.c, &l.s, &l.f, &l.u})
       if ((e = cudaMalloc((void**)p, l.m * sizeof(double))) != cudaSuccess) return bigsys_fail(e, "cudaMalloc");
     s->levels.push_back(l);
@@ -586,19 +609,29 @@ inline int bigsys_mid(const double* p0, const double* p1, const double* p2, cons
   return bigsys_mid_launch<256, SRC, MODE>(p0, p1, p2, p3, m, out, accum, flags, top8, us, ue, st);
 }
 
-// forward sweeps of every grid level: each application of k_tri_tile leaves 2 rows per 2048
+template <int SRC, bool SOLVE, bool ACCUM>
+inline void bigsys_launch_tile(int tt, size_t m, const double* p0, const double* p1, const double* p2, const double* p3, double* ra,
+                               double* rc, double* rs, double* rf, const double* ured, double* out, int flags, cudaStream_t st) {
+  if (tt == 32) {
+    const size_t tiles = (m + 255) / 256;
+    k_tri_tile<SRC, SOLVE, ACCUM, 32><<<(unsigned)((tiles + 7) / 8), BS_THREADS, 0, st>>>(p0, p1, p2, p3, (long long)m, ra, rc, rs, rf, ured, out, flags);
+  } else {
+    const size_t tiles = (m + BS_TILE - 1) / BS_TILE;
+    k_tri_tile<SRC, SOLVE, ACCUM, 256><<<(unsigned)tiles, BS_THREADS, 0, st>>>(p0, p1, p2, p3, (long long)m, ra, rc, rs, rf, ured, out, flags);
+  }
+}
+
+// forward sweeps of every grid level: each application of k_tri_tile leaves 2 rows per tile
 inline int bigsys_forward(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
                           cudaStream_t st, unsigned long long* launches) {
   cudaError_t e;
   for (size_t k = 0; k < s->levels.size(); ++k) {
     BigLevel& L = s->levels[k];
     if (k == 0) {
-      const unsigned tiles = (unsigned)((s->n + BS_TILE - 1) / BS_TILE);
-      k_tri_tile<BS_SRC_BANDS, false, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, L.a, L.c, L.s, L.f, nullptr, nullptr, flags);
+      bigsys_launch_tile<BS_SRC_BANDS, false, false>(s->tt, s->n, lo, di, up, f, L.a, L.c, L.s, L.f, nullptr, nullptr, flags, st);
     } else {
       BigLevel& Q = s->levels[k - 1];
-      const unsigned tiles = (unsigned)((Q.m + BS_TILE - 1) / BS_TILE);
-      k_tri_tile<BS_SRC_ROWS, false, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, L.a, L.c, L.s, L.f, nullptr, nullptr, flags);
+      bigsys_launch_tile<BS_SRC_ROWS, false, false>(s->tt, Q.m, Q.a, Q.c, Q.s, Q.f, L.a, L.c, L.s, L.f, nullptr, nullptr, flags, st);
     }
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<reduce>");
@@ -612,15 +645,13 @@ inline int bigsys_backward(BigSys* s, const double* lo, const double* di, const 
   for (size_t k = s->levels.size(); k-- > 0;) {
     BigLevel& L = s->levels[k];
     if (k == 0) {
-      const unsigned tiles = (unsigned)((s->n + BS_TILE - 1) / BS_TILE);
       if (accum)
-        k_tri_tile<BS_SRC_BANDS, true, true><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out, flags);
+        bigsys_launch_tile<BS_SRC_BANDS, true, true>(s->tt, s->n, lo, di, up, f, nullptr, nullptr, nullptr, nullptr, L.u, out, flags, st);
       else
-        k_tri_tile<BS_SRC_BANDS, true, false><<<tiles, BS_THREADS, 0, st>>>(lo, di, up, f, (long long)s->n, nullptr, nullptr, nullptr, nullptr, L.u, out, flags);
+        bigsys_launch_tile<BS_SRC_BANDS, true, false>(s->tt, s->n, lo, di, up, f, nullptr, nullptr, nullptr, nullptr, L.u, out, flags, st);
     } else {
       BigLevel& Q = s->levels[k - 1];
-      const unsigned tiles = (unsigned)((Q.m + BS_TILE - 1) / BS_TILE);
-      k_tri_tile<BS_SRC_ROWS, true, false><<<tiles, BS_THREADS, 0, st>>>(Q.a, Q.c, Q.s, Q.f, (long long)Q.m, nullptr, nullptr, nullptr, nullptr, L.u, Q.u, flags);
+      bigsys_launch_tile<BS_SRC_ROWS, true, false>(s->tt, Q.m, Q.a, Q.c, Q.s, Q.f, nullptr, nullptr, nullptr, nullptr, L.u, Q.u, flags, st);
     }
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<solve>");
