@@ -67,3 +67,34 @@ def launch_count(reset=False):
     c = C.c_ulonglong()
     lib.dzb_launch_count(C.byref(c), 1 if reset else 0)
     return c.value
+
+
+class PinnedBuffer:
+    """Page-locked host memory from dzb_host_alloc, viewed as a numpy array (`.array`): a result buffer for
+    `solve(out=...)` / `solve_into(...)` that the D2H copy fills at PCIe speed.  Freed by close() / garbage collection."""
+
+    def __init__(self, shape, dtype="float64"):
+        import ctypes as C
+        import numpy as np
+        from .errors import check
+        self._lib = _lib.load()
+        dt = np.dtype(dtype)
+        count = int(np.prod(shape))
+        self._p = C.c_void_p()
+        check(self._lib.dzb_host_alloc(C.byref(self._p), count * dt.itemsize), self._lib)
+        self._raw = (C.c_char * (count * dt.itemsize)).from_address(self._p.value)
+        self.array = np.frombuffer(self._raw, dtype=dt, count=count).reshape(shape)
+        self.ptr = self._p.value
+
+    def close(self):
+        if self._p:
+            self.array = None
+            self._raw = None
+            self._lib.dzb_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

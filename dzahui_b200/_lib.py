@@ -27,6 +27,8 @@ SIGNATURES = {
     "dzb_set_device": (C.c_int, [C.c_int]),
     "dzb_set_stream": (C.c_int, [C.c_void_p]),
     "dzb_synchronize": (C.c_int, []),
+    "dzb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "dzb_host_free": (C.c_int, [C.c_void_p]),
     "dzb_launch_count": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int]),
     "dzb_mesh_ingest_obj_1d": (C.c_int, [C.c_char_p, C.c_int, C.c_double, C.POINTER(C.c_void_p)]),
     "dzb_mesh_from_nodes": (C.c_int, [c_double_p, C.c_size_t, C.POINTER(C.c_void_p)]),

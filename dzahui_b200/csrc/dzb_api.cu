@@ -530,6 +530,18 @@ int dzb_set_stream(void* s) {
   return DZB_OK;
 }
 int dzb_synchronize(void) { return sync_stream(); }
+// Page-locked host memory for result buffers: a D2H copy into it runs at PCIe speed and asynchronously, into pageable
+// memory (a plain Vec<f64>) the driver stages it at a fraction of that.
+int dzb_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(DZB_INVALID, "null pointer");
+  *ptr = nullptr;
+  CK(cudaMallocHost(ptr, bytes ? bytes : 1));
+  return DZB_OK;
+}
+int dzb_host_free(void* ptr) {
+  if (ptr) CK(cudaFreeHost(ptr));
+  return DZB_OK;
+}
 int dzb_launch_count(unsigned long long* count, int reset) {
   if (count) *count = g_launches;
   if (reset) g_launches = 0;

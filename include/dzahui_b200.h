@@ -65,6 +65,10 @@ int dzb_device_count(int* count);
 int dzb_set_device(int device);            /* one process per GPU: call with LOCAL_RANK before anything else */
 int dzb_set_stream(void* cuda_stream);     /* cudaStream_t all subsequent work is enqueued on (default: stream 0) */
 int dzb_synchronize(void);
+/* page-locked host memory for the buffers handed to dzb_*_solve / dzb_*_state / dzb_*_read: copies into it run at PCIe speed;
+ * any other host pointer works too, only slower (the driver stages pageable memory) */
+int dzb_host_alloc(void** ptr, size_t bytes);
+int dzb_host_free(void* ptr);
 /* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
 int dzb_launch_count(unsigned long long* count, int reset);
 
@@ -172,7 +176,7 @@ int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double
                            const dzb_options* opt, dzb_ensemble** out);
 /* `steps` successive solve(time_step) on every bar, states stay on the device */
 int dzb_ensemble_step(dzb_ensemble* e, double time_step, size_t steps);
-/* one solve(time_step) on every bar; out_host[n_bars][n] holds all states on return (pinned staging inside) */
+/* one solve(time_step) on every bar; out_host[n_bars][n] holds all states on return (use dzb_host_alloc memory for PCIe speed) */
 int dzb_ensemble_solve(dzb_ensemble* e, double time_step, double* out_host, size_t len);
 int dzb_ensemble_state(const dzb_ensemble* e, double* out_host, size_t len);
 int dzb_ensemble_read_bars(const dzb_ensemble* e, const size_t* bar_ids, size_t count, double* out_host);
