@@ -509,6 +509,24 @@ __global__ void k_interface_solve(const double* __restrict__ rows, int m, double
   }
 }
 
+// ---- is the system one the partitioned elimination is reliable on? -------------------------------------------------
+// The chunk sweeps eliminate every chunk on its own (local Dirichlet problems).  That is as stable as serial Thomas
+// for an M-matrix (lo, up <= 0 and the row sum not below -1e-6 of the diagonal: weak dominance up to assembly noise) and
+// for a strictly dominant matrix with positive couplings (the mass matrix); on an indefinite system (e.g. the reference's
+// kink-straddling quadrature on a strongly irregular mesh, or a cell Peclet number above 1) the local problems can be
+// nearly singular while the serial recurrence, which always carries the left boundary along, is not.
+// flags: bit 0 set = not M-like, bit 1 set = not mass-like.  Interior rows only.
+__global__ void __launch_bounds__(256) k_tri_classify(const double* __restrict__ lo, const double* __restrict__ di,
+                                                      const double* __restrict__ up, long long n, int* __restrict__ flags) {
+  int f = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n - 1; i += (long long)gridDim.x * blockDim.x) {
+    const double a = lo[i], b = di[i], c = up[i];
+    if (!(a <= 0.0 && c <= 0.0 && excess3(a, b, c) >= -1e-6 * b)) f |= 1;
+    if (!(a >= 0.0 && c >= 0.0 && b >= 1.25 * (a + c))) f |= 2;
+  }
+  if (f) atomicOr(flags, f);
+}
+
 // ---- explicit-Euler right-hand side of one long bar (utils.rs:41-62, :16-30): b = dt (S u) + (M u) ---------------
 __global__ void __launch_bounds__(256) k_td_rhs(const double* __restrict__ u, const double* __restrict__ mlo,
                                                 const double* __restrict__ mdi, const double* __restrict__ mup,

@@ -255,7 +255,7 @@ struct dzb_ensemble {
   bool prepared = false;
   double prepared_dt = 0.0;
   dzb::BigSys big;  // single long bar (n > 1024) in PARALLEL mode
-  bool use_big = false;
+  bool use_big = false, want_big = false;
 };
 
 struct dzb_solver {
@@ -263,7 +263,8 @@ struct dzb_solver {
   size_t n = 0;
   // static solvers
   double *lo = nullptr, *di = nullptr, *up = nullptr, *rhs = nullptr, *c = nullptr, *den = nullptr, *out = nullptr;
-  bool parallel = false;
+  bool parallel = false;       // the partitioned solver is in use (requested and the matrix allows it)
+  bool want_parallel = false;  // DZB_SOLVE_PARALLEL requested / chosen by AUTO
   int refine_steps = 0;
   dzb::BigSys big;
   // block of a longer bar (SPIKE split across GPUs): the arrays above are views shifted by `off` into allocations that
@@ -426,12 +427,30 @@ int ensemble_step_once(dzb_ensemble* e, double dt) {
   return DZB_OK;
 }
 
+// true when the partitioned solver is reliable on (lo, di, up): an M-matrix or a strictly dominant positive one
+int tri_parallel_ok(const double* lo, const double* di, const double* up, size_t n, bool* ok) {
+  static int* d_flags = nullptr;
+  if (!d_flags) CK(cudaMalloc((void**)&d_flags, sizeof(int)));
+  CK(cudaMemsetAsync(d_flags, 0, sizeof(int), g_stream));
+  dzb::k_tri_classify<<<dzb::bigsys_grid(n), 256, 0, g_stream>>>(lo, di, up, (long long)n, d_flags);
+  LAUNCHED();
+  int f = 0;
+  CK(cudaMemcpyAsync(&f, d_flags, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  *ok = f != 3;  // at least one of the two classes holds on every interior row
+  return DZB_OK;
+}
 // assembly of M and S plus the per-matrix Thomas factors, into the buffers the handle already owns
 int ensemble_assemble(dzb_ensemble* e) {
   dzb::AsmParams P{e->mu, e->b, e->bc0, e->bc1, 0.0, 0.0};
   dzb::AsmOut o{e->slo, e->sdi, e->sup, nullptr, e->mlo, e->mdi, e->mup};
   int rc = launch_assembly<dzb::KIND_TD>(e->d_mesh, e->n, e->B, e->G, e->assembly_mode, P, o, nullptr);
   if (rc) return rc;
+  if (e->want_big) {  // one long bar: the partitioned solver if the mass matrix allows it (it does for linear hats)
+    bool ok = false;
+    if ((rc = tri_parallel_ok(e->mlo, e->mdi, e->mup, e->n, &ok))) return rc;
+    e->use_big = ok;
+  }
   if (!e->use_big) {
     dzb::k_thomas_factor<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)e->n,
                                                                               (long long)e->B);
@@ -480,7 +499,7 @@ int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, 
     return bail(fail(DZB_INVALID, "PARALLEL ensembles support bars of up to 1024 nodes (longer bars: one bar per handle)"));
   e->assembly_mode = opt.assembly_mode;
   if (solve_mode == DZB_SOLVE_PARALLEL && n > 1024) {
-    e->use_big = true;
+    e->want_big = true;
     if (dzb::bigsys_prepare(&e->big, n)) return bail(fail(DZB_CUDA, dzb::bigsys_error()));
   } else if (solve_mode == DZB_SOLVE_PARALLEL) {
     int L = 1;
@@ -695,8 +714,20 @@ static int static_alloc(dzb_solver* s, size_t n) {
     if ((rc = dalloc(p, n))) return rc;
   return DZB_OK;
 }
-static int static_factor(dzb_solver* s) {  // per-matrix work of the serial path (the PARALLEL path has none)
-  if (!s->parallel) {
+// Per-matrix work after (re)assembly: pick the solver the matrix allows, then factor for the serial path.
+static int static_factor(dzb_solver* s) {
+  int rc;
+  s->parallel = s->want_parallel;
+  if (s->want_parallel) {
+    bool ok = false;
+    if ((rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok))) return rc;
+    if (!ok) s->parallel = false;  // indefinite / convection-dominated system: the reference's serial recurrence
+  }
+  if (s->parallel) {
+    if (s->big.n != s->n && dzb::bigsys_prepare(&s->big, s->n)) return fail(DZB_CUDA, dzb::bigsys_error());
+  } else {
+    if (!s->c && (rc = dalloc(&s->c, s->n))) return rc;
+    if (!s->den && (rc = dalloc(&s->den, s->n))) return rc;
     dzb::k_thomas_factor<<<1, 32, 0, g_stream>>>(s->lo, s->di, s->up, s->c, s->den, (long long)s->n, 1);
     LAUNCHED();
   }
@@ -708,16 +739,11 @@ static int static_finish(dzb_solver* s, const dzb_options& opt) {
   if (solve_mode == DZB_SOLVE_AUTO) solve_mode = n <= 65536 ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
   // The Stokes matrix has a cancelling (~0) diagonal: only the serial recurrence started from row 0 is stable on it.
   if (s->kind == dzb::KIND_STOKES) solve_mode = DZB_SOLVE_FAITHFUL;
-  if (solve_mode == DZB_SOLVE_PARALLEL) {
-    s->parallel = true;
-    s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : 0;  // 1e-11 of the exact solution at 10^7 rows without any
-    if (dzb::bigsys_prepare(&s->big, n)) return fail(DZB_CUDA, dzb::bigsys_error());
-  } else {
-    int rc;
-    if ((rc = dalloc(&s->c, n))) return rc;
-    if ((rc = dalloc(&s->den, n))) return rc;
-    if ((rc = static_factor(s))) return rc;
-  }
+  s->want_parallel = solve_mode == DZB_SOLVE_PARALLEL;
+  s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : 0;  // 1e-11 of the exact solution at 10^7 rows without any
+  (void)n;
+  int rc = static_factor(s);
+  if (rc) return rc;
   return sync_stream();
 }
 
@@ -929,6 +955,13 @@ int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right
     s->off = 2 * lead;
     s->lo += s->off, s->di += s->off, s->up += s->off, s->rhs += s->off;
     if (dzb::bigsys_prepare(&s->big, s->n)) rc = fail(DZB_CUDA, dzb::bigsys_error());
+  }
+  if (!rc) {
+    bool ok = false;
+    rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok);
+    if (!rc && !ok)
+      rc = fail(DZB_INVALID, "the block's matrix is neither an M-matrix nor strictly dominant: the partitioned (SPIKE) solver "
+                             "is not reliable on it; solve the bar on one GPU (serial recurrence)");
   }
   if (!rc) rc = sync_stream();
   if (rc) {
