@@ -48,7 +48,7 @@ typedef enum dzb_assembly_mode {
 typedef enum dzb_solve_mode {
   DZB_SOLVE_AUTO = 0,     /* FAITHFUL for small problems (<= 2^16 unknowns in total), PARALLEL beyond */
   DZB_SOLVE_FAITHFUL = 1, /* matrix_solver::solve_by_thomas (mod.rs:17-48) operation for operation, one thread per bar */
-  DZB_SOLVE_PARALLEL = 2  /* ensembles: pre-factored Thomas, per-lane chunk sweeps + warp-shuffle scans of the affine recurrences; long bars: recursive Thomas/PCR-style chunk reduction (registers -> shared memory -> grid) */
+  DZB_SOLVE_PARALLEL = 2  /* ensembles: pre-factored Thomas, per-lane chunk sweeps + warp-shuffle scans of the affine recurrences; long bars: recursive Thomas/PCR-style chunk reduction (registers -> shared memory -> grid), used when the matrix is an M-matrix or strictly dominant (checked on the device after every assembly), the serial recurrence otherwise */
 } dzb_solve_mode;
 
 typedef struct dzb_options {
