@@ -292,3 +292,27 @@ def test_ingest_errors_and_ordering(tmp_path):
     nodes = o.filter_for_solving_1d(m["vertices"])
     assert list(nodes) == [-1.0, 0.0, 0.0, 1.0, 3.0]
     assert not np.signbit(nodes[1]) and np.signbit(nodes[2])
+
+
+def test_quadrature_tables_equal_the_reference_literals(tmp_path):
+    """Build container only (the reference tree is not on the GPU box): the 201 Gauss-Legendre tables the oracle and the
+    product are compiled with (regenerated from first principles by tools/gen_gl_tables.py) equal the reference's 25-30
+    digit literals (quadrature/gauss_legendre.rs:22-5673) bit for bit as f64, and both committed copies are that output."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir("/root/reference/src/lib/solvers/quadrature"):
+        pytest.skip("reference tree not present")
+    try:
+        import mpmath  # noqa: F401
+    except ImportError:
+        pytest.skip("mpmath not installed")
+    out = tmp_path / "gl.h"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_gl_tables.py"), "--check", "/root/reference", "--out", str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " 0 mismatches" in r.stdout
+    gen = out.read_bytes()
+    assert gen == open(os.path.join(root, "oracle", "gl_tables_generated.h"), "rb").read()
+    assert gen == open(os.path.join(root, "dzahui_b200", "csrc", "gl_tables_generated.h"), "rb").read()
