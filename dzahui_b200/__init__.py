@@ -6,7 +6,7 @@ ensemble driver.  All compute is hand-written CUDA reached through the C ABI in 
 from . import _lib
 from .ensemble import EnsembleTimeDependent
 from .errors import CudaError, Error, Integration, Invalid, Io, MeshParse, PieceWiseDims, WrongDims
-from .mesh import Mesh, MeshBuilder
+from .mesh import Mesh, Mesh2D, MeshBuilder
 from .params import (BuilderPanic, DiffussionParams, DiffussionParamsTimeDependent, DiffussionParamsTimeIndependent,
                      StaticPressureParams, StaticPressureParamsBuilder, StokesParams, StokesParams1D, StokesParams1DBuilder)
 from .writer import Writer, format_f64

@@ -42,6 +42,14 @@ SIGNATURES = {
     "dzb_mesh_device_nodes": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "dzb_mesh_update_gradient_1d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_float_p, C.c_size_t]),
     "dzb_mesh_destroy": (None, [C.c_void_p]),
+    "dzb_mesh_ingest_obj_2d": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "dzb_mesh2d_counts": (C.c_int, [C.c_void_p, c_size_p, c_size_p, c_size_p]),
+    "dzb_mesh2d_vertices": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
+    "dzb_mesh2d_indices": (C.c_int, [C.c_void_p, c_u32_p, C.c_size_t]),
+    "dzb_mesh2d_boundary_indices": (C.c_int, [C.c_void_p, c_u32_p, C.c_size_t]),
+    "dzb_mesh2d_info": (C.c_int, [C.c_void_p, c_double_p, c_float_p]),
+    "dzb_mesh2d_destroy": (None, [C.c_void_p]),
+    "dzb_boundary_vertices_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, c_size_p]),
     "dzb_quad_pair": (C.c_int, [C.c_size_t, C.c_size_t, c_double_p, c_double_p]),
     "dzb_quad_table": (C.c_int, [C.c_size_t, c_double_p, c_double_p]),
     "dzb_stokes1d_create": (C.c_int, [C.c_void_p, C.c_double, C.c_double, FORCE_FN, C.c_void_p, C.c_size_t,

@@ -18,6 +18,7 @@
 #include "assembly_kernels.cuh"
 #include "bigsys_kernels.cuh"
 #include "gl_quadrature.h"
+#include "mesh2d_kernels.cuh"
 #include "mesh_ingest.h"
 #include "tridiag_kernels.cuh"
 
@@ -705,6 +706,153 @@ void dzb_mesh_destroy(dzb_mesh* m) {
   if (!m) return;
   dfree(m->d_nodes), dfree(m->d_vertices), dfree(m->d_indices), dfree(m->d_elements), dfree(m->d_vertices_f32), dfree(m->d_minmax);
   delete m;
+}
+
+// ------------------------------------------------------------------------------------------------- 2D meshes (f3)
+struct dzb_mesh2d {
+  size_t n_vertices = 0, n_triangles = 0, n_boundary = 0;
+  double* d_vertices = nullptr;   // 6 V
+  uint32_t* d_indices = nullptr;  // 3 T
+  uint32_t* d_boundary = nullptr; // n_boundary, ascending
+  double max_length = 0.0;
+  float translation[3] = {0.f, 0.f, 0.f};
+};
+
+// boundary vertices of a device-resident triangle list; d_out needs room for n_vertices entries
+static int boundary_vertices_device(const uint32_t* d_tri, size_t n_tri, size_t n_vert, uint32_t* d_out, size_t* n_out) {
+  *n_out = 0;
+  if (n_tri == 0 || n_vert == 0) return DZB_OK;
+  unsigned long long slots = 1024;
+  while (slots < 8ull * n_tri) slots <<= 1;  // 3 T edges at most -> load factor <= 0.375
+  unsigned long long* keys = nullptr;
+  unsigned *cnt = nullptr, *blk = nullptr;
+  unsigned char* flag = nullptr;
+  unsigned long long* d_total = nullptr;
+  const size_t nblk = (n_vert + 1023) / 1024;
+  int rc = DZB_OK;
+  auto cleanup = [&]() {
+    for (void* p : {(void*)keys, (void*)cnt, (void*)blk, (void*)flag, (void*)d_total})
+      if (p) cudaFree(p);
+  };
+#define CK2(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      cleanup();                                                                                    \
+      return fail(DZB_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+    }                                                                                               \
+  } while (0)
+  CK2(cudaMalloc((void**)&keys, slots * sizeof(unsigned long long)));
+  CK2(cudaMalloc((void**)&cnt, slots * sizeof(unsigned)));
+  CK2(cudaMalloc((void**)&flag, n_vert));
+  CK2(cudaMalloc((void**)&blk, nblk * sizeof(unsigned)));
+  CK2(cudaMalloc((void**)&d_total, sizeof(unsigned long long)));
+  CK2(cudaMemsetAsync(keys, 0xff, slots * sizeof(unsigned long long), g_stream));
+  CK2(cudaMemsetAsync(cnt, 0, slots * sizeof(unsigned), g_stream));
+  CK2(cudaMemsetAsync(flag, 0, n_vert, g_stream));
+  const unsigned grid_e = (unsigned)std::min<unsigned long long>((3ull * n_tri + 255) / 256, 148ull * 32);
+  dzb::k_edge_count<<<grid_e, 256, 0, g_stream>>>(d_tri, (long long)n_tri, keys, cnt, slots - 1);
+  ++g_launches;
+  const unsigned grid_s = (unsigned)std::min<unsigned long long>((slots + 255) / 256, 148ull * 32);
+  dzb::k_edge_flag<<<grid_s, 256, 0, g_stream>>>(keys, cnt, slots, flag);
+  ++g_launches;
+  dzb::k_flag_count<<<(unsigned)nblk, 256, 0, g_stream>>>(flag, (long long)n_vert, blk);
+  ++g_launches;
+  dzb::k_block_scan<<<1, 1024, 0, g_stream>>>(blk, (long long)nblk, d_total);
+  ++g_launches;
+  dzb::k_flag_scatter<<<(unsigned)nblk, 256, 0, g_stream>>>(flag, (long long)n_vert, blk, d_out);
+  ++g_launches;
+  unsigned long long total = 0;
+  CK2(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, g_stream));
+  CK2(cudaStreamSynchronize(g_stream));
+  CK2(cudaGetLastError());
+#undef CK2
+  cleanup();
+  *n_out = (size_t)total;
+  return rc;
+}
+
+int dzb_mesh_ingest_obj_2d(const char* path, dzb_mesh2d** out) {
+  if (!out || !path) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  dzb::Ingested2D ing;
+  const dzb::IngestStatus st = dzb::ingest_obj_2d(path, &ing);
+  if (st == dzb::IngestStatus::Io) return fail(DZB_IO, ing.message);
+  if (st == dzb::IngestStatus::Parse) return fail(DZB_MESH_PARSE, ing.message);
+  const size_t V = ing.xy.size() / 2, T = ing.triangles.size() / 3;
+  for (unsigned v : ing.triangles)
+    if (v >= V) return fail(DZB_MESH_PARSE, "a face refers to a vertex that does not exist");
+  dzb_mesh2d* m = new dzb_mesh2d;
+  m->n_vertices = V, m->n_triangles = T, m->max_length = ing.max_length;
+  for (int k = 0; k < 3; ++k) m->translation[k] = ing.translation[k];
+  double* d_xy = nullptr;
+  int rc = dalloc(&m->d_vertices, 6 * V);
+  if (!rc) rc = dalloc(&m->d_indices, 3 * T);
+  if (!rc) rc = dalloc(&m->d_boundary, V);
+  if (!rc) rc = dalloc(&d_xy, 2 * V);
+  if (!rc && V) {
+    if (cudaMemcpyAsync(d_xy, ing.xy.data(), 2 * V * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess ||
+        (T && cudaMemcpyAsync(m->d_indices, ing.triangles.data(), 3 * T * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream) !=
+                  cudaSuccess))
+      rc = fail(DZB_CUDA, "H2D mesh");
+  }
+  if (!rc && V) {
+    dzb::k_mesh2d_vertices<<<blocks_for((long long)V, 256), 256, 0, g_stream>>>(d_xy, (long long)V, m->d_vertices);
+    ++g_launches;
+  }
+  if (!rc) rc = boundary_vertices_device(m->d_indices, T, V, m->d_boundary, &m->n_boundary);
+  if (!rc && m->n_boundary == 0)  // the reference panics inside merge_sort on an empty boundary (mesh_builder.rs:623-632)
+    rc = fail(DZB_MESH_PARSE, "the mesh has no boundary edge");
+  cudaStreamSynchronize(g_stream);
+  dfree(d_xy);
+  if (rc) {
+    dzb_mesh2d_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return DZB_OK;
+}
+int dzb_mesh2d_counts(const dzb_mesh2d* m, size_t* n_vertices, size_t* n_triangles, size_t* n_boundary) {
+  if (!m) return fail(DZB_INVALID, "null pointer");
+  if (n_vertices) *n_vertices = m->n_vertices;
+  if (n_triangles) *n_triangles = m->n_triangles;
+  if (n_boundary) *n_boundary = m->n_boundary;
+  return DZB_OK;
+}
+int dzb_mesh2d_vertices(const dzb_mesh2d* m, double* out, size_t len) {
+  if (!m || !out) return fail(DZB_INVALID, "null pointer");
+  if (len != 6 * m->n_vertices) return fail(DZB_WRONG_DIMS, "vertex buffer length (6 V)");
+  CK(cudaMemcpyAsync(out, m->d_vertices, len * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_mesh2d_indices(const dzb_mesh2d* m, uint32_t* out, size_t len) {
+  if (!m || !out) return fail(DZB_INVALID, "null pointer");
+  if (len != 3 * m->n_triangles) return fail(DZB_WRONG_DIMS, "index buffer length (3 T)");
+  CK(cudaMemcpyAsync(out, m->d_indices, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_mesh2d_boundary_indices(const dzb_mesh2d* m, uint32_t* out, size_t len) {
+  if (!m || !out) return fail(DZB_INVALID, "null pointer");
+  if (len != m->n_boundary) return fail(DZB_WRONG_DIMS, "boundary buffer length");
+  CK(cudaMemcpyAsync(out, m->d_boundary, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream));
+  return sync_stream();
+}
+int dzb_mesh2d_info(const dzb_mesh2d* m, double* max_length, float translation[3]) {
+  if (!m) return fail(DZB_INVALID, "null pointer");
+  if (max_length) *max_length = m->max_length;
+  if (translation)
+    for (int k = 0; k < 3; ++k) translation[k] = m->translation[k];
+  return DZB_OK;
+}
+void dzb_mesh2d_destroy(dzb_mesh2d* m) {
+  if (!m) return;
+  dfree(m->d_vertices), dfree(m->d_indices), dfree(m->d_boundary);
+  delete m;
+}
+// the detection alone, on a device-resident triangle list (large meshes that never were an .obj file)
+int dzb_boundary_vertices_device(const uint32_t* d_triangles, size_t n_triangles, size_t n_vertices, uint32_t* d_out, size_t* n_out) {
+  if (!d_triangles || !d_out || !n_out) return fail(DZB_INVALID, "null pointer");
+  return boundary_vertices_device(d_triangles, n_triangles, n_vertices, d_out, n_out);
 }
 
 // ------------------------------------------------------------------------------------------------- static solvers

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <unordered_set>
+#include <utility>
 
 namespace dzb {
 namespace {
@@ -169,6 +170,120 @@ IngestStatus ingest_obj_1d(const char* path, bool has_multiplier, double multipl
   const float mid1 = (float)out->prom_width / 2.0f;
   out->translation[0] = -mid0;
   out->translation[1] = -mid1;
+  out->translation[2] = 0.0f;
+  return IngestStatus::Ok;
+}
+
+IngestStatus ingest_obj_2d(const char* path, Ingested2D* out) {
+  std::FILE* f = std::fopen(path, "rb");
+  if (!f) {
+    out->message = std::string("cannot open ") + path;
+    return IngestStatus::Io;
+  }
+  std::string text;
+  char buf[1 << 16];
+  size_t got;
+  while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, got);
+  std::fclose(f);
+
+  std::vector<VertexLine> vs;
+  std::unordered_set<std::string> keys[3];
+  size_t pos = 0;
+  auto fields = [&](size_t s, size_t end, std::vector<std::pair<size_t, size_t>>* out_f) {  // str::split(" ") after the tag
+    out_f->clear();
+    for (;;) {
+      size_t sp = text.find(' ', s);
+      if (sp == std::string::npos || sp > end) sp = end;
+      out_f->push_back({s, sp});
+      if (sp == end) break;
+      s = sp + 1;
+    }
+  };
+  std::vector<std::pair<size_t, size_t>> fl;
+  while (pos < text.size()) {
+    size_t eol = text.find('\n', pos);
+    if (eol == std::string::npos) eol = text.size();
+    size_t end = eol;
+    if (end > pos && text[end - 1] == '\r') --end;
+    if (end - pos >= 2 && text[pos] == 'v' && text[pos + 1] == ' ') {
+      fields(pos + 2, end, &fl);
+      VertexLine vl;
+      bool ok = true;
+      for (size_t k = 0; k < fl.size(); ++k) {
+        double v;
+        if (!parse_rust_float(text.data() + fl[k].first, text.data() + fl[k].second, &v)) ok = false;
+        if (k < 3) vl.token[k].assign(text, fl[k].first, fl[k].second - fl[k].first), vl.value[k] = v;
+      }
+      if (!ok) {
+        out->message = "Error while parsing vertex coordinate from obj";
+        return IngestStatus::Parse;
+      }
+      if (fl.size() != 3) {
+        out->message = "A vertex line should contain 3 elements only";
+        return IngestStatus::Parse;
+      }
+      for (int a = 0; a < 3; ++a) {
+        const std::string& t = vl.token[a];
+        keys[a].insert((t.compare(0, 3, "0.0") == 0 || t.compare(0, 4, "-0.0") == 0) ? std::string("0.0") : t);
+      }
+      vs.push_back(std::move(vl));
+    } else if (end - pos >= 2 && text[pos] == 'f' && text[pos + 1] == ' ') {
+      fields(pos + 2, end, &fl);
+      if (fl.size() != 3) {
+        out->message = "Amount of face specificating elements should be 3.";
+        return IngestStatus::Parse;
+      }
+      for (size_t k = 0; k < 3; ++k) {  // a/b/c: the first field is the vertex, exactly two more must follow
+        const size_t b = fl[k].first, e = fl[k].second;
+        size_t slash = text.find('/', b);
+        if (slash == std::string::npos || slash > e) slash = e;
+        unsigned long long v = 0;
+        size_t i = b;
+        if (i < slash && text[i] == '+') ++i;
+        bool ok = i < slash;
+        for (; i < slash; ++i) {
+          if (text[i] < '0' || text[i] > '9') { ok = false; break; }
+          v = v * 10 + (unsigned)(text[i] - '0');
+          if (v > 0xffffffffULL) { ok = false; break; }
+        }
+        if (!ok) {
+          out->message = "Error while parsing face coordinate";
+          return IngestStatus::Parse;
+        }
+        size_t extra = 0;
+        for (size_t j = slash; j < e; ++j) extra += text[j] == '/';
+        if (extra != 2) {
+          out->message = "Amount of elements per face specification should be 3 in format a/b/c.";
+          return IngestStatus::Parse;
+        }
+        out->triangles.push_back((unsigned)v - 1u);
+      }
+    }
+    pos = eol + 1;
+  }
+  int cc;  // :355-363
+  if (keys[0].size() == 1) cc = 0;
+  else if (keys[1].size() == 1) cc = 1;
+  else if (keys[2].size() == 1) cc = 2;
+  else {
+    out->message = "Only coordinates over a plane paralell to x, y or z plane are accepted. Check .obj file.";
+    return IngestStatus::Parse;
+  }
+  out->constant_axis = cc;
+  double x_min = 0.0, y_min = 0.0, x_max = 0.0, y_max = 0.0;  // all start at 0.0 (:366-371)
+  out->xy.reserve(2 * vs.size());
+  for (const VertexLine& vl : vs) {
+    const double a = vl.value[cc == 0 ? 1 : 0], b = vl.value[cc == 2 ? 1 : 2];
+    if (a < x_min) x_min = a;
+    if (a > x_max) x_max = a;
+    if (b < y_min) y_min = b;
+    if (b > y_max) y_max = b;
+    out->xy.push_back(a), out->xy.push_back(b);
+  }
+  const double len_x = x_max - x_min, len_y = y_max - y_min;
+  out->max_length = len_x > len_y ? len_x : len_y;
+  out->translation[0] = (float)x_min + (float)out->max_length / 2.0f;
+  out->translation[1] = (float)y_min + (float)out->max_length / 2.0f;
   out->translation[2] = 0.0f;
   return IngestStatus::Ok;
 }

@@ -20,4 +20,16 @@ struct Ingested1D {
 
 IngestStatus ingest_obj_1d(const char* path, bool has_multiplier, double multiplier, Ingested1D* out);
 
+// Host half of MeshBuilder::build_mesh_2d (mesh/mesh_builder.rs:342-466, obj_face_checker :89-129): text -> the two kept
+// coordinates of every vertex, the 0-based triangle list, and the viewing scalars.  Boundary detection runs on the device.
+struct Ingested2D {
+  std::vector<double> xy;           // 2 per vertex, file order
+  std::vector<unsigned> triangles;  // 3 per triangle
+  int constant_axis = 2;
+  double max_length = 0.0;                 // :455-461
+  float translation[3] = {0.f, 0.f, 0.f};  // :464-465, :483-487
+  std::string message;
+};
+IngestStatus ingest_obj_2d(const char* path, Ingested2D* out);
+
 }  // namespace dzb

@@ -92,9 +92,60 @@ class Mesh:
             pass
 
 
+class Mesh2D:
+    """A planar triangle mesh on the device (`MeshBuilder::build_mesh_2d`, mesh_builder.rs:342-500): GL vertices
+    [a, b, 0, r, g, b] per vertex, triangle indices, and the sorted boundary vertices."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+        nv, nt, nb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(lib.dzb_mesh2d_counts(handle, C.byref(nv), C.byref(nt), C.byref(nb)), lib)
+        self.n_vertices, self.n_triangles, self.n_boundary = nv.value, nt.value, nb.value
+        ml = C.c_double()
+        tr = (C.c_float * 3)()
+        check(lib.dzb_mesh2d_info(handle, C.byref(ml), tr), lib)
+        self.max_length = ml.value
+        self.model_translation = np.array(list(tr), dtype=np.float32)
+
+    @property
+    def vertices(self):
+        out = np.empty(6 * self.n_vertices)
+        check(self._lib.dzb_mesh2d_vertices(self._h, out.ctypes.data_as(_lib.c_double_p), out.size), self._lib)
+        return out
+
+    @property
+    def indices(self):
+        out = np.empty(3 * self.n_triangles, dtype=np.uint32)
+        check(self._lib.dzb_mesh2d_indices(self._h, out.ctypes.data_as(_lib.c_u32_p), out.size), self._lib)
+        return out
+
+    @property
+    def boundary_indices(self):
+        out = np.empty(self.n_boundary, dtype=np.uint32)
+        check(self._lib.dzb_mesh2d_boundary_indices(self._h, out.ctypes.data_as(_lib.c_u32_p), out.size), self._lib)
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.dzb_mesh2d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class MeshBuilder:
     def __init__(self, location):
         self.location = str(location)
+
+    def build_mesh_2d(self):
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.dzb_mesh_ingest_obj_2d(self.location.encode(), C.byref(h)), lib)
+        return Mesh2D(h, lib)
 
     def build_mesh_1d(self, height_multiplier=None):
         lib = _lib.load()

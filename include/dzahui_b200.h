@@ -35,6 +35,7 @@ typedef enum dzb_status {
 
 typedef struct dzb_mesh dzb_mesh;         /* mesh::Mesh (mesh/mod.rs:30-37), 1D part, device resident */
 typedef struct dzb_solver dzb_solver;     /* Box<dyn DiffEquationSolver> (solvers/solver_trait.rs:12-23) */
+typedef struct dzb_mesh2d dzb_mesh2d;     /* mesh::Mesh of a planar triangle mesh (viewer only in the reference) */
 typedef struct dzb_ensemble dzb_ensemble; /* many independent DiffussionSolverTimeDependent bars stepped together */
 
 /* How the element integrals are evaluated on the device. */
@@ -92,6 +93,20 @@ int dzb_mesh_device_nodes(const dzb_mesh* m, const double** device_ptr);
  * colours the device-resident vertex buffer from |solution| and returns the f32[12n] buffer a renderer uploads. */
 int dzb_mesh_update_gradient_1d(dzb_mesh* m, const double* device_solution, size_t n, float* out_vertices_f32, size_t len);
 void dzb_mesh_destroy(dzb_mesh* m);
+
+/* ---- 2D ingestion: MeshBuilder::build_mesh_2d (mesh/mesh_builder.rs:342-500, obj_face_checker :89-129, merge_sort :623-680) ---- */
+/* Parses `v` and `f a/b/c` lines, drops the constant axis, and leaves on the device the GL vertices f64[6V] ([a,b,0,0,0,1]),
+ * the 0-based triangle indices u32[3T] and the ascending, duplicate-free list of boundary vertices (end points of the
+ * edges that belong to exactly one triangle), found with a device hash table instead of the reference's HashMap + sort. */
+int dzb_mesh_ingest_obj_2d(const char* path, dzb_mesh2d** out);
+int dzb_mesh2d_counts(const dzb_mesh2d* m, size_t* n_vertices, size_t* n_triangles, size_t* n_boundary);
+int dzb_mesh2d_vertices(const dzb_mesh2d* m, double* out, size_t len);           /* Mesh.vertices, len = 6V */
+int dzb_mesh2d_indices(const dzb_mesh2d* m, uint32_t* out, size_t len);          /* Mesh.indices,  len = 3T */
+int dzb_mesh2d_boundary_indices(const dzb_mesh2d* m, uint32_t* out, size_t len); /* Mesh.boundary_indices */
+int dzb_mesh2d_info(const dzb_mesh2d* m, double* max_length, float translation[3]);
+void dzb_mesh2d_destroy(dzb_mesh2d* m);
+/* the boundary detection alone on a device-resident triangle list; d_out needs room for n_vertices entries */
+int dzb_boundary_vertices_device(const uint32_t* d_triangles, size_t n_triangles, size_t n_vertices, uint32_t* d_out, size_t* n_out);
 
 /* ---- quadrature: gauss_legendre::quad_pair (quadrature/gauss_legendre.rs:5908-5927) ------------------------- */
 int dzb_quad_pair(size_t n, size_t k, double* theta, double* weight);

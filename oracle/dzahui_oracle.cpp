@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <set>
 #include <string>
 
@@ -906,6 +907,114 @@ int dzo_thomas_f80(const double* lo, const double* di, const double* up, const d
   return thomas_ext<long double>(lo, di, up, b, n, out);
 }
 
+// ---- 2D ingestion ("next" row f3): mesh/mesh_builder.rs:342-500 (build_mesh_2d), :89-129 (obj_face_checker),
+// :623-680 (merge_sort).  Boundary vertices = vertices of the edges that belong to exactly one triangle.
+struct Mesh2D {
+  std::vector<double> vertices;            // [a, b, 0, 0, 0, 1] per vertex
+  std::vector<uint32_t> indices;           // 3 per triangle, 0-based
+  std::vector<uint32_t> boundary_indices;  // ascending, unique
+  double max_length = 0;
+  float model_translation[3] = {0, 0, 0};
+};
+static bool rust_parse_u32(const std::string& s, uint32_t* out) {  // str::parse::<u32>: optional '+', digits only, no overflow
+  size_t i = 0;
+  if (i < s.size() && s[i] == '+') ++i;
+  if (i >= s.size()) return false;
+  unsigned long long v = 0;
+  for (; i < s.size(); ++i) {
+    if (s[i] < '0' || s[i] > '9') return false;
+    v = v * 10 + (unsigned)(s[i] - '0');
+    if (v > 0xffffffffULL) return false;
+  }
+  *out = (uint32_t)v;
+  return true;
+}
+static int build_mesh_2d(const char* path, Mesh2D* m) {
+  std::vector<std::string> lines;
+  if (!read_lines(path, &lines)) return IO;
+  std::vector<std::string> parts;
+  std::set<std::string> keys[3];  // check_for_constant_coordinates :140-190
+  for (const std::string& line : lines) {
+    if (line.rfind("v ", 0) != 0) continue;
+    split_single_space(line, &parts);
+    if (parts.size() - 1 != 3) return MESH_PARSE;
+    for (int a = 0; a < 3; ++a) {
+      const std::string& c = parts[a + 1];
+      double tmp;
+      if (!rust_parse_f64(c, &tmp)) return MESH_PARSE;
+      keys[a].insert((c.rfind("0.0", 0) == 0 || c.rfind("-0.0", 0) == 0) ? std::string("0.0") : c);
+    }
+  }
+  int constant_coordinate;  // :355-363
+  if (keys[0].size() == 1) constant_coordinate = 0;
+  else if (keys[1].size() == 1) constant_coordinate = 1;
+  else if (keys[2].size() == 1) constant_coordinate = 2;
+  else return MESH_PARSE;
+  double x_min = 0.0, y_min = 0.0, x_max = 0.0, y_max = 0.0;  // :366-371 — all start at 0.0
+  std::map<std::pair<uint32_t, uint32_t>, size_t> boundary_edges;  // HashMap<[u32;2], usize> (iteration order is irrelevant: sorted later)
+  auto count_edge = [&](uint32_t p, uint32_t q) {  // :417-446: (p,q), else (q,p), else insert (p,q)
+    auto it = boundary_edges.find({p, q});
+    if (it != boundary_edges.end()) { ++it->second; return; }
+    it = boundary_edges.find({q, p});
+    if (it != boundary_edges.end()) { ++it->second; return; }
+    boundary_edges[{p, q}] = 1;
+  };
+  for (const std::string& line : lines) {
+    if (line.rfind("v ", 0) == 0) {
+      split_single_space(line, &parts);
+      std::vector<double> coordinate;
+      for (size_t t = 1; t < parts.size(); ++t) {
+        double v;
+        if (!rust_parse_f64(parts[t], &v)) return MESH_PARSE;
+        coordinate.push_back(v);
+      }
+      if (coordinate.size() != 3) return MESH_PARSE;
+      coordinate.erase(coordinate.begin() + constant_coordinate);  // :388-389
+      coordinate.push_back(0.0);
+      if (coordinate[0] < x_min) x_min = coordinate[0];  // :392-407
+      if (coordinate[0] > x_max) x_max = coordinate[0];
+      if (coordinate[1] < y_min) y_min = coordinate[1];
+      if (coordinate[1] > y_max) y_max = coordinate[1];
+      m->vertices.insert(m->vertices.end(), coordinate.begin(), coordinate.end());
+      m->vertices.push_back(0.0), m->vertices.push_back(0.0), m->vertices.push_back(1.0);  // blue :411
+    } else if (line.rfind("f ", 0) == 0) {
+      split_single_space(line, &parts);  // obj_face_checker :89-129
+      if (parts.size() - 1 != 3) return MESH_PARSE;
+      uint32_t tri[3];
+      for (int k = 0; k < 3; ++k) {
+        std::vector<std::string> fp;
+        size_t start = 0;
+        const std::string& face = parts[k + 1];
+        for (;;) {  // str::split("/")
+          const size_t pos = face.find('/', start);
+          if (pos == std::string::npos) { fp.push_back(face.substr(start)); break; }
+          fp.push_back(face.substr(start, pos - start));
+          start = pos + 1;
+        }
+        uint32_t v;
+        if (!rust_parse_u32(fp[0], &v)) return MESH_PARSE;
+        if (fp.size() - 1 != 2) return MESH_PARSE;
+        tri[k] = v - 1;
+      }
+      count_edge(tri[0], tri[1]);
+      count_edge(tri[0], tri[2]);
+      count_edge(tri[2], tri[1]);
+      m->indices.insert(m->indices.end(), tri, tri + 3);
+    }
+  }
+  const double len_x = x_max - x_min, len_y = y_max - y_min;  // :455-461
+  m->max_length = len_x > len_y ? len_x : len_y;
+  m->model_translation[0] = (float)x_min + (float)m->max_length / 2.0f;  // :464-465
+  m->model_translation[1] = (float)y_min + (float)m->max_length / 2.0f;
+  m->model_translation[2] = 0.0f;
+  std::set<uint32_t> b;  // :468-478 HashSet of the vertices of the edges counted once; merge_sort -> ascending
+  for (const auto& kv : boundary_edges)
+    if (kv.second == 1) b.insert(kv.first.first), b.insert(kv.first.second);
+  if (b.empty()) return MESH_PARSE;  // the reference panics inside merge_sort on an empty vector
+  m->boundary_indices.assign(b.begin(), b.end());
+  return OK;
+}
+
 // ---- mesh ingestion.  Two-call protocol: n_out = number of nodes; buffers sized 12n / 6n-6.
 int dzo_mesh_ingest_1d(const char* path, int has_mult, double mult, size_t* n_out, double* vertices, size_t vcap,
                        uint32_t* indices, size_t icap, double* max_length, double* prom_width, float* translation) {
@@ -921,6 +1030,46 @@ int dzo_mesh_ingest_1d(const char* path, int has_mult, double mult, size_t* n_ou
     *prom_width = m.prom_width;
     for (int k = 0; k < 3; ++k) translation[k] = m.model_translation[k];
   }
+  return OK;
+}
+// Two-call protocol like dzo_mesh_ingest_1d: counts first (buffers NULL), then data.
+int dzo_mesh_ingest_2d(const char* path, size_t* n_vertices, size_t* n_triangles, size_t* n_boundary, double* vertices,
+                       uint32_t* indices, uint32_t* boundary, double* max_length, float* translation) {
+  Mesh2D m;
+  int rc = build_mesh_2d(path, &m);
+  if (rc) return rc;
+  *n_vertices = m.vertices.size() / 6, *n_triangles = m.indices.size() / 3, *n_boundary = m.boundary_indices.size();
+  if (vertices) {
+    std::memcpy(vertices, m.vertices.data(), m.vertices.size() * sizeof(double));
+    std::memcpy(indices, m.indices.data(), m.indices.size() * sizeof(uint32_t));
+    std::memcpy(boundary, m.boundary_indices.data(), m.boundary_indices.size() * sizeof(uint32_t));
+    *max_length = m.max_length;
+    for (int k = 0; k < 3; ++k) translation[k] = m.model_translation[k];
+  }
+  return OK;
+}
+// the same boundary detection on an in-memory triangle list (CPU baseline for large synthetic meshes)
+int dzo_boundary_vertices(const uint32_t* tris, size_t n_triangles, uint32_t* out, size_t cap, size_t* n_out) {
+  std::map<std::pair<uint32_t, uint32_t>, size_t> edges;
+  auto count_edge = [&](uint32_t p, uint32_t q) {
+    auto it = edges.find({p, q});
+    if (it != edges.end()) { ++it->second; return; }
+    it = edges.find({q, p});
+    if (it != edges.end()) { ++it->second; return; }
+    edges[{p, q}] = 1;
+  };
+  for (size_t t = 0; t < n_triangles; ++t) {
+    count_edge(tris[3 * t], tris[3 * t + 1]);
+    count_edge(tris[3 * t], tris[3 * t + 2]);
+    count_edge(tris[3 * t + 2], tris[3 * t + 1]);
+  }
+  std::set<uint32_t> b;
+  for (const auto& kv : edges)
+    if (kv.second == 1) b.insert(kv.first.first), b.insert(kv.first.second);
+  *n_out = b.size();
+  if (b.size() > cap) return WRONG_DIMS;
+  size_t k = 0;
+  for (uint32_t v : b) out[k++] = v;
   return OK;
 }
 // mesh/mod.rs:54-68 — every 6th value of the first half

@@ -21,7 +21,7 @@ import oracle_lib as o  # noqa: E402
 from dzahui_b200 import synthetic  # noqa: E402
 
 ASSETS = ["1dbar.obj", "1dbar_irregular.obj", "1dbar_irregular_small.obj", "1dbar_many_divisions.obj",
-          "1dbar_many_divisions_irregular.obj", "big_mesh.obj"]
+          "1dbar_many_divisions_irregular.obj", "big_mesh.obj", "test.obj", "trapezoid.obj", "untitled.obj"]
 
 
 def L(a):
@@ -55,6 +55,19 @@ def main():
                       max_length=m["max_length"], prom_width=m["prom_width"], translation=L(m["translation"]),
                       nodes=L(o.filter_for_solving_1d(m["vertices"])))
     g["ingest"] = ing
+
+    # ---- 2D ingestion: build_mesh_2d on the planar meshes the reference ships
+    ing2 = {}
+    for a in ("big_mesh.obj", "test.obj", "trapezoid.obj", "untitled.obj"):
+        try:
+            m = o.mesh_ingest_2d(os.path.join(adir, a))
+        except o.OracleError as e:
+            ing2[a] = dict(error=e.code)
+            continue
+        ing2[a] = dict(n_vertices=m["n_vertices"], n_triangles=m["n_triangles"], vertices=L(m["vertices"]),
+                       indices=[int(v) for v in m["indices"]], boundary_indices=[int(v) for v in m["boundary_indices"]],
+                       max_length=m["max_length"], translation=L(m["translation"]))
+    g["ingest2d"] = ing2
 
     # ---- quadrature
     g["quad"] = {str(G): dict(x=L(o.quad_table(G)[0]), w=L(o.quad_table(G)[1])) for G in (2, 3, 7, 50, 99, 100, 101, 150, 350, 600)}

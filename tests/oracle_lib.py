@@ -218,3 +218,30 @@ def update_gradient_1d(vertices, velocity_norm):
     s = _arr(velocity_norm)
     lib().dzo_update_gradient_1d(_p(v), C.c_size_t(len(v)), _p(s), C.c_size_t(len(s)))
     return v
+
+
+def mesh_ingest_2d(path):
+    """MeshBuilder::build_mesh_2d (mesh_builder.rs:342-500) -> dict(vertices, indices, boundary_indices, max_length, translation)"""
+    nv, nt, nb = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    _chk(lib().dzo_mesh_ingest_2d(path.encode(), C.byref(nv), C.byref(nt), C.byref(nb), None, None, None, None, None))
+    v = np.zeros(6 * nv.value)
+    idx = np.zeros(3 * nt.value, dtype=np.uint32)
+    bnd = np.zeros(nb.value, dtype=np.uint32)
+    ml = C.c_double()
+    tr = (C.c_float * 3)()
+    u32p = C.POINTER(C.c_uint32)
+    _chk(lib().dzo_mesh_ingest_2d(path.encode(), C.byref(nv), C.byref(nt), C.byref(nb), _p(v), idx.ctypes.data_as(u32p),
+                                  bnd.ctypes.data_as(u32p), C.byref(ml), tr))
+    return dict(n_vertices=nv.value, n_triangles=nt.value, vertices=v, indices=idx, boundary_indices=bnd, max_length=ml.value,
+                translation=np.array(list(tr), dtype=np.float32))
+
+
+def boundary_vertices(triangles):
+    """the reference's edge-count boundary detection on an in-memory triangle list [T][3]"""
+    t = np.ascontiguousarray(np.asarray(triangles, dtype=np.uint32)).reshape(-1, 3)
+    out = np.zeros(int(t.max()) + 1 if t.size else 0, dtype=np.uint32)
+    n = C.c_size_t(0)
+    u32p = C.POINTER(C.c_uint32)
+    _chk(lib().dzo_boundary_vertices(t.ctypes.data_as(u32p), C.c_size_t(t.shape[0]), out.ctypes.data_as(u32p), C.c_size_t(out.size),
+                                     C.byref(n)))
+    return out[:n.value].copy()

@@ -316,3 +316,31 @@ def test_quadrature_tables_equal_the_reference_literals(tmp_path):
     gen = out.read_bytes()
     assert gen == open(os.path.join(root, "oracle", "gl_tables_generated.h"), "rb").read()
     assert gen == open(os.path.join(root, "dzahui_b200", "csrc", "gl_tables_generated.h"), "rb").read()
+
+
+# ---------------------------------------------------------------- 2D ingestion, mesh_builder.rs:342-500
+def test_oracle_2d_ingestion_known_answers(assets_dir, golden, tmp_path):
+    """independent pins of the restated build_mesh_2d: every vertex of a lone triangle / a two-triangle trapezoid is on
+    the boundary; the boundary of big_mesh.obj (an 11 x 11 planar grid, 200 triangles) is its 40 perimeter vertices"""
+    t = o.mesh_ingest_2d(f"{assets_dir}/test.obj")
+    assert list(t["boundary_indices"]) == [0, 1, 2] and list(t["indices"]) == [0, 1, 2]
+    assert list(t["vertices"]) == [-1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]
+    assert t["max_length"] == 2.0 and list(t["translation"]) == [0.0, 1.0, 0.0]     # x_min + 2/2, y_min(=0.0) + 2/2
+    z = o.mesh_ingest_2d(f"{assets_dir}/trapezoid.obj")
+    assert list(z["boundary_indices"]) == [0, 1, 2, 3]
+    b = o.mesh_ingest_2d(f"{assets_dir}/big_mesh.obj")
+    assert (b["n_vertices"], b["n_triangles"]) == (121, 200)
+    xy = b["vertices"].reshape(-1, 6)[:, :2]
+    on_edge = (xy[:, 0] == xy[:, 0].min()) | (xy[:, 0] == xy[:, 0].max()) | (xy[:, 1] == xy[:, 1].min()) | (xy[:, 1] == xy[:, 1].max())
+    assert list(b["boundary_indices"]) == list(np.nonzero(on_edge)[0]) and len(b["boundary_indices"]) == 40
+    assert np.all(b["vertices"].reshape(-1, 6)[:, 2:] == [0.0, 0.0, 0.0, 1.0])
+    for name, g in golden["ingest2d"].items():
+        m = o.mesh_ingest_2d(f"{assets_dir}/{name}")
+        assert list(m["boundary_indices"]) == g["boundary_indices"] and list(m["indices"]) == g["indices"]
+        assert m["vertices"].tobytes() == np.array(g["vertices"]).tobytes() and m["max_length"] == g["max_length"]
+    # the in-memory variant agrees with the file variant
+    assert list(o.boundary_vertices(b["indices"].reshape(-1, 3))) == list(b["boundary_indices"])
+    nofaces = tmp_path / "nofaces.obj"
+    nofaces.write_text("v 0.5 0.0 1.0\nv 1.0 0.5 1.0\nv 0.25 1.0 1.0\n")
+    with pytest.raises(o.OracleError):          # no `f` lines: no boundary edge (the reference panics inside merge_sort)
+        o.mesh_ingest_2d(str(nofaces))
