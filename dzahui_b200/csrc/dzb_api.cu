@@ -185,14 +185,10 @@ __global__ void k_mesh_tables(const double* __restrict__ nodes, long long n, dou
     if (i < n - 1) elements[2 * i] = u, elements[2 * i + 1] = u + 1;  // element e = (node e, node e+1)
   }
 }
-// Mesh::update_gradient_1d (mesh/mod.rs:73-90): min/max of |u| by one CTA, then the colour map + f32 cast.
-__global__ void k_absminmax(const double* __restrict__ u, long long n, double* __restrict__ mm) {
+// Mesh::update_gradient_1d (mesh/mod.rs:73-90): min/max of |u| (grid-wide partials, then one CTA), then the colour map
+// + f32 cast.  mm[0] = min, mm[1] = max; part[] holds 2 doubles per block of the first pass.
+__device__ __forceinline__ void block_minmax(double lo, double hi, double* out) {
   __shared__ double smin[256], smax[256];
-  double lo = INFINITY, hi = -INFINITY;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const double a = fabs(u[i]);
-    lo = fmin(lo, a), hi = fmax(hi, a);
-  }
   smin[threadIdx.x] = lo, smax[threadIdx.x] = hi;
   __syncthreads();
   for (int s = blockDim.x / 2; s > 0; s >>= 1) {
@@ -202,7 +198,20 @@ __global__ void k_absminmax(const double* __restrict__ u, long long n, double* _
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) mm[0] = smin[0], mm[1] = smax[0];
+  if (threadIdx.x == 0) out[0] = smin[0], out[1] = smax[0];
+}
+__global__ void __launch_bounds__(256) k_absminmax(const double* __restrict__ u, long long n, double* __restrict__ part) {
+  double lo = INFINITY, hi = -INFINITY;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = fabs(u[i]);
+    lo = fmin(lo, a), hi = fmax(hi, a);
+  }
+  block_minmax(lo, hi, part + 2 * blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_absminmax_final(const double* __restrict__ part, int n_parts, double* __restrict__ mm) {
+  double lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) lo = fmin(lo, part[2 * i]), hi = fmax(hi, part[2 * i + 1]);
+  block_minmax(lo, hi, mm);
 }
 __global__ void k_gradient(const double* __restrict__ u, long long n, const double* __restrict__ mm, double* __restrict__ vertices,
                            float* __restrict__ vf) {
@@ -694,8 +703,12 @@ int dzb_mesh_update_gradient_1d(dzb_mesh* m, const double* d_solution, size_t n,
   if (!m->d_vertices || n != m->n || len != 12 * m->n) return fail(DZB_WRONG_DIMS, "gradient buffers");
   int rc;
   if (!m->d_vertices_f32 && (rc = dalloc(&m->d_vertices_f32, 12 * n))) return rc;
-  if (!m->d_minmax && (rc = dalloc(&m->d_minmax, 2))) return rc;
-  k_absminmax<<<1, 256, 0, g_stream>>>(d_solution, (long long)n, m->d_minmax);
+  constexpr int MAX_PARTS = 148 * 4;
+  if (!m->d_minmax && (rc = dalloc(&m->d_minmax, 2 + 2 * MAX_PARTS))) return rc;
+  const int parts = (int)std::min<long long>(MAX_PARTS, ((long long)n + 255) / 256);
+  k_absminmax<<<parts, 256, 0, g_stream>>>(d_solution, (long long)n, m->d_minmax + 2);
+  LAUNCHED();
+  k_absminmax_final<<<1, 256, 0, g_stream>>>(m->d_minmax + 2, parts, m->d_minmax);
   LAUNCHED();
   k_gradient<<<blocks_for((long long)n, 256), 256, 0, g_stream>>>(d_solution, (long long)n, m->d_minmax, m->d_vertices, m->d_vertices_f32);
   LAUNCHED();
