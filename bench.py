@@ -354,6 +354,10 @@ def main():
                    if dof * 56 > 2.6e8 else "working set may fit L2", "e2e_steps": e2e_steps,
                    "e2e_call": "dzb_ensemble_solve(dt, host_out)" if args.workload == "c5" else
                    "dzb_mesh_set_nodes(host_x) + dzb_solver_rebuild + dzb_solver_solve(host_out)",
+                   "e2e_inputs": ("solve(dt) takes one scalar: the bars' state and operators live on the device by the API's nature, so a "
+                                  "step has no H2D; the one-off H2D of meshes + initial conditions (1.07 GB) and the assembly are charged "
+                                  "in extra.e2e_including_create") if args.workload == "c5" else
+                                 "node coordinates H2D (pinned) + assembly + solve + nodal values D2H (pinned) every step",
                    "parallelism": f"{world} independent slices, no collective"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / e2e_steps * 1e3},
