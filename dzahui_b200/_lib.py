@@ -16,7 +16,7 @@ FORCE_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
 
 class Options(C.Structure):
-    _fields_ = [("assembly_mode", C.c_int), ("solve_mode", C.c_int), ("refine_steps", C.c_int), ("reserved", C.c_int)]
+    _fields_ = [("assembly_mode", C.c_int), ("solve_mode", C.c_int), ("refine_steps", C.c_int), ("stored_operators", C.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/dzahui_b200.h declares (tests/test_abi.py checks it)

@@ -114,7 +114,7 @@ dzb_options resolve_options(const dzb_options* opt) {
 }
 bool options_valid(const dzb_options& o) {
   return o.assembly_mode >= 0 && o.assembly_mode <= 2 && o.solve_mode >= 0 && o.solve_mode <= 2 && o.refine_steps >= -1 &&
-         o.refine_steps <= 8 && (o.reserved == 0 || o.reserved == 1);
+         o.refine_steps <= 8 && (o.stored_operators == 0 || o.stored_operators == 1);
 }
 
 // ---- assembly launcher -----------------------------------------------------------------------------------------
@@ -516,7 +516,7 @@ int ensemble_create_impl(const double* h_meshes, size_t B, size_t n, double mu, 
     while ((size_t)32 * L < n) L <<= 1;
     e->L = L;
     e->fast = true;
-    e->lean_ok = opt.reserved == 0;  // dzb_options.reserved = 1 keeps the pre-scaled operator arrays (k_td_step_fast)
+    e->lean_ok = opt.stored_operators == 0;  // dzb_options.stored_operators = 1 keeps the pre-scaled operator arrays (k_td_step_fast)
     // at most 8 rows per lane (~100 registers): 1 warp per bar up to 256 nodes, 2 up to 512, 4 up to 1024
     e->lean_wpb = n > 512 ? 4 : (n > 256 ? 2 : 1);
     if (const char* w = std::getenv("DZB_LEAN_WPB")) {  // tuning knob: 2 warps x 16 rows for 513..1024 nodes

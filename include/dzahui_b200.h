@@ -56,7 +56,7 @@ typedef struct dzb_options {
   int assembly_mode; /* dzb_assembly_mode */
   int solve_mode;    /* dzb_solve_mode */
   int refine_steps;  /* static solvers, PARALLEL mode: iterative-refinement sweeps with a double-double residual (-1 = auto = 0: the unrefined solve is within 1e-11 of the exact solution of the system at 10^7 rows; one sweep reaches 1e-18) */
-  int reserved;      /* ensembles, PARALLEL mode: 0 = operator rebuilt on chip (k_td_step_lean, 40 B per DOF-step), 1 = pre-scaled operator arrays (k_td_step_fast, 56 B) */
+  int stored_operators; /* ensembles, PARALLEL mode: 0 = operator rebuilt on chip (k_td_step_lean, 40 B per DOF-step), 1 = pre-scaled operator arrays (k_td_step_fast, 56 B) */
 } dzb_options;
 
 /* ---- library / device ------------------------------------------------------------------------------------ */
