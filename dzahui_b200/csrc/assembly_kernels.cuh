@@ -24,7 +24,9 @@ struct RuleView {      // device pointers into one allocation, see gl_quadrature
   const double* v2;
   int m;               // G - 1
   double t0, t1p, t1m, q;
+  const unsigned short* guess;  // [GUESS_BINS + 1]: guess[k] = #{j : x_j >= -1 + 2 k / GUESS_BINS}, a bracket for the kink split
 };
+constexpr int GUESS_BINS = 1024;
 
 // ---- the reference's basis pieces, restated -----------------------------------------------------------------
 // FirstDegreePolynomial (polynomials_1d.rs:16-19): evaluate = coefficient*x + independent_term (two roundings).
@@ -290,61 +292,72 @@ __global__ void __launch_bounds__(128) k_assemble_faithful(const double* __restr
 //                        own two-rounding predicate fl(fl(cs*x_k) + ms) < c, found by bisection (x_k decreasing in k).
 // Falls back to the faithful loop for a row whose pieces could be selected differently by rounding (degenerate
 // or unsorted spacing), so FAST never silently changes which polynomial piece a node hits.
-template <int KIND>
-__device__ __forceinline__ void fast_row(const double* __restrict__ mesh, long long n, long long i,
-                                         const RuleView& R, const double* __restrict__ qx,
-                                         const double* __restrict__ qw, const AsmParams& P, double out[7]) {
+// true when every node image of row i stays inside the element(s) it is meant for (so the closed forms apply)
+__device__ __forceinline__ bool fast_row_ok(const double* __restrict__ mesh, long long n, long long i, double x_hi, double x_lo,
+                                            int m) {
   const double a = mesh[i - 1], c = mesh[i], e = mesh[i + 1];
-  const int m = R.m;
+  if (!(m > 0 && (a < c) && (c < e))) return false;
   const Affine tp = from_m1_p1(a, c), tn = from_m1_p1(c, e), ts = from_m1_p1(a, e);
-  bool ok = m > 0 && (a < c) && (c < e);
-  if (ok) {
-    const double x_hi = qx[0], x_lo = qx[m - 1];
-    ok = (tp(x_hi) < c) && !(tp(x_lo) < a) && (tn(x_hi) < e) && !(tn(x_lo) < c) && (ts(x_hi) < e) && !(ts(x_lo) < a);
-    if (i >= 2) ok = ok && !(a < mesh[i - 2]);
-    if (i + 2 < n) ok = ok && !(mesh[i + 2] < e);
-  }
-  if (!ok) {
-    faithful_row<KIND>(mesh, n, i, qx, qw, m, P, nullptr, 0, out);
-    return;
-  }
-  // first node index whose image is left of the kink (predicate is monotone in j because x_j decreases)
-  int lo = 0, hi = m;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (ts(qx[mid]) < c) hi = mid; else lo = mid + 1;
-  }
-  const int s = lo;
+  bool ok = (tp(x_hi) < c) && !(tp(x_lo) < a) && (tn(x_hi) < e) && !(tn(x_lo) < c) && (ts(x_hi) < e) && !(ts(x_lo) < a);
+  if (i >= 2) ok = ok && !(a < mesh[i - 2]);
+  if (i + 2 < n) ok = ok && !(mesh[i + 2] < e);
+  return ok;
+}
+
+// Returns false (out untouched) for a row that must take the quadrature loop (k_assemble_fixup).
+template <int KIND>
+__device__ __forceinline__ bool fast_row(const double* __restrict__ mesh, long long n, long long i,
+                                         const RuleView& R, const double* __restrict__ qx, const AsmParams& P, double out[7]) {
+  const int m = R.m;
+  if (m <= 0) return false;
+  if (!fast_row_ok(mesh, n, i, qx[0], qx[m - 1], m)) return false;
+  const double a = mesh[i - 1], c = mesh[i], e = mesh[i + 1];
+  const Affine ts = from_m1_p1(a, e);
   const double h1 = c - a, h2 = e - c, H = e - a;
+  // First node index whose image is left of the kink.  The predicate fl(fl(cs x_j) + ms) < c is the reference's own and is
+  // monotone in j (x_j decreases); a table over x* = (h1 - h2) / H brackets the answer, two probes settle it exactly.
+  int s;
+  {
+    const float xs = __fdividef((float)(h1 - h2), (float)H);
+    int bin = (int)((xs + 1.0f) * (0.5f * GUESS_BINS));
+    bin = max(0, min(GUESS_BINS - 1, bin));
+    s = R.guess[bin + 1];
+    while (s < m && !(ts(qx[s]) < c)) ++s;
+    while (s > 0 && (ts(qx[s - 1]) < c)) --s;
+  }
   const double r1 = __drcp_rn(h1), r2 = __drcp_rn(h2);  // two reciprocals instead of four divisions
   const double ih1sq = r1 * r1, ih2sq = r2 * r2;
   const double U0 = R.u0[s], U1 = R.u1[s], V0 = R.v0[s], V1 = R.v1[s];
   const double prime_prev = -0.5 * R.t0 * r1, prime_next = -0.5 * R.t0 * r2;
-  const double prime_sq = (H / 2.0) * (U0 * ih1sq + V0 * ih2sq);
-  const double half_prev = -R.t1p / 4.0, half_next = R.t1m / 4.0;
-  const double half_sq = (H * H / 4.0) * (U1 * ih1sq - V1 * ih2sq);
+  const double prime_sq = (0.5 * H) * fma(U0, ih1sq, V0 * ih2sq);
+  const double half_prev = -0.25 * R.t1p, half_next = 0.25 * R.t1m;
+  const double half_sq = (0.25 * H * H) * fma(U1, ih1sq, -V1 * ih2sq);
   if (KIND == KIND_TI) {
-    out[0] = P.mu * prime_prev + P.b * half_prev;
-    out[1] = P.mu * prime_sq + P.b * half_sq;
-    out[2] = P.mu * prime_next + P.b * half_next;
+    out[0] = fma(P.mu, prime_prev, P.b * half_prev);
+    out[1] = fma(P.mu, prime_sq, P.b * half_sq);
+    out[2] = fma(P.mu, prime_next, P.b * half_next);
     out[3] = 0.0;
     out[4] = out[5] = out[6] = 0.0;
   } else {
     const double U2 = R.u2[s], V2 = R.v2[s];
-    out[0] = -P.mu * prime_prev - P.b * half_prev;
-    out[1] = -P.mu * prime_sq - P.b * half_sq;
-    out[2] = -P.mu * prime_next - P.b * half_next;
+    out[0] = -fma(P.mu, prime_prev, P.b * half_prev);
+    out[1] = -fma(P.mu, prime_sq, P.b * half_sq);
+    out[2] = -fma(P.mu, prime_next, P.b * half_next);
     out[3] = 0.0;
-    out[4] = (h1 / 8.0) * R.q;
-    out[5] = (H * H * H / 8.0) * (U2 * ih1sq + V2 * ih2sq);
-    out[6] = (h2 / 8.0) * R.q;
+    out[4] = (0.125 * h1) * R.q;
+    out[5] = (0.125 * H * H * H) * fma(U2, ih1sq, V2 * ih2sq);
+    out[6] = (0.125 * h2) * R.q;
   }
+  return true;
 }
 
-// One thread per row, grid-stride; x table (and nothing else) staged in shared memory for the bisection.
+// One thread per row, grid-stride; x table (and nothing else) staged in shared memory for the probes.  Rows the closed
+// form does not cover are counted in *bad and left to k_assemble_fixup, which keeps the quadrature-loop code (and its
+// local-memory frame) out of this kernel.
 template <int KIND>
 __global__ void __launch_bounds__(256) k_assemble_fast(const double* __restrict__ mesh, long long n, long long n_bars,
-                                                       RuleView rule, AsmParams P, AsmOut o, int smem_rule) {
+                                                       RuleView rule, AsmParams P, AsmOut o, int smem_rule,
+                                                       unsigned* __restrict__ bad) {
   extern __shared__ double s_rule[];
   const double* qx = rule.x;
   if (smem_rule) {
@@ -353,14 +366,38 @@ __global__ void __launch_bounds__(256) k_assemble_fast(const double* __restrict_
     qx = s_rule;
   }
   const long long total = n * n_bars;
+  unsigned nbad = 0;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
     long long bar, i;
     split_index(g, n, n_bars, &bar, &i);
     double v[7];
     if (i == 0 || i == n - 1)
       boundary_row<KIND>(i == 0, P, v);
-    else
-      fast_row<KIND>(mesh + bar * n, n, i, rule, qx, rule.w, P, v);
+    else if (!fast_row<KIND>(mesh + bar * n, n, i, rule, qx, P, v)) {
+      ++nbad;
+      continue;
+    }
+    store_row<KIND>(o, g, v);
+  }
+  if (nbad) atomicAdd(bad, nbad);
+}
+// The rows k_assemble_fast skipped, through the reference's quadrature loop.  Launched unconditionally (no host
+// synchronisation); returns at once when nothing was skipped.
+template <int KIND>
+__global__ void __launch_bounds__(128) k_assemble_fixup(const double* __restrict__ mesh, long long n, long long n_bars,
+                                                        RuleView rule, AsmParams P, AsmOut o,
+                                                        const unsigned* __restrict__ bad) {
+  if (*bad == 0) return;
+  const int m = rule.m;
+  const long long total = n * n_bars;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    long long bar, i;
+    split_index(g, n, n_bars, &bar, &i);
+    if (i == 0 || i == n - 1) continue;
+    const double* bm = mesh + bar * n;
+    if (m > 0 && fast_row_ok(bm, n, i, rule.x[0], rule.x[m - 1], m)) continue;
+    double v[7];
+    faithful_row<KIND>(bm, n, i, rule.x, rule.w, m, P, nullptr, 0, v);
     store_row<KIND>(o, g, v);
   }
 }

@@ -66,6 +66,7 @@ inline unsigned blocks_for(long long work, int threads) { return (unsigned)((wor
 // ---- quadrature rule cache (device copies keyed by (device, G)) -------------------------------------------------
 struct DeviceRule {
   double* buf = nullptr;
+  unsigned short* guess = nullptr;
   dzb::RuleView view{};
 };
 std::map<std::pair<int, size_t>, DeviceRule> g_rules;
@@ -102,6 +103,19 @@ int get_rule(size_t G, dzb::RuleView* out) {
   d.view.v2 = p, p += m + 1;
   d.view.m = (int)m;
   d.view.t0 = r.t0, d.view.t1p = r.t1p, d.view.t1m = r.t1m, d.view.q = r.q;
+  {  // bracket table for the kink split: guess[k] = #{j : x_j >= -1 + 2 k / GUESS_BINS} (x_j decreasing in j)
+    std::vector<unsigned short> gt(dzb::GUESS_BINS + 1);
+    for (int k = 0; k <= dzb::GUESS_BINS; ++k) {
+      const double edge = -1.0 + 2.0 * (double)k / (double)dzb::GUESS_BINS;
+      size_t c = 0;
+      while (c < m && r.x[c] >= edge) ++c;
+      gt[(size_t)k] = (unsigned short)std::min<size_t>(c, 65535);
+    }
+    CK(cudaMalloc((void**)&d.guess, gt.size() * sizeof(unsigned short)));
+    CK(cudaMemcpyAsync(d.guess, gt.data(), gt.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    d.view.guess = d.guess;
+  }
   g_rules[{dev, G}] = d;
   *out = d.view;
   return DZB_OK;
@@ -148,8 +162,14 @@ int launch_assembly(const double* d_mesh, size_t n, size_t n_bars, size_t G, int
     long long blocks = (total + 255) / 256;
     const long long cap = 148LL * 8 * 4;  // grid-stride: a few waves of 8 resident CTAs on each of the 148 SMs
     if (blocks > cap) blocks = cap;
+    static unsigned* d_bad = nullptr;  // rows the closed form did not cover in the last launch (device side only)
+    if (!d_bad) CK(cudaMalloc((void**)&d_bad, sizeof(unsigned)));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), g_stream));
     dzb::k_assemble_fast<KIND><<<(unsigned)blocks, 256, smem, g_stream>>>(d_mesh, (long long)n, (long long)n_bars, rule, P, o,
-                                                                         smem_rule);
+                                                                         smem_rule, d_bad);
+    LAUNCHED();
+    dzb::k_assemble_fixup<KIND><<<(unsigned)std::min<long long>(blocks, 148LL * 8), 128, 0, g_stream>>>(d_mesh, (long long)n,
+                                                                                                       (long long)n_bars, rule, P, o, d_bad);
     LAUNCHED();
   }
   return DZB_OK;
