@@ -27,6 +27,7 @@ namespace {
 thread_local std::string g_err;
 cudaStream_t g_stream = 0;
 unsigned long long g_launches = 0;
+unsigned long long g_mesh_stamp = 0;
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -255,6 +256,7 @@ struct dzb_mesh {
   bool from_obj = false;
   std::vector<double> h_nodes;  // host copy of the coordinates (may be stale after dzb_mesh_set_nodes: see host_nodes())
   bool h_stale = false;
+  unsigned long long version = 0;  // process-unique stamp of the current coordinates (new at creation and at dzb_mesh_set_nodes)
   double* d_nodes = nullptr;
   double* d_vertices = nullptr;   // 12 n
   uint32_t* d_indices = nullptr;  // 6 n - 6
@@ -295,6 +297,9 @@ struct dzb_solver {
   double *lo = nullptr, *di = nullptr, *up = nullptr, *rhs = nullptr, *c = nullptr, *den = nullptr, *out = nullptr;
   bool parallel = false;       // the partitioned solver is in use (requested and the matrix allows it)
   bool want_parallel = false;  // DZB_SOLVE_PARALLEL requested / chosen by AUTO
+  const dzb_mesh* classified_mesh = nullptr;  // the matrix class (M-matrix / dominant) was decided for this mesh ...
+  unsigned long long classified_version = 0;  // ... at this version of its coordinates (same mesh => same bands => same class)
+  bool classified_ok = false;
   int refine_steps = 0;
   dzb::BigSys big;
   // block of a longer bar (SPIKE split across GPUs): the arrays above are views shifted by `off` into allocations that
@@ -616,6 +621,7 @@ int dzb_quad_table(size_t G, double* x, double* w) {
 // ------------------------------------------------------------------------------------------------- mesh
 static int mesh_finish(dzb_mesh* m, bool tables) {
   const size_t n = m->n;
+  m->version = ++g_mesh_stamp;
   int rc;
   if ((rc = dalloc(&m->d_nodes, n))) return rc;
   CK(cudaMemcpyAsync(m->d_nodes, m->h_nodes.data(), n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
@@ -672,6 +678,7 @@ int dzb_mesh_set_nodes(dzb_mesh* m, const double* x, size_t n) {
   if (n != m->n) return fail(DZB_WRONG_DIMS, "node count");
   if (m->from_obj) return fail(DZB_INVALID, "only meshes made by dzb_mesh_from_nodes can be re-pointed");
   m->h_stale = true;  // refreshed from the device only if a later call needs host coordinates
+  m->version = ++g_mesh_stamp;
   m->max_length = -x[0] + x[n - 1];
   CK(cudaMemcpyAsync(m->d_nodes, x, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   return sync_stream();
@@ -896,12 +903,17 @@ static int static_alloc(dzb_solver* s, size_t n) {
   return DZB_OK;
 }
 // Per-matrix work after (re)assembly: pick the solver the matrix allows, then factor for the serial path.
-static int static_factor(dzb_solver* s) {
+static int static_factor(dzb_solver* s, const dzb_mesh* m) {
   int rc;
   s->parallel = s->want_parallel;
   if (s->want_parallel) {
     bool ok = false;
-    if ((rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok))) return rc;
+    if (m && s->classified_mesh == m && s->classified_version == m->version) {
+      ok = s->classified_ok;  // re-assembly of unchanged coordinates: identical bands, identical answer
+    } else {
+      if ((rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok))) return rc;
+      s->classified_mesh = m, s->classified_version = m ? m->version : 0, s->classified_ok = ok;
+    }
     if (!ok) s->parallel = false;  // indefinite / convection-dominated system: the reference's serial recurrence
   }
   if (s->parallel) {
@@ -914,7 +926,7 @@ static int static_factor(dzb_solver* s) {
   }
   return DZB_OK;
 }
-static int static_finish(dzb_solver* s, const dzb_options& opt) {
+static int static_finish(dzb_solver* s, const dzb_options& opt, const dzb_mesh* m) {
   const size_t n = s->n;
   int solve_mode = opt.solve_mode;
   if (solve_mode == DZB_SOLVE_AUTO) solve_mode = n <= 65536 ? DZB_SOLVE_FAITHFUL : DZB_SOLVE_PARALLEL;
@@ -923,7 +935,7 @@ static int static_finish(dzb_solver* s, const dzb_options& opt) {
   s->want_parallel = solve_mode == DZB_SOLVE_PARALLEL;
   s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : 0;  // 1e-11 of the exact solution at 10^7 rows without any
   (void)n;
-  int rc = static_factor(s);
+  int rc = static_factor(s, m);
   if (rc) return rc;
   return sync_stream();
 }
@@ -944,7 +956,7 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
     dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
     rc = launch_assembly<dzb::KIND_TI>(m->d_nodes, s->n, 1, G, opt.assembly_mode, P, o, nullptr);
   }
-  if (!rc) rc = static_finish(s, opt);
+  if (!rc) rc = static_finish(s, opt, m);
   if (rc) {
     dzb_solver_destroy(s);
     return rc;
@@ -991,7 +1003,7 @@ int dzb_stokes1d_create(const dzb_mesh* m, double rho, double pressure, double (
     dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
     rc = launch_assembly<dzb::KIND_STOKES>(m->d_nodes, n, 1, G, opt.assembly_mode, P, o, d_force);
   }
-  if (!rc) rc = static_finish(s, opt);
+  if (!rc) rc = static_finish(s, opt, m);
   cudaStreamSynchronize(g_stream);
   dfree(d_force);
   if (rc) {
@@ -1026,7 +1038,7 @@ int dzb_solver_rebuild(dzb_solver* s, const dzb_mesh* m) {
     dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
     int rc = launch_assembly<dzb::KIND_TI>(m->d_nodes, s->n, 1, s->G, s->assembly_mode, P, o, nullptr);
     if (rc) return rc;
-    return static_factor(s);
+    return static_factor(s, m);
   }
   if (s->kind == dzb::KIND_TD) {
     dzb_ensemble* e = s->td;
