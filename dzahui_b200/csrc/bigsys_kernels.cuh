@@ -32,8 +32,10 @@
 //   F_0 + sum_j G_j delta~_j / (P_j P_{j-1})).   For an M-matrix every term of every sum has the same sign.
 //   Once u_s, u_e are known: u_j = (delta~_j - alpha~_j u_s - g~_j u_{j+1}) / P_j, j = 6..1.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -46,6 +48,8 @@ constexpr int BS_R = 8;                       // rows per chunk at every level
 constexpr int BS_THREADS = 256;               // tile kernel
 constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
 constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
+constexpr int BS_TMA_MIN_TILES = 64;          // smaller systems are launch-latency bound: plain k_tri_tile
+constexpr int BS_SHALLOW_MIN_TILES = 592;     // 4 tiles per SM: from here on an application is throughput bound
 #ifndef BS_MIN_CTAS
 #define BS_MIN_CTAS 3
 #endif
@@ -65,6 +69,20 @@ __device__ __forceinline__ double excess3(double lo, double di, double up) {
 __device__ __forceinline__ double pow2_inv(double x) {
   const int E = (__double2hiint(x) >> 20) & 0x7ff;
   return (E == 0 || E == 0x7ff) ? 1.0 : __hiloint2double((2046 - E) << 20, 0);
+}
+
+// 1/x for the pivots of the sweeps: the hardware seed (MUFU.RCP64H, ~2^-23) and two Newton steps, no special cases and
+// therefore no branch — __drcp_rn's slow-path check is a scheduling barrier that serialised the unrolled row-steps (each
+// 8-row sweep took ~1500 cycles).  Within an ulp of the correctly rounded value; the pivots are O(1) by construction
+// (chunks are pre-scaled by a power of two), so the flushed denormal range is never reached on a system k_tri_classify
+// accepts, and a zero pivot gives NaN instead of inf — garbage either way.
+__device__ __forceinline__ double pivot_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
 }
 
 // Shared-memory level: 8*P rows, SoA, row r of the level at (r % 8) * P + r / 8.
@@ -102,8 +120,9 @@ __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int
   double s_c = C0, s_s = S0, s_f = F0;  // s-row (its a stays A0)
   double rn = 1.0;                      // normalisation of the e-row
   if (FULL || len >= 3) {
-    double Pm = (sig - alp) - g;        // P_1
-    double rP = __drcp_rn(Pm);
+    double D = sig - alp;               // sigma~ - alpha~
+    double Pm = D - g;                  // P_1
+    double rP = pivot_rcp(Pm);
     lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rP, lv.d[idx] = dlt;
     double G = -C0;
     s_s = fma(G * rP, sig, S0), s_f = fma(G * rP, dlt, F0);
@@ -112,14 +131,17 @@ __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int
     for (int j = 2; j < BS_R; ++j) {
       if (FULL || j < len) {
         idx += P;
-        const double Aj = lv.a[idx] * sc, Cj = lv.c[idx] * sc;
-        sig = fma(lv.s[idx] * sc, Pm, -Aj * sig);
-        dlt = fma(lv.d[idx] * sc, Pm, -Aj * dlt);
-        alp = -Aj * alp;
+        const double nA = -(lv.a[idx] * sc), Cj = lv.c[idx] * sc, Sj = lv.s[idx] * sc;
+        const double q = nA * D;
+        const double Pn = fma(Sj - Cj, Pm, q);  // P_j by its own two-term recurrence (see chunk0_forward)
+        D = fma(Sj, Pm, q);
+        sig = fma(Sj, Pm, nA * sig);
+        dlt = fma(lv.d[idx] * sc, Pm, nA * dlt);
+        alp = nA * alp;
         g = Cj * Pm;
         if (FULL ? j < BS_R - 1 : j < len - 1) {
-          Pm = (sig - alp) - g;
-          const double rPn = __drcp_rn(Pm);
+          Pm = Pn;
+          const double rPn = pivot_rcp(Pm);
           lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rPn, lv.d[idx] = dlt;
           G *= -Cprev;
           const double w = G * rPn * rP;
@@ -181,22 +203,37 @@ struct Pyramid {
   __device__ __forceinline__ static void sync() {
     if (WARP) __syncwarp(); else __syncthreads();
   }
-  // forward sweeps from level 1 (holding rows1 rows) to the final 2 rows; every thread of the tile must call
-  __device__ __forceinline__ void reduce(int t, int rows1) {
-    int off = 0, rows = rows1;
+  // Forward sweeps from level 1 (holding rows1 rows); every thread of the tile must call.  NLEV == 0: down to the final 2
+  // rows.  NLEV > 0: only NLEV level reductions.  The level that is left starts at row `off` of the arrays, holds `rows`
+  // rows and is chunk-interleaved with capacity `cap` (row r at off + lvl_pos(r, cap); cap == 0: the final pair, at off + r).
+  struct Left {
+    int off, rows, cap;
+    __device__ __forceinline__ int pos(int r) const { return off + (cap ? lvl_pos(r, cap) : r); }
+  };
+  template <int NLEV>
+  __device__ __forceinline__ Left reduce_to(int t, int rows1) {
+    Left out{0, rows1, P1};
+    int lev = 0;
 #pragma unroll
     for (int p = P1;; p = (p + 3) / 4) {
       sync();
-      if (chunk_len(rows, t) > 0) level_reduce(level(off), p, chunk_len(rows, t), level(off + 8 * p), p == 1 ? 0 : (p + 3) / 4, t);
-      off += 8 * p;
-      rows = 2 * ((rows + BS_R - 1) / BS_R);
-      if (p == 1) break;
+      const int pn = p == 1 ? 0 : (p + 3) / 4;
+      if (chunk_len(out.rows, t) > 0) level_reduce(level(out.off), p, chunk_len(out.rows, t), level(out.off + 8 * p), pn, t);
+      out.off += 8 * p;
+      out.rows = 2 * ((out.rows + BS_R - 1) / BS_R);
+      out.cap = pn;
+      ++lev;
+      if (p == 1 || lev == NLEV) break;
     }
     sync();
+    return out;
   }
+  __device__ __forceinline__ void reduce(int t, int rows1) { reduce_to<0>(t, rows1); }
   __device__ __forceinline__ LevelPtr top() { return level(ROWS - 2); }
-  // back-substitution; top().d[0..1] must hold the solved pair
-  __device__ __forceinline__ void backsolve(int t, int rows1) {
+  // back-substitution through the levels reduce_to<NLEV> went through; the d[] of the level it left must hold that
+  // level's solved unknowns
+  template <int NLEV>
+  __device__ __forceinline__ void backsolve_from(int t, int rows1) {
     int rows_at[8], cap[8], offs[8], nl = 0;
     {
       int rows = rows1, off = 0;
@@ -205,7 +242,7 @@ struct Pyramid {
         rows_at[nl] = rows, cap[nl] = p, offs[nl] = off, ++nl;
         off += 8 * p;
         rows = 2 * ((rows + BS_R - 1) / BS_R);
-        if (p == 1) break;
+        if (p == 1 || nl == NLEV) break;
       }
     }
 #pragma unroll
@@ -219,7 +256,18 @@ struct Pyramid {
     }
     sync();
   }
+  __device__ __forceinline__ void backsolve(int t, int rows1) { backsolve_from<0>(t, rows1); }
 };
+// rows a full tile of 8 P1 level-1 rows leaves after NLEV level reductions (NLEV == 0: all of them)
+__host__ __device__ constexpr int bs_rows_left(int P1, int NLEV) {
+  int rows = 8 * P1;
+  for (int p = P1, lev = 0;; p = (p + 3) / 4) {
+    rows = 2 * ((rows + BS_R - 1) / BS_R);
+    ++lev;
+    if (p == 1 || lev == NLEV) break;
+  }
+  return rows;
+}
 
 // Level 0: the forward sweep over a chunk held in registers; KEEP stores (alpha~_j, g~_j, 1/P_j, delta~_j) over
 // (A, C, S, F)[1..len-2] for the back-substitution.  FULL: len == 8.
@@ -233,8 +281,13 @@ __device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS
   double s_c = C0, s_s = S0, s_f = F0;
   double rn = 1.0;
   if (FULL || len >= 3) {
-    double Pm = (sig - alp) - g;  // P_1
-    double rP = __drcp_rn(Pm);
+    // The minors are not formed as sigma~_j - alpha~_j - g~_j (four dependent operations per row-step) but by the
+    // equivalent two-term recurrence  P_j = (S_j - C_j) P_{j-1} - A_j D_{j-1},  D_j = sigma~_j - alpha~_j = S_j P_{j-1} - A_j D_{j-1},
+    // which has two on its critical path (q = -A_j D_{j-1}, then one fma each) and, for an M-matrix, still only adds
+    // terms of one sign.  sigma~, alpha~, delta~, g~ hang off P_{j-1} and are not on the chain.
+    double D = sig - alp;
+    double Pm = D - g;  // P_1
+    double rP = pivot_rcp(Pm);
     if (KEEP) A[1] = alp, C[1] = g, S[1] = rP, F[1] = dlt;
     double G = -C0;
     s_s = fma(G * rP, sig, S0), s_f = fma(G * rP, dlt, F0);
@@ -242,14 +295,17 @@ __device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS
 #pragma unroll
     for (int j = 2; j < BS_R; ++j) {
       if (FULL || j < len) {
-        const double Aj = A[j] * sc, Cj = C[j] * sc;
-        sig = fma(S[j] * sc, Pm, -Aj * sig);
-        dlt = fma(F[j] * sc, Pm, -Aj * dlt);
-        alp = -Aj * alp;
+        const double nA = -(A[j] * sc), Cj = C[j] * sc, Sj = S[j] * sc;
+        const double q = nA * D;
+        const double Pn = fma(Sj - Cj, Pm, q);
+        D = fma(Sj, Pm, q);
+        sig = fma(Sj, Pm, nA * sig);
+        dlt = fma(F[j] * sc, Pm, nA * dlt);
+        alp = nA * alp;
         g = Cj * Pm;
         if (FULL ? j < BS_R - 1 : j < len - 1) {
-          Pm = (sig - alp) - g;
-          const double rPn = __drcp_rn(Pm);
+          Pm = Pn;
+          const double rPn = pivot_rcp(Pm);
           if (KEEP) A[j] = alp, C[j] = g, S[j] = rPn, F[j] = dlt;
           G *= -Cprev;
           const double w = G * rPn * rP;
@@ -266,52 +322,58 @@ __device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS
   l1.a[i1] = alp * rn, l1.c[i1] = g * rn, l1.s[i1] = sig * rn, l1.d[i1] = dlt * rn;
 }
 
-// ---- tile kernel --------------------------------------------------------------------------------------------------
+// ---- tile kernels -------------------------------------------------------------------------------------------------
 // SOLVE == false: forward sweeps, the tile's two reduced rows -> red_{a,c,s,f}[2 tile + {0,1}].
 // SOLVE == true : forward sweeps again, (u_s, u_e) of the tile from ured[2 tile + {0,1}], back-substitution, out[]
 //                 (ACCUM: out[] += value, the iterative-refinement update).
 // SRC: p0..p3 = (lo, di, up, f) of the caller's system, or (a, c, s, f) of a reduced system.
-// TT: threads that share a tile.  256: the CTA (2048 rows, __syncthreads between the pyramid levels).  32: one warp (256
-// rows, __syncwarp only), so that while one warp is inside its latency-bound pyramid the other warps of the SM keep
-// streaming; a tile then leaves 2 rows per 256.
-template <int SRC, bool SOLVE, bool ACCUM, int TT>
-__global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const double* __restrict__ p0, const double* __restrict__ p1,
-                                                            const double* __restrict__ p2, const double* __restrict__ p3,
-                                                            long long m, double* __restrict__ red_a,
-                                                            double* __restrict__ red_c, double* __restrict__ red_s,
-                                                            double* __restrict__ red_f, const double* __restrict__ ured,
-                                                            double* __restrict__ out, int flags) {
-  constexpr bool WARP = TT == 32;
-  constexpr int TILE = BS_R * TT;
-  constexpr int P1 = TT / 4;  // chunks of level 1
-  __shared__ Pyramid<P1, WARP> pyrs[BS_THREADS / TT];
-  Pyramid<P1, WARP>& pyr = pyrs[WARP ? threadIdx.x / 32 : 0];
-  const int t = WARP ? (threadIdx.x & 31) : threadIdx.x;
-  const long long tile = WARP ? (long long)blockIdx.x * (BS_THREADS / 32) + threadIdx.x / 32 : (long long)blockIdx.x;
+// NLEV: shared-memory levels the tile goes through (0: all, the tile leaves 2 rows; 1: it leaves the 128 rows of level 2).
+//
+// Two front ends share tile_body(): k_tri_tile loads its chunk straight into registers (any alignment, any size), and
+// k_tri_tile_tma (below) is the persistent, TMA-staged version used for the big level-0 systems.
+struct TileArgs {
+  const double *p0, *p1, *p2, *p3;
+  long long m;
+  double *red_a, *red_c, *red_s, *red_f;
+  const double* ured;
+  double* out;
+  int flags;
+};
+struct ChunkGeom {
+  int len;       // rows of the chunk (0: idle thread)
+  long long g0;  // its first row
+};
+__device__ __forceinline__ ChunkGeom chunk_geom(int rows0, int c, long long tile0) {
+  ChunkGeom g;
+  g.len = chunk_len(rows0, c);
+  const bool shifted = (rows0 & 7) == 1 && rows0 > 1 && c == ((rows0 - 1) >> 3);  // the "2" of a 7 + 2 split
+  g.g0 = tile0 + (long long)c * BS_R - (shifted ? 1 : 0);
+  return g;
+}
+// first row and row count of tile `tile` of an m-row system cut into TILE-row tiles; a single left-over row is
+// never left to the last tile: the last two tiles split (TILE - 1) + 2 instead
+__device__ __forceinline__ int tile_rows(long long tile, long long m, int TILE, long long* tile0) {
   const long long ntiles = (m + TILE - 1) / TILE;
-  if (tile >= ntiles) return;  // whole warps only (warp scope); never taken in CTA scope
-  long long tile0 = tile * TILE;
-  int rows0 = (int)min((long long)TILE, m - tile0);               // rows of this tile
-  {  // never leave a single row to the last tile: split (TILE - 1) + 2 instead
-    const long long rem = m - (ntiles - 1) * TILE;
-    if (rem == 1 && ntiles > 1) {
-      if (tile == ntiles - 1) tile0 -= 1, rows0 = 2;
-      else if (tile == ntiles - 2) rows0 = TILE - 1;
-    }
+  *tile0 = tile * TILE;
+  int rows0 = (int)min((long long)TILE, m - *tile0);
+  if (m - (ntiles - 1) * TILE == 1 && ntiles > 1) {
+    if (tile == ntiles - 1) *tile0 -= 1, rows0 = 2;
+    else if (tile == ntiles - 2) rows0 = TILE - 1;
   }
-  const int rows1 = 2 * ((rows0 + BS_R - 1) / BS_R);              // rows it leaves at level 1
-  const int len = chunk_len(rows0, t);                            // rows of this thread's chunk (0: idle)
-  const bool shifted = (rows0 & 7) == 1 && rows0 > 1 && t == ((rows0 - 1) >> 3);  // the "2" of a 7 + 2 split
-  const long long g0 = tile0 + (long long)t * BS_R - (shifted ? 1 : 0);
-  double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
+  return rows0;
+}
+// rows g0 .. g0+len of the system -> registers, straight from global memory; returns whether the 128-bit path was taken
+template <int SRC, bool SOLVE>
+__device__ __forceinline__ bool chunk_load_direct(const TileArgs& k, long long g0, int len, double (&A)[BS_R], double (&C)[BS_R],
+                                                  double (&S)[BS_R], double (&F)[BS_R]) {
   const bool vec = len == BS_R &&  // full chunk whose 128-bit accesses are aligned
-                   !((reinterpret_cast<size_t>(p0 + g0) | reinterpret_cast<size_t>(p1 + g0) | reinterpret_cast<size_t>(p2 + g0) |
-                      reinterpret_cast<size_t>(p3 + g0) | (SOLVE ? reinterpret_cast<size_t>(out + g0) : 0)) & 15);
+                   !((reinterpret_cast<size_t>(k.p0 + g0) | reinterpret_cast<size_t>(k.p1 + g0) | reinterpret_cast<size_t>(k.p2 + g0) |
+                      reinterpret_cast<size_t>(k.p3 + g0) | (SOLVE ? reinterpret_cast<size_t>(k.out + g0) : 0)) & 15);
   if (vec) {
-    const double2* q0 = reinterpret_cast<const double2*>(p0 + g0);
-    const double2* q1 = reinterpret_cast<const double2*>(p1 + g0);
-    const double2* q2 = reinterpret_cast<const double2*>(p2 + g0);
-    const double2* q3 = reinterpret_cast<const double2*>(p3 + g0);
+    const double2* q0 = reinterpret_cast<const double2*>(k.p0 + g0);
+    const double2* q1 = reinterpret_cast<const double2*>(k.p1 + g0);
+    const double2* q2 = reinterpret_cast<const double2*>(k.p2 + g0);
+    const double2* q3 = reinterpret_cast<const double2*>(k.p3 + g0);
 #pragma unroll
     for (int j = 0; j < BS_R / 2; ++j) {
       const double2 v0 = __ldcs(q0 + j), v1 = __ldcs(q1 + j), v2 = __ldcs(q2 + j), v3 = __ldcs(q3 + j);
@@ -329,11 +391,22 @@ __global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const doub
     for (int j = 0; j < BS_R; ++j) {
       const long long g = g0 + j;
       const bool in = j < len;
-      if (SRC == BS_SRC_BANDS) A[j] = in ? p0[g] : 0.0, S[j] = in ? p1[g] : 1.0, C[j] = in ? p2[g] : 0.0;
-      else A[j] = in ? p0[g] : 0.0, C[j] = in ? p1[g] : 0.0, S[j] = in ? p2[g] : 1.0;
-      F[j] = in ? p3[g] : 0.0;
+      if (SRC == BS_SRC_BANDS) A[j] = in ? k.p0[g] : 0.0, S[j] = in ? k.p1[g] : 1.0, C[j] = in ? k.p2[g] : 0.0;
+      else A[j] = in ? k.p0[g] : 0.0, C[j] = in ? k.p1[g] : 0.0, S[j] = in ? k.p2[g] : 1.0;
+      F[j] = in ? k.p3[g] : 0.0;
     }
   }
+  return vec;
+}
+
+// Everything after the chunk is in registers: (a, c, s, f) form, level 0, the shared-memory pyramid, and either the
+// tile's two reduced rows or the back-substitution.  Every thread of the tile must call.  vec: out[] takes 128-bit stores.
+template <int SRC, bool SOLVE, bool ACCUM, int NLEV, int P1, bool WARP>
+__device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs& k, double (&A)[BS_R], double (&C)[BS_R],
+                                          double (&S)[BS_R], double (&F)[BS_R], int len, long long g0, bool vec, int t,
+                                          long long tile, int rows1) {
+  const long long m = k.m;
+  const int flags = k.flags;
   // closed ends cut the first / last coupling; a block of a longer bar (SPIKE split) keeps them
   if (g0 == 0 && len > 0 && !(flags & BS_OPEN_LEFT)) A[0] = 0.0;
   if (!(flags & BS_OPEN_RIGHT) && len > 0 && g0 + len == m) {
@@ -351,31 +424,39 @@ __global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const doub
     if (len == BS_R) chunk0_forward<SOLVE, true>(A, C, S, F, len, l1, i0, i1);
     else chunk0_forward<SOLVE, false>(A, C, S, F, len, l1, i0, i1);
   }
-  pyr.reduce(t, rows1);
-  LevelPtr top = pyr.top();
+  // NLEV == 0: the pyramid runs down to the tile's final 2 rows.  NLEV > 0: it stops after NLEV levels and the tile
+  // hands all rows of that level to the next application (2 P1 of them after one level: a reduction by 16 instead of
+  // 1024).  The upper levels keep one warp busy and seven parked, so a throughput-bound first application is better off
+  // leaving them to the next one, which then works on a 16x smaller system with full CTAs again.
+  constexpr int ROUT = bs_rows_left(P1, NLEV);  // rows a full tile leaves
+  const typename Pyramid<P1, WARP>::Left left = pyr.template reduce_to<NLEV>(t, rows1);
+  const long long obase = (long long)ROUT * tile;
   if (!SOLVE) {
-    if (t < 2) {
-      const long long o = 2LL * tile + t;
-      red_a[o] = top.a[t], red_c[o] = top.c[t], red_s[o] = top.s[t], red_f[o] = top.d[t];
+    for (int r = t; r < left.rows; r += WARP ? 32 : BS_THREADS) {
+      const int q = left.pos(r);
+      k.red_a[obase + r] = pyr.a[q], k.red_c[obase + r] = pyr.c[q], k.red_s[obase + r] = pyr.s[q], k.red_f[obase + r] = pyr.d[q];
     }
     return;
   }
-  if (t < 2) top.d[t] = ured[2LL * tile + t];
-  pyr.backsolve(t, rows1);
+  if (SOLVE) {  // (a branch, not fall-through, only to keep the !SOLVE instantiation free of unreachable-code warnings)
+    for (int r = t; r < left.rows; r += WARP ? 32 : BS_THREADS) pyr.d[left.pos(r)] = k.ured[obase + r];
+    pyr.template backsolve_from<NLEV>(t, rows1);
+  }
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
     const double us = l1.d[lvl_pos(2 * t, P1)], ue = l1.d[lvl_pos(2 * t + 1, P1)];
+    double* __restrict__ out = k.out;
     double o[BS_R];
     // A decoupled end row of the caller's system (a Dirichlet row: lo = up = 0) is returned exactly as Thomas returns it,
     // f / di (matrix_solver/mod.rs:36-39 with a zero coupling); the scaled sweeps would be off by an ulp.
-    const bool fix_first = SRC == BS_SRC_BANDS && g0 == 0 && !(flags & BS_OPEN_LEFT) && p2[0] == 0.0;
-    const bool fix_last = SRC == BS_SRC_BANDS && g0 + len == m && !(flags & BS_OPEN_RIGHT) && p0[m - 1] == 0.0;
+    const bool fix_first = SRC == BS_SRC_BANDS && g0 == 0 && !(flags & BS_OPEN_LEFT) && k.p2[0] == 0.0;
+    const bool fix_last = SRC == BS_SRC_BANDS && g0 + len == m && !(flags & BS_OPEN_RIGHT) && k.p0[m - 1] == 0.0;
     if (vec) {
       o[0] = us, o[BS_R - 1] = ue;
 #pragma unroll
       for (int j = BS_R - 2; j >= 1; --j) o[j] = fma(-C[j], o[j + 1], fma(-A[j], us, F[j])) * S[j];
-      if (fix_first) o[0] = p3[0] / p1[0];
-      if (fix_last) o[BS_R - 1] = p3[m - 1] / p1[m - 1];
+      if (fix_first) o[0] = k.p3[0] / k.p1[0];
+      if (fix_last) o[BS_R - 1] = k.p3[m - 1] / k.p1[m - 1];
       double2* po = reinterpret_cast<double2*>(out + g0);
 #pragma unroll
       for (int j = 0; j < BS_R / 2; ++j) {
@@ -395,13 +476,139 @@ __global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const doub
         else if (j < len - 1) nxt = fma(-C[j], nxt, fma(-A[j], us, F[j])) * S[j], o[j] = nxt;
         else o[j] = 0.0;
       }
-      if (fix_first) o[0] = p3[0] / p1[0];
+      if (fix_first) o[0] = k.p3[0] / k.p1[0];
 #pragma unroll
       for (int j = 0; j < BS_R; ++j) {
-        if (fix_last && j == len - 1) o[j] = p3[m - 1] / p1[m - 1];
+        if (fix_last && j == len - 1) o[j] = k.p3[m - 1] / k.p1[m - 1];
         if (j < len) out[g0 + j] = ACCUM ? out[g0 + j] + o[j] : o[j];
       }
     }
+  }
+}
+
+template <int SRC, bool SOLVE, bool ACCUM, int NLEV>
+__global__ void __launch_bounds__(BS_THREADS, BS_MIN_CTAS) k_tri_tile(const TileArgs k) {
+  __shared__ Pyramid<BS_THREADS / 4> pyr;
+  const int t = threadIdx.x;
+  const long long tile = blockIdx.x;
+  long long tile0;
+  const int rows0 = tile_rows(tile, k.m, BS_TILE, &tile0);        // rows of this tile
+  const int rows1 = 2 * ((rows0 + BS_R - 1) / BS_R);              // rows it leaves at level 1
+  const ChunkGeom gm = chunk_geom(rows0, t, tile0);
+  double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
+  const bool vec = chunk_load_direct<SRC, SOLVE>(k, gm.g0, gm.len, A, C, S, F);
+  tile_body<SRC, SOLVE, ACCUM, NLEV>(pyr, k, A, C, S, F, gm.len, gm.g0, vec, t, tile, rows1);
+}
+
+// ---- TMA-staged persistent tile kernel (level 0 of a big system given as bands) ----------------------------------------
+// k_tri_tile's loads are its weak spot: a thread owns 8 consecutive rows, so a warp's 128-bit load touches 16 lines (16 L1
+// wavefronts per instruction; ncu: l1tex data pipe 67 % busy at 42 % DRAM), and nothing is in flight while a CTA
+// computes.  Here each of the four arrays is described to the TMA as a 2-D tensor of 128-byte rows (16 doubles); one
+// elected thread asks for the tile's 128 x 128 B box of each array (4 x 16 KB, SWIZZLE_128B) and the CTA's threads then
+// read their 64-byte chunks from shared memory conflict-free (the swizzle XORs the 16-byte column with the row, which
+// spreads the 8 threads of an LDS.128 phase over all 32 banks).  CTAs are persistent (2 per SM, tiles strided by the
+// grid): as soon as every thread has its chunk in registers the stage buffer is re-armed for the CTA's NEXT tile, so that
+// tile's HBM latency is hidden behind this tile's sweeps and pyramid.  Only full, 16-byte aligned tiles take the staged
+// path; a ragged last tile goes through chunk_load_direct.
+constexpr int BS_TMA_ROW = 16;                                      // doubles per 128-byte tensor row
+constexpr int BS_TMA_BOX = BS_TILE / BS_TMA_ROW;                    // tensor rows per tile
+constexpr unsigned BS_STAGE_BYTES = 4u * BS_TILE * sizeof(double);  // 64 KB
+struct TileStage {
+  alignas(1024) double rows[4][BS_TILE];
+  Pyramid<BS_THREADS / 4> pyr;
+  alignas(8) unsigned long long mbar;
+};
+constexpr size_t BS_STAGE_SMEM = sizeof(TileStage) + 1024;  // + slack to align the dynamic window to 1024 B
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();  // a lost copy becomes an error, not a hang
+  }
+}
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, int row, unsigned long long* b) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(0), "r"(row), "r"(smem_u32(b))
+      : "memory");
+}
+
+template <int SRC, bool SOLVE, bool ACCUM, int NLEV>
+__global__ void __launch_bounds__(BS_THREADS, 2) k_tri_tile_tma(const __grid_constant__ CUtensorMap map0,
+                                                                const __grid_constant__ CUtensorMap map1,
+                                                                const __grid_constant__ CUtensorMap map2,
+                                                                const __grid_constant__ CUtensorMap map3, const TileArgs k) {
+  extern __shared__ unsigned char tile_stage_raw[];
+  TileStage& sm = *reinterpret_cast<TileStage*>((reinterpret_cast<size_t>(tile_stage_raw) + 1023) & ~(size_t)1023);
+  const int t = threadIdx.x;
+  const long long ntiles = (k.m + BS_TILE - 1) / BS_TILE;
+  if (t == 0) mbar_init(&sm.mbar, 1);
+  __syncthreads();
+  auto request = [&](long long tile) {  // thread 0: stage the four 16 KB boxes of a full tile
+    mbar_arrive_expect_tx(&sm.mbar, BS_STAGE_BYTES);
+    const int row = (int)(tile * BS_TMA_BOX);
+    tma_load_box(sm.rows[0], &map0, row, &sm.mbar);
+    tma_load_box(sm.rows[1], &map1, row, &sm.mbar);
+    tma_load_box(sm.rows[2], &map2, row, &sm.mbar);
+    tma_load_box(sm.rows[3], &map3, row, &sm.mbar);
+  };
+  auto staged = [&](long long tile) {
+    long long t0;
+    return tile < ntiles && tile_rows(tile, k.m, BS_TILE, &t0) == BS_TILE;
+  };
+  long long tile = blockIdx.x;
+  if (t == 0 && staged(tile)) request(tile);
+  unsigned phase = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    long long tile0;
+    const int rows0 = tile_rows(tile, k.m, BS_TILE, &tile0);
+    const int rows1 = 2 * ((rows0 + BS_R - 1) / BS_R);
+    const ChunkGeom gm = chunk_geom(rows0, t, tile0);
+    double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
+    bool vec;
+    if (rows0 == BS_TILE) {
+      mbar_wait(&sm.mbar, phase);
+      phase ^= 1;
+      // chunk t = bytes [64 t, 64 t + 64) of every array = 16-byte columns 4 (t & 1) + j of tensor row t / 2
+      const int row = t >> 1;
+      const unsigned char* base = reinterpret_cast<const unsigned char*>(sm.rows[0]) + row * 128;
+#pragma unroll
+      for (int j = 0; j < BS_R / 2; ++j) {
+        const int col = ((((t & 1) << 2) + j) ^ (row & 7)) << 4;
+        const double2 v0 = *reinterpret_cast<const double2*>(base + col);
+        const double2 v1 = *reinterpret_cast<const double2*>(base + col + BS_TILE * 8);
+        const double2 v2 = *reinterpret_cast<const double2*>(base + col + BS_TILE * 16);
+        const double2 v3 = *reinterpret_cast<const double2*>(base + col + BS_TILE * 24);
+        if (SRC == BS_SRC_BANDS) {
+          A[2 * j] = v0.x, A[2 * j + 1] = v0.y, S[2 * j] = v1.x, S[2 * j + 1] = v1.y;  // S holds di for now
+          C[2 * j] = v2.x, C[2 * j + 1] = v2.y;
+        } else {
+          A[2 * j] = v0.x, A[2 * j + 1] = v0.y, C[2 * j] = v1.x, C[2 * j + 1] = v1.y;
+          S[2 * j] = v2.x, S[2 * j + 1] = v2.y;
+        }
+        F[2 * j] = v3.x, F[2 * j + 1] = v3.y;
+      }
+      __syncthreads();  // every chunk is in registers (and the previous tile is done with the pyramid)
+      if (t == 0 && staged(tile + gridDim.x)) request(tile + gridDim.x);
+      vec = !SOLVE || !(reinterpret_cast<size_t>(k.out + gm.g0) & 15);
+    } else {
+      __syncthreads();  // the previous tile is done with the pyramid
+      vec = chunk_load_direct<SRC, SOLVE>(k, gm.g0, gm.len, A, C, S, F);
+    }
+    tile_body<SRC, SOLVE, ACCUM, NLEV>(sm.pyr, k, A, C, S, F, gm.len, gm.g0, vec, t, tile, rows1);
   }
 }
 
@@ -549,11 +756,19 @@ __global__ void k_set_ends(double* __restrict__ u, long long n, double bc0, doub
 // ---- host orchestration --------------------------------------------------------------------------------------------
 struct BigLevel {
   size_t m = 0;  // rows of the reduced system produced at this level
+  int nlev = 0;  // shared-memory levels its tiles go through: 0 = all (2 rows per tile), 1 = one (128 rows per tile)
   double *a = nullptr, *c = nullptr, *s = nullptr, *f = nullptr, *u = nullptr;
 };
 struct BigSys {
   size_t n = 0;
-  int tt = 256;  // threads per tile of k_tri_tile: 256 (CTA tiles of 2048 rows; measured 4 % faster) or 32 (warp tiles of 256 rows)
+  size_t shallow_min_tiles = BS_SHALLOW_MIN_TILES;  // applications with at least this many tiles stop after one level
+  bool tma = true;  // big band systems go through k_tri_tile_tma (DZB_NO_TMA=1: always k_tri_tile)
+  struct Map {
+    const double* p;
+    size_t m;
+    CUtensorMap map;
+  };
+  std::vector<Map> maps;         // tensor maps of the arrays seen so far (encoding one costs a few microseconds)
   std::vector<BigLevel> levels;  // levels[k]: reduced system of the k-th application of the tile kernel
   double* resid = nullptr;       // refinement residual / explicit-Euler right-hand side
 };
@@ -577,17 +792,29 @@ inline void bigsys_free(BigSys* s) {
   s->n = 0;
 }
 
+// rows an m-row system leaves after one application of the tile kernel (same tiling rules as tile_rows / chunk_len)
+inline size_t bigsys_rows_left(size_t m, int nlev) {
+  const size_t ntiles = (m + BS_TILE - 1) / BS_TILE;
+  size_t last = m - (ntiles - 1) * BS_TILE;  // rows of the last tile
+  if (last == 1 && ntiles > 1) last = 2;     // the (TILE - 1) + 2 split
+  size_t left = 2 * ((last + BS_R - 1) / BS_R);             // after level 0
+  left = nlev ? 2 * ((left + BS_R - 1) / BS_R) : 2;         // after one level / after all of them
+  return (ntiles - 1) * (size_t)bs_rows_left(BS_THREADS / 4, nlev) + left;
+}
+
 // Allocates the scratch pyramid for systems of n rows.
 inline int bigsys_prepare(BigSys* s, size_t n) {
   bigsys_free(s);
   s->n = n;
-  if (const char* v = std::getenv("DZB_TILE_THREADS")) s->tt = std::atoi(v) == 32 ? 32 : 256;  // tuning knob
+  if (const char* v = std::getenv("DZB_SHALLOW_MIN_TILES")) s->shallow_min_tiles = (size_t)std::atoll(v);  // tuning knob
+  if (const char* v = std::getenv("DZB_NO_TMA")) s->tma = std::atoi(v) == 0;
+  s->maps.clear();
   cudaError_t e;
   size_t m = n;
   while (m > (size_t)BS_MID_CAP) {
     BigLevel l;
-    const size_t tile = (size_t)BS_R * (size_t)s->tt;
-    l.m = 2 * ((m + tile - 1) / tile);
+    l.nlev = (m + BS_TILE - 1) / BS_TILE >= s->shallow_min_tiles ? 1 : 0;
+    l.m = bigsys_rows_left(m, l.nlev);
     for (double** p : {&l.a, &l.c, &l.s, &l.f, &l.u})
       if ((e = cudaMalloc((void**)p, l.m * sizeof(double))) != cudaSuccess) return bigsys_fail(e, "cudaMalloc");
     s->levels.push_back(l);
@@ -627,16 +854,83 @@ inline int bigsys_mid(const double* p0, const double* p1, const double* p2, cons
   return bigsys_mid_launch<256, SRC, MODE>(p0, p1, p2, p3, m, out, accum, flags, top8, us, ue, st);
 }
 
-template <int SRC, bool SOLVE, bool ACCUM>
-inline void bigsys_launch_tile(int tt, size_t m, const double* p0, const double* p1, const double* p2, const double* p3, double* ra,
-                               double* rc, double* rs, double* rf, const double* ured, double* out, int flags, cudaStream_t st) {
-  if (tt == 32) {
-    const size_t tiles = (m + 255) / 256;
-    k_tri_tile<SRC, SOLVE, ACCUM, 32><<<(unsigned)((tiles + 7) / 8), BS_THREADS, 0, st>>>(p0, p1, p2, p3, (long long)m, ra, rc, rs, rf, ured, out, flags);
-  } else {
-    const size_t tiles = (m + BS_TILE - 1) / BS_TILE;
-    k_tri_tile<SRC, SOLVE, ACCUM, 256><<<(unsigned)tiles, BS_THREADS, 0, st>>>(p0, p1, p2, p3, (long long)m, ra, rc, rs, rf, ured, out, flags);
+// ---- tensor maps for the staged kernel ------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn bigsys_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// the array p[0..m) as 128-byte rows (only the floor(m / 16) complete ones: full tiles never reach past them)
+inline const CUtensorMap* bigsys_map(BigSys* s, const double* p, size_t m) {
+  for (const BigSys::Map& e : s->maps)
+    if (e.p == p && e.m == m) return &e.map;
+  EncodeTiledFn enc = bigsys_encoder();
+  if (!enc) return nullptr;
+  BigSys::Map e;
+  e.p = p, e.m = m;
+  const cuuint64_t dims[2] = {(cuuint64_t)BS_TMA_ROW, (cuuint64_t)(m / BS_TMA_ROW)};
+  const cuuint64_t strides[1] = {(cuuint64_t)BS_TMA_ROW * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)BS_TMA_ROW, (cuuint32_t)BS_TMA_BOX};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return nullptr;
+  if (s->maps.size() >= 32) s->maps.erase(s->maps.begin());
+  s->maps.push_back(e);
+  return &s->maps.back().map;
+}
+inline int bigsys_sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+// One application of the tile kernel.  Big systems whose arrays are 16-byte aligned go through the TMA-staged persistent
+// kernel; everything else (offset views of a SPIKE block, small systems) through k_tri_tile.
+template <int SRC, bool SOLVE, bool ACCUM, int NLEV>
+inline cudaError_t bigsys_launch_tile_n(BigSys* s, size_t m, const double* p0, const double* p1, const double* p2, const double* p3,
+                                        double* ra, double* rc, double* rs, double* rf, const double* ured, double* out, int flags,
+                                        cudaStream_t st) {
+  const TileArgs k{p0, p1, p2, p3, (long long)m, ra, rc, rs, rf, ured, out, flags};
+  const size_t tiles = (m + BS_TILE - 1) / BS_TILE;
+  if (s->tma && tiles >= (size_t)BS_TMA_MIN_TILES &&
+      !((reinterpret_cast<size_t>(p0) | reinterpret_cast<size_t>(p1) | reinterpret_cast<size_t>(p2) | reinterpret_cast<size_t>(p3)) & 15)) {
+    const CUtensorMap *m0 = bigsys_map(s, p0, m), *m1 = bigsys_map(s, p1, m), *m2 = bigsys_map(s, p2, m), *m3 = bigsys_map(s, p3, m);
+    if (m0 && m1 && m2 && m3) {
+      static bool attr_set = false;  // per instantiation
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_tri_tile_tma<SRC, SOLVE, ACCUM, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)BS_STAGE_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+      }
+      const size_t grid = std::min(tiles, (size_t)2 * bigsys_sm_count());
+      const CUtensorMap c0 = *m0, c1 = *m1, c2 = *m2, c3 = *m3;  // bigsys_map may move its cache
+      k_tri_tile_tma<SRC, SOLVE, ACCUM, NLEV><<<(unsigned)grid, BS_THREADS, BS_STAGE_SMEM, st>>>(c0, c1, c2, c3, k);
+      return cudaGetLastError();
+    }
   }
+  k_tri_tile<SRC, SOLVE, ACCUM, NLEV><<<(unsigned)tiles, BS_THREADS, 0, st>>>(k);
+  return cudaGetLastError();
+}
+template <int SRC, bool SOLVE, bool ACCUM>
+inline cudaError_t bigsys_launch_tile(BigSys* s, int nlev, size_t m, const double* p0, const double* p1, const double* p2,
+                                      const double* p3, double* ra, double* rc, double* rs, double* rf, const double* ured,
+                                      double* out, int flags, cudaStream_t st) {
+  if (nlev) return bigsys_launch_tile_n<SRC, SOLVE, ACCUM, 1>(s, m, p0, p1, p2, p3, ra, rc, rs, rf, ured, out, flags, st);
+  return bigsys_launch_tile_n<SRC, SOLVE, ACCUM, 0>(s, m, p0, p1, p2, p3, ra, rc, rs, rf, ured, out, flags, st);
 }
 
 // forward sweeps of every grid level: each application of k_tri_tile leaves 2 rows per tile
@@ -646,13 +940,13 @@ inline int bigsys_forward(BigSys* s, const double* lo, const double* di, const d
   for (size_t k = 0; k < s->levels.size(); ++k) {
     BigLevel& L = s->levels[k];
     if (k == 0) {
-      bigsys_launch_tile<BS_SRC_BANDS, false, false>(s->tt, s->n, lo, di, up, f, L.a, L.c, L.s, L.f, nullptr, nullptr, flags, st);
+      e = bigsys_launch_tile<BS_SRC_BANDS, false, false>(s, L.nlev, s->n, lo, di, up, f, L.a, L.c, L.s, L.f, nullptr, nullptr, flags, st);
     } else {
       BigLevel& Q = s->levels[k - 1];
-      bigsys_launch_tile<BS_SRC_ROWS, false, false>(s->tt, Q.m, Q.a, Q.c, Q.s, Q.f, L.a, L.c, L.s, L.f, nullptr, nullptr, flags, st);
+      e = bigsys_launch_tile<BS_SRC_ROWS, false, false>(s, L.nlev, Q.m, Q.a, Q.c, Q.s, Q.f, L.a, L.c, L.s, L.f, nullptr, nullptr, flags, st);
     }
     ++*launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<reduce>");
+    if (e != cudaSuccess) return bigsys_fail(e, "k_tri_tile<reduce>");
   }
   return 0;
 }
@@ -664,15 +958,15 @@ inline int bigsys_backward(BigSys* s, const double* lo, const double* di, const 
     BigLevel& L = s->levels[k];
     if (k == 0) {
       if (accum)
-        bigsys_launch_tile<BS_SRC_BANDS, true, true>(s->tt, s->n, lo, di, up, f, nullptr, nullptr, nullptr, nullptr, L.u, out, flags, st);
+        e = bigsys_launch_tile<BS_SRC_BANDS, true, true>(s, L.nlev, s->n, lo, di, up, f, nullptr, nullptr, nullptr, nullptr, L.u, out, flags, st);
       else
-        bigsys_launch_tile<BS_SRC_BANDS, true, false>(s->tt, s->n, lo, di, up, f, nullptr, nullptr, nullptr, nullptr, L.u, out, flags, st);
+        e = bigsys_launch_tile<BS_SRC_BANDS, true, false>(s, L.nlev, s->n, lo, di, up, f, nullptr, nullptr, nullptr, nullptr, L.u, out, flags, st);
     } else {
       BigLevel& Q = s->levels[k - 1];
-      bigsys_launch_tile<BS_SRC_ROWS, true, false>(s->tt, Q.m, Q.a, Q.c, Q.s, Q.f, nullptr, nullptr, nullptr, nullptr, L.u, Q.u, flags, st);
+      e = bigsys_launch_tile<BS_SRC_ROWS, true, false>(s, L.nlev, Q.m, Q.a, Q.c, Q.s, Q.f, nullptr, nullptr, nullptr, nullptr, L.u, Q.u, flags, st);
     }
     ++*launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return bigsys_fail(e, "k_tri_tile<solve>");
+    if (e != cudaSuccess) return bigsys_fail(e, "k_tri_tile<solve>");
   }
   return 0;
 }
