@@ -109,7 +109,7 @@ __device__ __forceinline__ int row_slot(int r, int rows, int P) {
 
 // One chunk (thread t of P) of a shared-memory level, reduced rows -> next level (PN chunks; PN == 0: the next level is
 // the final 2-row system stored at index 0/1).
-template <bool FULL>  // FULL: len == 8, loops unrolled
+template <bool FULL, bool KEEP>  // FULL: len == 8, loops unrolled.  KEEP: leave (alpha~, g~, 1/P, delta~) for level_backsolve
 __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
   int idx = P + t;
@@ -123,7 +123,7 @@ __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int
     double D = sig - alp;               // sigma~ - alpha~
     double Pm = D - g;                  // P_1
     double rP = pivot_rcp(Pm);
-    lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rP, lv.d[idx] = dlt;
+    if (KEEP) lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rP, lv.d[idx] = dlt;
     double G = -C0;
     s_s = fma(G * rP, sig, S0), s_f = fma(G * rP, dlt, F0);
     double lastC = g, Cprev = g;
@@ -131,24 +131,25 @@ __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int
     for (int j = 2; j < BS_R; ++j) {
       if (FULL || j < len) {
         idx += P;
-        const double nA = -(lv.a[idx] * sc), Cj = lv.c[idx] * sc, Sj = lv.s[idx] * sc;
+        // the chunk's power-of-two scale rides on P_{j-1} (exact), so only A_j needs its own scaling
+        const double Ps = Pm * sc, nA = -(lv.a[idx] * sc), Cr = lv.c[idx], Sr = lv.s[idx];
         const double q = nA * D;
-        const double Pn = fma(Sj - Cj, Pm, q);  // P_j by its own two-term recurrence (see chunk0_forward)
-        D = fma(Sj, Pm, q);
-        sig = fma(Sj, Pm, nA * sig);
-        dlt = fma(lv.d[idx] * sc, Pm, nA * dlt);
+        const double Pn = fma(Sr - Cr, Ps, q);  // P_j by its own two-term recurrence (see chunk0_forward)
+        D = fma(Sr, Ps, q);
+        sig = fma(Sr, Ps, nA * sig);
+        dlt = fma(lv.d[idx], Ps, nA * dlt);
         alp = nA * alp;
-        g = Cj * Pm;
+        g = Cr * Ps;
         if (FULL ? j < BS_R - 1 : j < len - 1) {
           Pm = Pn;
           const double rPn = pivot_rcp(Pm);
-          lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rPn, lv.d[idx] = dlt;
+          if (KEEP) lv.a[idx] = alp, lv.c[idx] = g, lv.s[idx] = rPn, lv.d[idx] = dlt;
           G *= -Cprev;
           const double w = G * rPn * rP;
           s_s = fma(w, sig, s_s), s_f = fma(w, dlt, s_f);
-          lastC = Cj, rP = rPn;
+          lastC = Cr * sc, rP = rPn;
         }
-        Cprev = Cj;
+        Cprev = Cr * sc;
       }
     }
     s_c = G * lastC * rP;
@@ -157,9 +158,10 @@ __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int
   nx.a[p0] = A0, nx.c[p0] = s_c, nx.s[p0] = s_s, nx.d[p0] = s_f;
   nx.a[p1] = alp * rn, nx.c[p1] = g * rn, nx.s[p1] = sig * rn, nx.d[p1] = dlt * rn;
 }
+template <bool KEEP>
 __device__ __forceinline__ void level_reduce(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
-  if (len == BS_R) level_reduce_impl<true>(lv, P, len, nx, PN, t);
-  else level_reduce_impl<false>(lv, P, len, nx, PN, t);
+  if (len == BS_R) level_reduce_impl<true, KEEP>(lv, P, len, nx, PN, t);
+  else level_reduce_impl<false, KEEP>(lv, P, len, nx, PN, t);
 }
 // Back-substitution of the same chunk: the next level's d[] holds the solved u_s / u_e; this level's d[] receives u.
 __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
@@ -210,7 +212,7 @@ struct Pyramid {
     int off, rows, cap;
     __device__ __forceinline__ int pos(int r) const { return off + (cap ? lvl_pos(r, cap) : r); }
   };
-  template <int NLEV>
+  template <int NLEV, bool KEEP = true>  // KEEP == false: no back-substitution will follow
   __device__ __forceinline__ Left reduce_to(int t, int rows1) {
     Left out{0, rows1, P1};
     int lev = 0;
@@ -218,7 +220,7 @@ struct Pyramid {
     for (int p = P1;; p = (p + 3) / 4) {
       sync();
       const int pn = p == 1 ? 0 : (p + 3) / 4;
-      if (chunk_len(out.rows, t) > 0) level_reduce(level(out.off), p, chunk_len(out.rows, t), level(out.off + 8 * p), pn, t);
+      if (chunk_len(out.rows, t) > 0) level_reduce<KEEP>(level(out.off), p, chunk_len(out.rows, t), level(out.off + 8 * p), pn, t);
       out.off += 8 * p;
       out.rows = 2 * ((out.rows + BS_R - 1) / BS_R);
       out.cap = pn;
@@ -258,6 +260,16 @@ struct Pyramid {
   }
   __device__ __forceinline__ void backsolve(int t, int rows1) { backsolve_from<0>(t, rows1); }
 };
+// rows a tile holding rows1 level-1 rows leaves after NLEV level reductions (NLEV == 0: all of them)
+__host__ __device__ constexpr int bs_rows_left_of(int rows1, int P1, int NLEV) {
+  int rows = rows1;
+  for (int p = P1, lev = 0;; p = (p + 3) / 4) {
+    rows = 2 * ((rows + BS_R - 1) / BS_R);
+    ++lev;
+    if (p == 1 || lev == NLEV) break;
+  }
+  return rows;
+}
 // rows a full tile of 8 P1 level-1 rows leaves after NLEV level reductions (NLEV == 0: all of them)
 __host__ __device__ constexpr int bs_rows_left(int P1, int NLEV) {
   int rows = 8 * P1;
@@ -417,6 +429,12 @@ __device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs
 #pragma unroll
     for (int j = 0; j < BS_R; ++j) S[j] = excess3(A[j], S[j], C[j]);
   }
+  constexpr int ROUT = bs_rows_left(P1, NLEV);  // rows a full tile leaves
+  const long long obase = (long long)ROUT * tile;
+  // SOLVE: the solved unknowns of the level the pyramid stops at are fetched now (one per thread) and land while the
+  // sweeps run; read after the forward sweeps they would put an L2 round trip on every tile's critical path
+  double u_left = 0.0;
+  if (SOLVE && t < bs_rows_left_of(rows1, P1, NLEV)) u_left = k.ured[obase + t];
   // level 0 in registers; SOLVE keeps (alpha~_j, g~_j, 1/P_j, delta~_j) in (A, C, S, F)[1..len-2]
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
@@ -428,9 +446,8 @@ __device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs
   // hands all rows of that level to the next application (2 P1 of them after one level: a reduction by 16 instead of
   // 1024).  The upper levels keep one warp busy and seven parked, so a throughput-bound first application is better off
   // leaving them to the next one, which then works on a 16x smaller system with full CTAs again.
-  constexpr int ROUT = bs_rows_left(P1, NLEV);  // rows a full tile leaves
-  const typename Pyramid<P1, WARP>::Left left = pyr.template reduce_to<NLEV>(t, rows1);
-  const long long obase = (long long)ROUT * tile;
+  static_assert(ROUT <= 32 || !WARP, "one unknown per thread");
+  const typename Pyramid<P1, WARP>::Left left = pyr.template reduce_to<NLEV, SOLVE>(t, rows1);
   if (!SOLVE) {
     for (int r = t; r < left.rows; r += WARP ? 32 : BS_THREADS) {
       const int q = left.pos(r);
@@ -439,7 +456,7 @@ __device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs
     return;
   }
   if (SOLVE) {  // (a branch, not fall-through, only to keep the !SOLVE instantiation free of unreachable-code warnings)
-    for (int r = t; r < left.rows; r += WARP ? 32 : BS_THREADS) pyr.d[left.pos(r)] = k.ured[obase + r];
+    if (t < left.rows) pyr.d[left.pos(t)] = u_left;
     pyr.template backsolve_from<NLEV>(t, rows1);
   }
   if (len >= 2) {
@@ -869,11 +886,14 @@ inline EncodeTiledFn bigsys_encoder() {
   return fn;
 }
 // the array p[0..m) as 128-byte rows (only the floor(m / 16) complete ones: full tiles never reach past them)
-inline const CUtensorMap* bigsys_map(BigSys* s, const double* p, size_t m) {
+inline bool bigsys_map(BigSys* s, const double* p, size_t m, CUtensorMap* out) {
   for (const BigSys::Map& e : s->maps)
-    if (e.p == p && e.m == m) return &e.map;
+    if (e.p == p && e.m == m) {
+      *out = e.map;
+      return true;
+    }
   EncodeTiledFn enc = bigsys_encoder();
-  if (!enc) return nullptr;
+  if (!enc) return false;
   BigSys::Map e;
   e.p = p, e.m = m;
   const cuuint64_t dims[2] = {(cuuint64_t)BS_TMA_ROW, (cuuint64_t)(m / BS_TMA_ROW)};
@@ -882,10 +902,11 @@ inline const CUtensorMap* bigsys_map(BigSys* s, const double* p, size_t m) {
   const cuuint32_t estr[2] = {1, 1};
   if (enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return nullptr;
+    return false;
   if (s->maps.size() >= 32) s->maps.erase(s->maps.begin());
   s->maps.push_back(e);
-  return &s->maps.back().map;
+  *out = e.map;
+  return true;
 }
 inline int bigsys_sm_count() {
   static int n = [] {
@@ -907,8 +928,8 @@ inline cudaError_t bigsys_launch_tile_n(BigSys* s, size_t m, const double* p0, c
   const size_t tiles = (m + BS_TILE - 1) / BS_TILE;
   if (s->tma && tiles >= (size_t)BS_TMA_MIN_TILES &&
       !((reinterpret_cast<size_t>(p0) | reinterpret_cast<size_t>(p1) | reinterpret_cast<size_t>(p2) | reinterpret_cast<size_t>(p3)) & 15)) {
-    const CUtensorMap *m0 = bigsys_map(s, p0, m), *m1 = bigsys_map(s, p1, m), *m2 = bigsys_map(s, p2, m), *m3 = bigsys_map(s, p3, m);
-    if (m0 && m1 && m2 && m3) {
+    CUtensorMap c0, c1, c2, c3;  // by value: a lookup may grow the cache
+    if (bigsys_map(s, p0, m, &c0) && bigsys_map(s, p1, m, &c1) && bigsys_map(s, p2, m, &c2) && bigsys_map(s, p3, m, &c3)) {
       static bool attr_set = false;  // per instantiation
       if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_tri_tile_tma<SRC, SOLVE, ACCUM, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -917,7 +938,6 @@ inline cudaError_t bigsys_launch_tile_n(BigSys* s, size_t m, const double* p0, c
         attr_set = true;
       }
       const size_t grid = std::min(tiles, (size_t)2 * bigsys_sm_count());
-      const CUtensorMap c0 = *m0, c1 = *m1, c2 = *m2, c3 = *m3;  // bigsys_map may move its cache
       k_tri_tile_tma<SRC, SOLVE, ACCUM, NLEV><<<(unsigned)grid, BS_THREADS, BS_STAGE_SMEM, st>>>(c0, c1, c2, c3, k);
       return cudaGetLastError();
     }
