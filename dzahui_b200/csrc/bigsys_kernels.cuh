@@ -85,10 +85,15 @@ __device__ __forceinline__ double pivot_rcp(double x) {
   return fma(r, e, r);
 }
 
-// Shared-memory level: 8*P rows, SoA, row r of the level at (r % 8) * P + r / 8.
+// Shared-memory level of capacity p chunks: SoA, row r at (r % 8) * P + r / 8 with the row stride P = lvl_stride(p) = p + 2.
+// Chunk t reads its rows at j P + t (consecutive threads, consecutive words); the two pad words make the OTHER access
+// pattern conflict-free as well — thread t writing rows 2t, 2t+1 of the next level, or reading row t for the copy-out —
+// since (r % 8) * (p + 2) spreads the four even (odd) rows a half-warp touches over all 16 64-bit banks.  With P = p it
+// was a 4-way conflict on every level-1 store (ncu: 4.0 wavefronts per ideal one).
 struct LevelPtr {
   double *a, *c, *s, *d;
 };
+__host__ __device__ constexpr int lvl_stride(int p) { return p + 2; }
 __device__ __forceinline__ int lvl_pos(int r, int P) { return (r & 7) * P + (r >> 3); }
 
 // Ragged sizes are handled without padding rows: a level holds `rows` rows and its last chunk is simply shorter
@@ -101,14 +106,14 @@ __device__ __forceinline__ int chunk_len(int rows, int t) {
   if ((rows & 7) == 1 && rows > 1) return t == T ? 2 : (t == T - 1 ? 7 : (t < T ? BS_R : 0));
   return max(0, min(BS_R, rows - BS_R * t));
 }
-// slot (chunk-interleaved position) of row r of a level of `rows` rows with capacity P chunks
+// slot (chunk-interleaved position) of row r of a level of `rows` rows with row stride P
 __device__ __forceinline__ int row_slot(int r, int rows, int P) {
   if ((rows & 7) == 1 && r >= rows - 2 && rows > 1) return (r - (rows - 2)) * P + ((rows - 1) >> 3);
   return lvl_pos(r, P);
 }
 
-// One chunk (thread t of P) of a shared-memory level, reduced rows -> next level (PN chunks; PN == 0: the next level is
-// the final 2-row system stored at index 0/1).
+// One chunk (thread t) of a shared-memory level with row stride P, reduced rows -> next level (row stride PN; PN == 0: the
+// next level is the final 2-row system stored at index 0/1).
 template <bool FULL, bool KEEP>  // FULL: len == 8, loops unrolled.  KEEP: leave (alpha~, g~, 1/P, delta~) for level_backsolve
 __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
@@ -191,11 +196,11 @@ __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int l
 // of a CTA run their tiles independently; otherwise it belongs to the CTA (__syncthreads).
 template <int P>
 struct PyramidRows {
-  static constexpr int value = 8 * P + PyramidRows<(P + 3) / 4>::value;
+  static constexpr int value = 8 * lvl_stride(P) + PyramidRows<(P + 3) / 4>::value;
 };
 template <>
 struct PyramidRows<1> {
-  static constexpr int value = 8 + 2;
+  static constexpr int value = 8 * lvl_stride(1) + 2;
 };
 template <int P1, bool WARP = false>
 struct Pyramid {
@@ -207,21 +212,22 @@ struct Pyramid {
   }
   // Forward sweeps from level 1 (holding rows1 rows); every thread of the tile must call.  NLEV == 0: down to the final 2
   // rows.  NLEV > 0: only NLEV level reductions.  The level that is left starts at row `off` of the arrays, holds `rows`
-  // rows and is chunk-interleaved with capacity `cap` (row r at off + lvl_pos(r, cap); cap == 0: the final pair, at off + r).
+  // rows and is chunk-interleaved with row stride `cap` (row r at off + lvl_pos(r, cap); cap == 0: the final pair, at off + r).
   struct Left {
     int off, rows, cap;
     __device__ __forceinline__ int pos(int r) const { return off + (cap ? lvl_pos(r, cap) : r); }
   };
   template <int NLEV, bool KEEP = true>  // KEEP == false: no back-substitution will follow
   __device__ __forceinline__ Left reduce_to(int t, int rows1) {
-    Left out{0, rows1, P1};
+    Left out{0, rows1, lvl_stride(P1)};
     int lev = 0;
 #pragma unroll
     for (int p = P1;; p = (p + 3) / 4) {
       sync();
-      const int pn = p == 1 ? 0 : (p + 3) / 4;
-      if (chunk_len(out.rows, t) > 0) level_reduce<KEEP>(level(out.off), p, chunk_len(out.rows, t), level(out.off + 8 * p), pn, t);
-      out.off += 8 * p;
+      const int pn = p == 1 ? 0 : lvl_stride((p + 3) / 4);  // row stride of the next level
+      if (chunk_len(out.rows, t) > 0)
+        level_reduce<KEEP>(level(out.off), lvl_stride(p), chunk_len(out.rows, t), level(out.off + 8 * lvl_stride(p)), pn, t);
+      out.off += 8 * lvl_stride(p);
       out.rows = 2 * ((out.rows + BS_R - 1) / BS_R);
       out.cap = pn;
       ++lev;
@@ -242,7 +248,7 @@ struct Pyramid {
 #pragma unroll
       for (int p = P1;; p = (p + 3) / 4) {
         rows_at[nl] = rows, cap[nl] = p, offs[nl] = off, ++nl;
-        off += 8 * p;
+        off += 8 * lvl_stride(p);
         rows = 2 * ((rows + BS_R - 1) / BS_R);
         if (p == 1 || nl == NLEV) break;
       }
@@ -253,7 +259,8 @@ struct Pyramid {
         const int p = cap[k];
         sync();
         if (chunk_len(rows_at[k], t) > 0)
-          level_backsolve(level(offs[k]), p, chunk_len(rows_at[k], t), level(offs[k] + 8 * p), p == 1 ? 0 : (p + 3) / 4, t);
+          level_backsolve(level(offs[k]), lvl_stride(p), chunk_len(rows_at[k], t), level(offs[k] + 8 * lvl_stride(p)),
+                          p == 1 ? 0 : lvl_stride((p + 3) / 4), t);
       }
     }
     sync();
@@ -438,7 +445,7 @@ __device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs
   // level 0 in registers; SOLVE keeps (alpha~_j, g~_j, 1/P_j, delta~_j) in (A, C, S, F)[1..len-2]
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
-    const int i0 = lvl_pos(2 * t, P1), i1 = lvl_pos(2 * t + 1, P1);
+    const int i0 = lvl_pos(2 * t, lvl_stride(P1)), i1 = lvl_pos(2 * t + 1, lvl_stride(P1));
     if (len == BS_R) chunk0_forward<SOLVE, true>(A, C, S, F, len, l1, i0, i1);
     else chunk0_forward<SOLVE, false>(A, C, S, F, len, l1, i0, i1);
   }
@@ -461,7 +468,7 @@ __device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs
   }
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
-    const double us = l1.d[lvl_pos(2 * t, P1)], ue = l1.d[lvl_pos(2 * t + 1, P1)];
+    const double us = l1.d[lvl_pos(2 * t, lvl_stride(P1))], ue = l1.d[lvl_pos(2 * t + 1, lvl_stride(P1))];
     double* __restrict__ out = k.out;
     double o[BS_R];
     // A decoupled end row of the caller's system (a Dirichlet row: lo = up = 0) is returned exactly as Thomas returns it,
@@ -535,7 +542,7 @@ struct TileStage {
   Pyramid<BS_THREADS / 4> pyr;
   alignas(8) unsigned long long mbar;
 };
-constexpr size_t BS_STAGE_SMEM = sizeof(TileStage) + 1024;  // + slack to align the dynamic window to 1024 B
+constexpr size_t BS_STAGE_SMEM = sizeof(TileStage);
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
@@ -568,8 +575,9 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_tile_tma(const __grid_con
                                                                 const __grid_constant__ CUtensorMap map1,
                                                                 const __grid_constant__ CUtensorMap map2,
                                                                 const __grid_constant__ CUtensorMap map3, const TileArgs k) {
-  extern __shared__ unsigned char tile_stage_raw[];
-  TileStage& sm = *reinterpret_cast<TileStage*>((reinterpret_cast<size_t>(tile_stage_raw) + 1023) & ~(size_t)1023);
+  extern __shared__ __align__(1024) unsigned char tile_stage_raw[];  // the kernel has no static shared memory
+  TileStage& sm = *reinterpret_cast<TileStage*>(tile_stage_raw);
+  if (smem_u32(tile_stage_raw) & 1023) __trap();  // SWIZZLE_128B needs the stage on a 1024-byte boundary
   const int t = threadIdx.x;
   const long long ntiles = (k.m + BS_TILE - 1) / BS_TILE;
   if (t == 0) mbar_init(&sm.mbar, 1);
@@ -645,7 +653,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict
   const bool open_left = flags & BS_OPEN_LEFT, open_right = flags & BS_OPEN_RIGHT;
   LevelPtr l1 = pyr.level(0);
   for (int r = t; r < m; r += BS_THREADS) {
-    const int p = row_slot(r, m, P1);
+    const int p = row_slot(r, m, lvl_stride(P1));
     const double a = (r > 0 || open_left) ? p0[r] : 0.0;
     const double c = (r < m - 1 || open_right) ? (SRC == BS_SRC_BANDS ? p2[r] : p1[r]) : 0.0;
     l1.a[p] = a, l1.c[p] = c, l1.s[p] = SRC == BS_SRC_BANDS ? excess3(a, p1[r], c) : p2[r], l1.d[p] = p3[r];
@@ -670,7 +678,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict
   }
   pyr.backsolve(t, m);
   for (int r = t; r < m; r += BS_THREADS) {
-    double v = l1.d[row_slot(r, m, P1)];
+    double v = l1.d[row_slot(r, m, lvl_stride(P1))];
     if (SRC == BS_SRC_BANDS) {  // exact Dirichlet end rows, as in k_tri_tile
       if (r == 0 && !open_left && p2[0] == 0.0) v = p3[0] / p1[0];
       if (r == m - 1 && !open_right && p0[m - 1] == 0.0) v = p3[m - 1] / p1[m - 1];
@@ -779,7 +787,8 @@ struct BigLevel {
 struct BigSys {
   size_t n = 0;
   size_t shallow_min_tiles = BS_SHALLOW_MIN_TILES;  // applications with at least this many tiles stop after one level
-  bool tma = true;  // big band systems go through k_tri_tile_tma (DZB_NO_TMA=1: always k_tri_tile)
+  bool tma = true;  // big systems go through k_tri_tile_tma (DZB_NO_TMA=1: always k_tri_tile)
+  size_t tma_min_tiles = BS_TMA_MIN_TILES;
   struct Map {
     const double* p;
     size_t m;
@@ -825,6 +834,7 @@ inline int bigsys_prepare(BigSys* s, size_t n) {
   s->n = n;
   if (const char* v = std::getenv("DZB_SHALLOW_MIN_TILES")) s->shallow_min_tiles = (size_t)std::atoll(v);  // tuning knob
   if (const char* v = std::getenv("DZB_NO_TMA")) s->tma = std::atoi(v) == 0;
+  if (const char* v = std::getenv("DZB_TMA_MIN_TILES")) s->tma_min_tiles = (size_t)std::atoll(v);  // tuning knob
   s->maps.clear();
   cudaError_t e;
   size_t m = n;
@@ -926,7 +936,7 @@ inline cudaError_t bigsys_launch_tile_n(BigSys* s, size_t m, const double* p0, c
                                         cudaStream_t st) {
   const TileArgs k{p0, p1, p2, p3, (long long)m, ra, rc, rs, rf, ured, out, flags};
   const size_t tiles = (m + BS_TILE - 1) / BS_TILE;
-  if (s->tma && tiles >= (size_t)BS_TMA_MIN_TILES &&
+  if (s->tma && tiles >= s->tma_min_tiles &&
       !((reinterpret_cast<size_t>(p0) | reinterpret_cast<size_t>(p1) | reinterpret_cast<size_t>(p2) | reinterpret_cast<size_t>(p3)) & 15)) {
     CUtensorMap c0, c1, c2, c3;  // by value: a lookup may grow the cache
     if (bigsys_map(s, p0, m, &c0) && bigsys_map(s, p1, m, &c1) && bigsys_map(s, p2, m, &c2) && bigsys_map(s, p3, m, &c3)) {
