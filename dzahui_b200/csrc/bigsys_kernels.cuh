@@ -5,11 +5,13 @@
 // interior unknowns and leaves two equations coupling the chunk's first/last unknown (u_s, u_e) with the neighbouring
 // chunks — again a tridiagonal system, of a quarter of the size, in the order (s_0, e_0, s_1, e_1, ...).  The reduction
 // is applied recursively:
-//     level 0   registers      2048 rows per CTA (256 threads x 8 rows, 128-bit loads)
-//     level 1-4 shared memory  512 -> 128 -> 32 -> 8 -> 2 rows, chunk-interleaved SoA (conflict-free)
-//     grid      k_tri_tile<REDUCE> writes 2 rows per tile; k_tri_mid (one CTA, shared memory only) solves that system
-//               (recursing through k_tri_tile again while it exceeds 2048 rows); k_tri_tile<SOLVE> redoes the forward
-//               sweeps on chip and back-substitutes.  HBM traffic: 32 B/row (reduce) + 40 B/row (solve).
+//     level 0   registers      2048 rows per CTA (256 threads x 8 rows; TMA-staged through shared memory, or direct
+//                              128-bit loads for ragged / unaligned tiles)
+//     level 1-4 shared memory  512 -> 128 -> 32 -> 8 -> 2 rows, chunk-interleaved SoA with a padded row stride
+//     grid      k_tri_tile[_tma]<REDUCE> hands 2 rows per tile (full pyramid) or, when the application is throughput
+//               bound, the 128 rows of level 2 (one shared-memory level only) to the next application; k_tri_mid (one
+//               CTA, shared memory only) solves what is left once it is <= 2048 rows; k_tri_tile[_tma]<SOLVE> redoes
+//               the forward sweeps on chip and back-substitutes.  HBM traffic: 32 B/row (reduce) + 40 B/row (solve).
 //
 // Accuracy.  A plain partitioned elimination is ~150x LESS accurate than serial Thomas on the n = 10^7 stiffness matrix
 // (identical chunks make identical rounding errors, which add up coherently in the nearly-cancelling row sums).  Rows are
