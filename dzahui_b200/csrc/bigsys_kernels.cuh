@@ -27,7 +27,9 @@
 // by P_{j-1},
 //     sigma~_j = S_j P_{j-1} - A_j sigma~_{j-1},   alpha~_j = -A_j alpha~_{j-1},   delta~_j = F_j P_{j-1} - A_j delta~_{j-1},
 //     g~_j = C_j P_{j-1},   P_j = sigma~_j - alpha~_j - g~_j          (row j:  alpha~_j u_s + P_j u_j + g~_j u_{j+1} = delta~_j)
-// so a step is 3 dependent fp64 operations instead of ~14 (the reciprocals 1/P_j are off the chain and pipeline).  The
+// The minors themselves are advanced by the equivalent two-term form  P_j = (S_j - C_j) P_{j-1} - A_j D_{j-1},
+// D_j = sigma~_j - alpha~_j = S_j P_{j-1} - A_j D_{j-1}  (same-signed sums again), so a step has 2 dependent fp64 operations on
+// its chain instead of ~14; the reciprocals 1/P_j (hardware seed + two Newton steps, pivot_rcp) are off the chain.  The
 // chunk is first scaled by the power of two nearest 1/beta_1, which keeps P_j ~ O(1) for any magnitude of the entries.
 //   e-row = (alpha~_7, g~_7, sigma~_7, delta~_7) / P_6;  the s-row needs rows 1..6 folded back into row 0, accumulated on
 //   the way with G_j = (-C_0)(-C_1)...(-C_{j-1}):  s-row = (A_0, G_6 C_6 / P_6, S_0 + sum_j G_j sigma~_j / (P_j P_{j-1}),
