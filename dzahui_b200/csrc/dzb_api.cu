@@ -276,6 +276,7 @@ struct dzb_ensemble {
   double* d_mesh = nullptr;
   double *mlo = nullptr, *mdi = nullptr, *mup = nullptr, *slo = nullptr, *sdi = nullptr, *sup = nullptr;  // natural [B][n]
   double *c = nullptr, *den = nullptr;                                                                     // natural [B][n]
+  double* rden = nullptr;  // RN(1 / den), only for the warp-per-bar FAITHFUL kernels (B <= TW_MAX_BARS)
   double *a_lo = nullptr, *a_di = nullptr, *a_up = nullptr, *alpha = nullptr, *cc = nullptr;               // interleaved [B][32 L]
   double *bdi = nullptr, *idn = nullptr, *hh = nullptr;  // lean step: unscaled diagonal, 1/den, element lengths (interleaved)
   int* d_bad = nullptr;
@@ -294,7 +295,7 @@ struct dzb_solver {
   int kind = 0;  // dzb::KIND_*
   size_t n = 0;
   // static solvers
-  double *lo = nullptr, *di = nullptr, *up = nullptr, *rhs = nullptr, *c = nullptr, *den = nullptr, *out = nullptr;
+  double *lo = nullptr, *di = nullptr, *up = nullptr, *rhs = nullptr, *c = nullptr, *den = nullptr, *rden = nullptr, *out = nullptr;
   bool parallel = false;       // the partitioned solver is in use (requested and the matrix allows it)
   bool want_parallel = false;  // DZB_SOLVE_PARALLEL requested / chosen by AUTO
   const dzb_mesh* classified_mesh = nullptr;  // the matrix class (M-matrix / dominant) was decided for this mesh ...
@@ -332,8 +333,8 @@ int host_nodes(const dzb_mesh* cm, const std::vector<double>** out) {
 
 void ensemble_free(dzb_ensemble* e) {
   if (!e) return;
-  for (double** p : {&e->d_mesh, &e->mlo, &e->mdi, &e->mup, &e->slo, &e->sdi, &e->sup, &e->c, &e->den, &e->a_lo, &e->a_di, &e->a_up,
-                     &e->alpha, &e->cc, &e->u[0], &e->u[1], &e->bdi, &e->idn, &e->hh})
+  for (double** p : {&e->d_mesh, &e->mlo, &e->mdi, &e->mup, &e->slo, &e->sdi, &e->sup, &e->c, &e->den, &e->rden, &e->a_lo, &e->a_di,
+                     &e->a_up, &e->alpha, &e->cc, &e->u[0], &e->u[1], &e->bdi, &e->idn, &e->hh})
     dfree(*p);
   if (e->d_bad) cudaFree(e->d_bad), e->d_bad = nullptr;
   dzb::bigsys_free(&e->big);
@@ -453,9 +454,13 @@ int ensemble_step_once(dzb_ensemble* e, double dt) {
     }
     if (rc) return rc;
   } else {
-    dzb::k_td_step_faithful<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->mlo, e->mdi, e->mup,
-                                                                                 e->slo, e->sdi, e->sup, e->c, e->den, (long long)e->n,
-                                                                                 (long long)e->B, dt, e->bc0, e->bc1);
+    if ((long long)e->B <= dzb::TW_MAX_BARS)  // few bars: a warp per bar (same arithmetic, operands staged through shared memory)
+      dzb::k_td_step_faithful_warp<<<(unsigned)e->B, 32, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->mlo, e->mdi, e->mup, e->slo,
+                                                                        e->sdi, e->sup, e->c, e->den, e->rden, (long long)e->n, dt, e->bc0, e->bc1);
+    else
+      dzb::k_td_step_faithful<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->mlo, e->mdi,
+                                                                                   e->mup, e->slo, e->sdi, e->sup, e->c, e->den,
+                                                                                   (long long)e->n, (long long)e->B, dt, e->bc0, e->bc1);
     LAUNCHED();
   }
   e->cur ^= 1;
@@ -487,8 +492,12 @@ int ensemble_assemble(dzb_ensemble* e) {
     e->use_big = ok;
   }
   if (!e->use_big) {
-    dzb::k_thomas_factor<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)e->n,
-                                                                              (long long)e->B);
+    if ((long long)e->B <= dzb::TW_MAX_BARS && !e->rden && (rc = dalloc(&e->rden, e->B * e->n))) return rc;
+    if ((long long)e->B <= dzb::TW_MAX_BARS)
+      dzb::k_thomas_factor_warp<<<(unsigned)e->B, 32, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, e->rden, (long long)e->n);
+    else
+      dzb::k_thomas_factor<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)e->n,
+                                                                                (long long)e->B);
     LAUNCHED();
   }
   e->prepared = false;
@@ -921,7 +930,8 @@ static int static_factor(dzb_solver* s, const dzb_mesh* m) {
   } else {
     if (!s->c && (rc = dalloc(&s->c, s->n))) return rc;
     if (!s->den && (rc = dalloc(&s->den, s->n))) return rc;
-    dzb::k_thomas_factor<<<1, 32, 0, g_stream>>>(s->lo, s->di, s->up, s->c, s->den, (long long)s->n, 1);
+    if (!s->rden && (rc = dalloc(&s->rden, s->n))) return rc;
+    dzb::k_thomas_factor_warp<<<1, 32, 0, g_stream>>>(s->lo, s->di, s->up, s->c, s->den, s->rden, (long long)s->n);
     LAUNCHED();
   }
   return DZB_OK;
@@ -1061,7 +1071,7 @@ int dzb_solver_solve_device(dzb_solver* s, double dt, const double** dev) {
     if (dzb::bigsys_solve(&s->big, s->lo, s->di, s->up, s->rhs, s->out, s->refine_steps, g_stream, &g_launches))
       return fail(DZB_CUDA, dzb::bigsys_error());
   } else {
-    dzb::k_thomas_solve_faithful<<<1, 32, 0, g_stream>>>(s->lo, s->c, s->den, s->rhs, s->out, (long long)s->n, 1);
+    dzb::k_thomas_solve_faithful_warp<<<1, 32, 0, g_stream>>>(s->lo, s->c, s->den, s->rden, s->rhs, s->out, (long long)s->n);
     LAUNCHED();
   }
   *dev = s->out;
@@ -1113,7 +1123,7 @@ void dzb_solver_destroy(dzb_solver* s) {
     if (*p) *p -= s->off;
     dfree(*p);
   }
-  for (double** p : {&s->c, &s->den, &s->out, &s->d_top8}) dfree(*p);
+  for (double** p : {&s->c, &s->den, &s->rden, &s->out, &s->d_top8}) dfree(*p);
   dzb::bigsys_free(&s->big);
   ensemble_free(s->td);
   delete s;

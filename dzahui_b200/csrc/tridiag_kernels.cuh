@@ -42,26 +42,6 @@ __global__ void k_thomas_factor(const double* __restrict__ lo, const double* __r
   c[o + n - 1] = 0.0;
 }
 
-// ---- FAITHFUL: solve_by_thomas with precomputed (bit-identical) c / den ------------------------------------------
-__global__ void k_thomas_solve_faithful(const double* __restrict__ lo, const double* __restrict__ c,
-                                        const double* __restrict__ den, const double* __restrict__ rhs,
-                                        double* __restrict__ out, long long n, long long n_bars) {
-  const long long bar = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (bar >= n_bars) return;
-  const long long o = bar * n;
-  double d = rhs[o] / den[o];
-  out[o] = d;
-  for (long long i = 1; i < n; ++i) {
-    d = (rhs[o + i] - lo[o + i] * d) / den[o + i];
-    out[o + i] = d;
-  }
-  double s = d;
-  for (long long i = n - 2; i >= 0; --i) {
-    s = out[o + i] - c[o + i] * s;
-    out[o + i] = s;
-  }
-}
-
 // ---- FAITHFUL: one DiffussionSolverTimeDependent::solve(dt) per thread (time_dependent.rs:257-280) ---------------
 __global__ void k_td_step_faithful(const double* __restrict__ u, double* __restrict__ u_new,
                                    const double* __restrict__ mlo, const double* __restrict__ mdi,
@@ -100,6 +80,259 @@ __global__ void k_td_step_faithful(const double* __restrict__ u, double* __restr
   }
   u_new[o] = bc0;          // :273
   u_new[o + n - 1] = bc1;  // :274
+}
+
+// ---- FAITHFUL, one warp per bar ---------------------------------------------------------------------------------------
+// The kernels above run a bar's recurrence in one thread and leave every load on its dependent chain: ~600 cycles
+// per row measured on one bar (0.32 ms for the reference's own 1000-node case), ten times what the arithmetic needs.  These
+// versions give a bar to a warp: the lanes stream 256-row chunks through shared memory (coalesced; the next chunk is
+// already in flight in registers while the current one is swept) and lane 0 runs exactly the same expressions in the same
+// order on operands that are one LDS away.  Bit-identical to the kernels above (and to the oracle); used when there are
+// few bars (the reference's single-bar solvers), where latency, not throughput, is what a caller sees.
+// The forward sweep divides by den_i on its dependent chain (an IEEE division is ~130 cycles: reciprocal seed, Newton
+// steps, a slow-path check that is also a scheduling barrier).  den is known from the factorisation, so the factor kernel
+// also stores r_i = RN(1 / den_i) (__drcp_rn, off every chain) and the sweep forms the quotient by Markstein's sequence
+//     q0 = RN(a r),  e0 = RN(a - den q0),  q1 = RN(q0 + e0 r)      (q1 is a faithful rounding of a / den)
+//     e1 = a - den q1  (exact, one fma),   q  = RN(q1 + e1 r)
+// and q IS the correctly rounded a / den whenever r is the correctly rounded reciprocal, q1 is faithful and nothing
+// under/overflows (Markstein 1990; Muller et al., Handbook of Floating-Point Arithmetic, section 4.7) — five dependent
+// operations, ~40 cycles.  The first correction is there because q0 alone can be 2 ulps off when den's significand is
+// close to all ones (tools/check_exact_div.py replays the sequence in exact rational arithmetic on adversarial
+// operands: e1 always exact, no mismatch in 2 million cases; tests/test_abi_and_host.py runs a sample).  Outside a generous
+// safe range (zero, tiny, huge or non-finite numerator; a chunk whose denominators are not all comfortably normal) the
+// sweep falls back to the division itself, so the result has the bits of a / den in every case.
+__device__ __noinline__ double exact_div_slow(double a, double den) { return a / den; }  // never speculated: a real call
+__device__ __forceinline__ double exact_div(double a, double den, double r, bool den_safe) {
+  // the sequence is issued unconditionally and the range test, which needs only `a`, runs beside it instead of in front
+  const double q0 = a * r;
+  const double e0 = fma(-den, q0, a);
+  const double q1 = fma(e0, r, q0);
+  const double e1 = fma(-den, q1, a);
+  double q = fma(e1, r, q1);
+  const double t = fabs(a);
+  if (!(den_safe && t > 0x1p-800 && t < 0x1p+800)) {
+    // a signed zero over a normal den (homogeneous right-hand sides: the common case of the static problem): RN(a r)
+    // already has the right sign, the corrections would turn -0 into +0.  Everything else: the division itself.
+    if (den_safe && t == 0.0) q = q0;
+    else q = exact_div_slow(a, den);
+  }
+  return q;
+}
+__device__ __forceinline__ bool den_in_safe_range(double den) {
+  const double t = fabs(den);
+  return t > 0x1p-200 && t < 0x1p+200;
+}
+
+constexpr int TW_CH = 256;         // rows per staged chunk
+constexpr int TW_K = TW_CH / 32;   // rows per lane per chunk
+constexpr long long TW_MAX_BARS = 2048;  // beyond this the thread-per-bar kernels have enough bars to fill the GPU
+
+struct WarpStage3 {  // three input streams, chunk by chunk, double-buffered through registers
+  double ra[TW_K], rb[TW_K], rc[TW_K];
+  __device__ __forceinline__ void fetch(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                                        long long base, long long n, int lane) {
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) {
+      const long long i = base + k * 32 + lane;
+      const bool in = i >= 0 && i < n;
+      ra[k] = in ? a[i] : 0.0, rb[k] = in ? b[i] : 0.0, rc[k] = in ? c[i] : 0.0;
+    }
+  }
+  __device__ __forceinline__ void commit(double* sa, double* sb, double* sc, int lane) const {
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) sa[k * 32 + lane] = ra[k], sb[k * 32 + lane] = rb[k], sc[k * 32 + lane] = rc[k];
+  }
+};
+
+__global__ void __launch_bounds__(32) k_thomas_factor_warp(const double* __restrict__ lo, const double* __restrict__ di,
+                                                           const double* __restrict__ up, double* __restrict__ c,
+                                                           double* __restrict__ den, double* __restrict__ rden, long long n) {
+  __shared__ double s_lo[TW_CH], s_di[TW_CH], s_up[TW_CH], s_c[TW_CH], s_den[TW_CH];
+  const int lane = threadIdx.x;
+  const long long o = (long long)blockIdx.x * n;
+  lo += o, di += o, up += o, c += o, den += o, rden += o;
+  WarpStage3 st;
+  st.fetch(lo, di, up, 0, n, lane);
+  double cp = 0.0;
+  for (long long base = 0; base < n; base += TW_CH) {
+    const int len = (int)min((long long)TW_CH, n - base);
+    st.commit(s_lo, s_di, s_up, lane);
+    __syncwarp();
+    if (base + TW_CH < n) st.fetch(lo, di, up, base + TW_CH, n, lane);
+    if (lane == 0) {
+      int j = 0;
+      if (base == 0) {  // row 0
+        cp = s_up[0] / s_di[0];
+        s_c[0] = cp, s_den[0] = s_di[0];
+        j = 1;
+      }
+      const int jend = (base + len == n) ? len - 1 : len;  // the last row of the bar is handled below
+#pragma unroll 4
+      for (; j < jend; ++j) {
+        const double dn = s_di[j] - s_lo[j] * cp;
+        cp = s_up[j] / dn;
+        s_c[j] = cp, s_den[j] = dn;
+      }
+      if (base + len == n && (n > 1)) {
+        s_den[len - 1] = s_di[len - 1] - s_lo[len - 1] * cp;
+        s_c[len - 1] = 0.0;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) {
+      const int j = k * 32 + lane;
+      if (j < len) c[base + j] = s_c[j], den[base + j] = s_den[j], rden[base + j] = __drcp_rn(s_den[j]);
+    }
+    __syncwarp();
+  }
+}
+
+// forward + backward sweeps of solve_by_thomas (matrix_solver/mod.rs:17-48, with the bit-identical c / den of the factor
+// kernel) on staged operands; `chunk_rhs(base, len)` must fill s_rhs[0..len)
+// (all lanes) with the bar's right-hand side rows base.. before the chunk is swept
+template <class RhsFn>
+__device__ __forceinline__ void warp_thomas_sweeps(const double* __restrict__ lo, const double* __restrict__ c,
+                                                   const double* __restrict__ den, const double* __restrict__ rden,
+                                                   double* __restrict__ out, long long n, int lane, double* s_lo, double* s_den,
+                                                   double* s_r, double* s_rhs, double* s_out, RhsFn chunk_rhs) {
+  // ---- forward: d_0 = rhs_0 / den_0, d_i = (rhs_i - lo_i d_{i-1}) / den_i
+  WarpStage3 st;
+  st.fetch(lo, den, rden, 0, n, lane);
+  double d = 0.0;
+  for (long long base = 0; base < n; base += TW_CH) {
+    const int len = (int)min((long long)TW_CH, n - base);
+    st.commit(s_lo, s_den, s_r, lane);
+    bool safe = true;
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) safe = safe && (base + k * 32 + lane >= n || den_in_safe_range(st.rb[k]));
+    safe = __all_sync(0xffffffffu, safe);
+    chunk_rhs(base, len);
+    __syncwarp();
+    if (base + TW_CH < n) st.fetch(lo, den, rden, base + TW_CH, n, lane);
+    if (lane == 0) {
+      int j = 0;
+      if (base == 0) {
+        d = exact_div(s_rhs[0], s_den[0], s_r[0], safe);
+        s_out[0] = d;
+        j = 1;
+      }
+      // the operands of row j + 1 are read while row j is on the chain (the arrays have one spare slot at the end)
+      double a = s_lo[j], dn = s_den[j], r = s_r[j], b = s_rhs[j];
+#pragma unroll 4
+      for (; j < len; ++j) {
+        const double na = s_lo[j + 1], ndn = s_den[j + 1], nr = s_r[j + 1], nb = s_rhs[j + 1];
+        d = exact_div(b - a * d, dn, r, safe);
+        s_out[j] = d;
+        a = na, dn = ndn, r = nr, b = nb;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) {
+      const int j = k * 32 + lane;
+      if (j < len) out[base + j] = s_out[j];
+    }
+    __syncwarp();
+  }
+  // ---- backward: x_{n-1} = d_{n-1}, x_i = d_i - c_i x_{i+1}; chunks from the top, s_lo / s_den now hold c / d
+  double* s_c = s_lo + 1;  // one spare slot in FRONT this time: the pipelined loop reads index -1
+  double* s_d = s_den + 1;
+  const long long last = ((n - 1) / TW_CH) * TW_CH;
+  double r_c[TW_K], r_d[TW_K];
+  auto fetch_b = [&](long long base) {
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) {
+      const long long i = base + k * 32 + lane;
+      r_c[k] = i < n ? c[i] : 0.0, r_d[k] = i < n ? out[i] : 0.0;
+    }
+  };
+  fetch_b(last);
+  double x = 0.0;
+  for (long long base = last; base >= 0; base -= TW_CH) {
+    const int len = (int)min((long long)TW_CH, n - base);
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) s_c[k * 32 + lane] = r_c[k], s_d[k * 32 + lane] = r_d[k];
+    __syncwarp();
+    if (base >= TW_CH) fetch_b(base - TW_CH);
+    if (lane == 0) {
+      int j = len - 1;
+      if (base == last) {  // the bar's last row: x = d
+        x = s_d[j];
+        s_out[j] = x;
+        --j;
+      }
+      double cc = s_c[j], dd = s_d[j];
+#pragma unroll 4
+      for (; j >= 0; --j) {
+        const double nc = s_c[j - 1], nd = s_d[j - 1];
+        x = dd - cc * x;
+        s_out[j] = x;
+        cc = nc, dd = nd;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) {
+      const int j = k * 32 + lane;
+      if (j < len) out[base + j] = s_out[j];
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32) k_thomas_solve_faithful_warp(const double* __restrict__ lo, const double* __restrict__ c,
+                                                                   const double* __restrict__ den, const double* __restrict__ rden,
+                                                                   const double* __restrict__ rhs, double* __restrict__ out,
+                                                                   long long n) {
+  __shared__ double s_lo[TW_CH + 2], s_den[TW_CH + 2], s_r[TW_CH + 2], s_rhs[TW_CH + 2], s_out[TW_CH];
+  const int lane = threadIdx.x;
+  const long long o = (long long)blockIdx.x * n;
+  rhs += o;
+  warp_thomas_sweeps(lo + o, c + o, den + o, rden + o, out + o, n, lane, s_lo, s_den, s_r, s_rhs, s_out, [&](long long base, int len) {
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) {
+      const int j = k * 32 + lane;
+      if (j < len) s_rhs[j] = rhs[base + j];
+    }
+  });
+}
+
+// one DiffussionSolverTimeDependent::solve(dt) of one bar per warp: the right-hand side rows are independent of one
+// another (same expressions as k_td_step_faithful, evaluated by all lanes), the sweeps are warp_thomas_sweeps
+__global__ void __launch_bounds__(32) k_td_step_faithful_warp(const double* __restrict__ u, double* __restrict__ u_new,
+                                                              const double* __restrict__ mlo, const double* __restrict__ mdi,
+                                                              const double* __restrict__ mup, const double* __restrict__ slo,
+                                                              const double* __restrict__ sdi, const double* __restrict__ sup,
+                                                              const double* __restrict__ c, const double* __restrict__ den,
+                                                              const double* __restrict__ rden, long long n, double dt, double bc0,
+                                                              double bc1) {
+  __shared__ double s_lo[TW_CH + 2], s_den[TW_CH + 2], s_r[TW_CH + 2], s_rhs[TW_CH + 2], s_out[TW_CH];
+  const int lane = threadIdx.x;
+  const long long o = (long long)blockIdx.x * n;
+  u += o, u_new += o, mlo += o, mdi += o, mup += o, slo += o, sdi += o, sup += o;
+  warp_thomas_sweeps(mlo, c + o, den + o, rden + o, u_new, n, lane, s_lo, s_den, s_r, s_rhs, s_out, [&](long long base, int len) {
+#pragma unroll
+    for (int k = 0; k < TW_K; ++k) {
+      const int j = k * 32 + lane;
+      if (j < len) {
+        const long long i = base + j;
+        double b1, b2;  // b = add(c*(S u), 1*(M u))   utils.rs:52-59, :16-30
+        if (i == 0) {
+          b1 = dt * (sdi[i] * u[i] + sup[i] * u[i + 1]);
+          b2 = 1.0 * (mdi[i] * u[i] + mup[i] * u[i + 1]);
+        } else if (i == n - 1) {
+          b1 = dt * (slo[i] * u[i - 1] + sdi[i] * u[i]);
+          b2 = 1.0 * (mlo[i] * u[i - 1] + mdi[i] * u[i]);
+        } else {
+          b1 = dt * (slo[i] * u[i - 1] + sdi[i] * u[i] + sup[i] * u[i + 1]);
+          b2 = 1.0 * (mlo[i] * u[i - 1] + mdi[i] * u[i] + mup[i] * u[i + 1]);
+        }
+        s_rhs[j] = b1 + b2;
+      }
+    }
+  });
+  if (lane == 0) u_new[0] = bc0, u_new[n - 1] = bc1;  // time_dependent.rs:273-274
 }
 
 // ---- FAST path ----------------------------------------------------------------------------------------------------

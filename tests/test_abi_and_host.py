@@ -181,3 +181,14 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_exact_division_sequence_is_correctly_rounded():
+    """exact_div() of tridiag_kernels.cuh (quotient by a precomputed correctly rounded reciprocal + two corrections, used
+    by the warp-per-bar FAITHFUL sweeps) replayed in exact rational arithmetic: the bits of a / den, every time"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("check_exact_div", os.path.join(ROOT, "tools", "check_exact_div.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    bad, inexact = mod.run(seed=2026, cases=30000)
+    assert bad == 0 and inexact == 0

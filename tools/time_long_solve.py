@@ -12,7 +12,7 @@ def main():
         x = np.linspace(0.0, 1.0, n)
         mesh = dz.Mesh.from_nodes(x)
         p = params.DiffussionParams.time_independent().mu(1.0).b(0.5).boundary_conditions(0.0, 1.0).build()
-        s = solvers.DiffussionSolverTimeIndependent(p, mesh, 2, options=solvers.make_options(
+        s = solvers.DiffussionSolverTimeIndependent(p, mesh, 150, options=solvers.make_options(
             assembly_mode=solvers.ASSEMBLY_FAST, solve_mode=solvers.SOLVE_PARALLEL, refine_steps=0))
         for _ in range(5):
             s.solve_device(0.0)

@@ -1,0 +1,41 @@
+"""Latency of the reference-arithmetic (FAITHFUL, bit-identical) path on ONE bar, the shape the reference itself runs:
+static solve(), time-dependent solve(dt) and XSolver::new (assembly + factorisation) at a few sizes.  Device-resident,
+CUDA events.  Usage: python tools/time_small_bar.py [n ...]   (tuning aid; not part of the test suite)"""
+import os, sys, json, time, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dzahui_b200 as dz
+from dzahui_b200 import solvers, params
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # microseconds
+
+
+def main():
+    sizes = [int(float(a)) for a in sys.argv[1:]] or [100, 1000, 10000, 65536]
+    out = {}
+    opt = solvers.make_options(assembly_mode=solvers.ASSEMBLY_FAITHFUL, solve_mode=solvers.SOLVE_FAITHFUL)
+    for n in sizes:
+        x = np.linspace(0.0, 1.0, n)
+        mesh = dz.Mesh.from_nodes(x)
+        reps = max(3, min(200, 2_000_000 // n))
+        p = params.DiffussionParams.time_independent().mu(1.0).b(0.5).boundary_conditions(float(os.environ.get('BC0', '1.0')), 15.0).build()
+        s = solvers.DiffussionSolverTimeIndependent(p, mesh, 150, options=opt)
+        q = params.DiffussionParams.time_dependent().mu(1.0).b(0.5).boundary_conditions(0.0, 1.0).initial_conditions(np.sin(x[1:-1])).build()
+        td = solvers.DiffussionSolverTimeDependent(q, mesh, 150, options=opt)
+        out[n] = {"static_solve_us": timed(lambda: s.solve_device(0.0), reps), "td_step_us": timed(lambda: td.solve_device(1e-9), reps),
+                  "static_rebuild_us": timed(lambda: s.rebuild(), max(3, reps // 4)), "td_rebuild_us": timed(lambda: td.rebuild(), max(3, reps // 4))}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
