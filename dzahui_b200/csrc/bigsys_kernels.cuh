@@ -37,6 +37,7 @@
 //   Once u_s, u_e are known: u_j = (delta~_j - alpha~_j u_s - g~_j u_{j+1}) / P_j, j = 6..1.
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -53,6 +54,7 @@ constexpr int BS_THREADS = 256;               // tile kernel
 constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
 constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
 constexpr int BS_TMA_MIN_TILES = 64;          // smaller systems are launch-latency bound: plain k_tri_tile
+constexpr int BS_FUSED_MAX_TILES = 256;        // closed systems of up to this many tiles are solved by ONE cooperative launch
 constexpr int BS_SHALLOW_MIN_TILES = 592;     // 4 tiles per SM: from here on an application is throughput bound
 #ifndef BS_MIN_CTAS
 #define BS_MIN_CTAS 3
@@ -422,12 +424,14 @@ __device__ __forceinline__ bool chunk_load_direct(const TileArgs& k, long long g
   return vec;
 }
 
-// Everything after the chunk is in registers: (a, c, s, f) form, level 0, the shared-memory pyramid, and either the
-// tile's two reduced rows or the back-substitution.  Every thread of the tile must call.  vec: out[] takes 128-bit stores.
-template <int SRC, bool SOLVE, bool ACCUM, int NLEV, int P1, bool WARP>
-__device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs& k, double (&A)[BS_R], double (&C)[BS_R],
-                                          double (&S)[BS_R], double (&F)[BS_R], int len, long long g0, bool vec, int t,
-                                          long long tile, int rows1) {
+// Everything after the chunk is in registers, in two halves.  tile_forward: (a, c, s, f) form, level 0 and the
+// shared-memory pyramid; returns the level the pyramid stopped at (see Pyramid::Left).  tile_backward: that level's d[] now
+// holds its solved unknowns; back-substitution through the pyramid and the chunk, out[].  Every thread of the tile must
+// call both.  vec: out[] takes 128-bit stores.  tile_body strings them together for the two-pass kernels.
+template <int SRC, bool KEEP, int NLEV, int P1, bool WARP>
+__device__ __forceinline__ typename Pyramid<P1, WARP>::Left tile_forward(Pyramid<P1, WARP>& pyr, const TileArgs& k, double (&A)[BS_R],
+                                                                         double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R],
+                                                                         int len, long long g0, int t, int rows1) {
   const long long m = k.m;
   const int flags = k.flags;
   // closed ends cut the first / last coupling; a block of a longer bar (SPIKE split) keeps them
@@ -440,36 +444,27 @@ __device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs
 #pragma unroll
     for (int j = 0; j < BS_R; ++j) S[j] = excess3(A[j], S[j], C[j]);
   }
-  constexpr int ROUT = bs_rows_left(P1, NLEV);  // rows a full tile leaves
-  const long long obase = (long long)ROUT * tile;
-  // SOLVE: the solved unknowns of the level the pyramid stops at are fetched now (one per thread) and land while the
-  // sweeps run; read after the forward sweeps they would put an L2 round trip on every tile's critical path
-  double u_left = 0.0;
-  if (SOLVE && t < bs_rows_left_of(rows1, P1, NLEV)) u_left = k.ured[obase + t];
-  // level 0 in registers; SOLVE keeps (alpha~_j, g~_j, 1/P_j, delta~_j) in (A, C, S, F)[1..len-2]
+  // level 0 in registers; KEEP leaves (alpha~_j, g~_j, 1/P_j, delta~_j) in (A, C, S, F)[1..len-2]
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
     const int i0 = lvl_pos(2 * t, lvl_stride(P1)), i1 = lvl_pos(2 * t + 1, lvl_stride(P1));
-    if (len == BS_R) chunk0_forward<SOLVE, true>(A, C, S, F, len, l1, i0, i1);
-    else chunk0_forward<SOLVE, false>(A, C, S, F, len, l1, i0, i1);
+    if (len == BS_R) chunk0_forward<KEEP, true>(A, C, S, F, len, l1, i0, i1);
+    else chunk0_forward<KEEP, false>(A, C, S, F, len, l1, i0, i1);
   }
   // NLEV == 0: the pyramid runs down to the tile's final 2 rows.  NLEV > 0: it stops after NLEV levels and the tile
   // hands all rows of that level to the next application (2 P1 of them after one level: a reduction by 16 instead of
   // 1024).  The upper levels keep one warp busy and seven parked, so a throughput-bound first application is better off
   // leaving them to the next one, which then works on a 16x smaller system with full CTAs again.
-  static_assert(ROUT <= 32 || !WARP, "one unknown per thread");
-  const typename Pyramid<P1, WARP>::Left left = pyr.template reduce_to<NLEV, SOLVE>(t, rows1);
-  if (!SOLVE) {
-    for (int r = t; r < left.rows; r += WARP ? 32 : BS_THREADS) {
-      const int q = left.pos(r);
-      k.red_a[obase + r] = pyr.a[q], k.red_c[obase + r] = pyr.c[q], k.red_s[obase + r] = pyr.s[q], k.red_f[obase + r] = pyr.d[q];
-    }
-    return;
-  }
-  if (SOLVE) {  // (a branch, not fall-through, only to keep the !SOLVE instantiation free of unreachable-code warnings)
-    if (t < left.rows) pyr.d[left.pos(t)] = u_left;
-    pyr.template backsolve_from<NLEV>(t, rows1);
-  }
+  return pyr.template reduce_to<NLEV, KEEP>(t, rows1);
+}
+
+template <int SRC, bool ACCUM, int NLEV, int P1, bool WARP>
+__device__ __forceinline__ void tile_backward(Pyramid<P1, WARP>& pyr, const TileArgs& k, const double (&A)[BS_R],
+                                              const double (&C)[BS_R], const double (&S)[BS_R], const double (&F)[BS_R], int len,
+                                              long long g0, bool vec, int t, int rows1) {
+  const long long m = k.m;
+  const int flags = k.flags;
+  pyr.template backsolve_from<NLEV>(t, rows1);
   if (len >= 2) {
     LevelPtr l1 = pyr.level(0);
     const double us = l1.d[lvl_pos(2 * t, lvl_stride(P1))], ue = l1.d[lvl_pos(2 * t + 1, lvl_stride(P1))];
@@ -511,6 +506,29 @@ __device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs
         if (j < len) out[g0 + j] = ACCUM ? out[g0 + j] + o[j] : o[j];
       }
     }
+  }
+}
+
+template <int SRC, bool SOLVE, bool ACCUM, int NLEV, int P1, bool WARP>
+__device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs& k, double (&A)[BS_R], double (&C)[BS_R],
+                                          double (&S)[BS_R], double (&F)[BS_R], int len, long long g0, bool vec, int t,
+                                          long long tile, int rows1) {
+  constexpr int ROUT = bs_rows_left(P1, NLEV);  // rows a full tile leaves
+  static_assert(ROUT <= 32 || !WARP, "one unknown per thread");
+  const long long obase = (long long)ROUT * tile;
+  // SOLVE: the solved unknowns of the level the pyramid stops at are fetched now (one per thread) and land while the
+  // sweeps run; read after the forward sweeps they would put an L2 round trip on every tile's critical path
+  double u_left = 0.0;
+  if (SOLVE && t < bs_rows_left_of(rows1, P1, NLEV)) u_left = k.ured[obase + t];
+  const typename Pyramid<P1, WARP>::Left left = tile_forward<SRC, SOLVE, NLEV>(pyr, k, A, C, S, F, len, g0, t, rows1);
+  if (!SOLVE) {
+    for (int r = t; r < left.rows; r += WARP ? 32 : BS_THREADS) {
+      const int q = left.pos(r);
+      k.red_a[obase + r] = pyr.a[q], k.red_c[obase + r] = pyr.c[q], k.red_s[obase + r] = pyr.s[q], k.red_f[obase + r] = pyr.d[q];
+    }
+  } else {
+    if (t < left.rows) pyr.d[left.pos(t)] = u_left;
+    tile_backward<SRC, ACCUM, NLEV>(pyr, k, A, C, S, F, len, g0, vec, t, rows1);
   }
 }
 
@@ -558,13 +576,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, uns
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
   unsigned done = 0;
+  long long t0 = 0;
   for (unsigned spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(smem_u32(b)), "r"(parity)
         : "memory");
-    if (spin > (1u << 26)) __trap();  // a lost copy becomes an error, not a hang
+    if (!done && (spin & 1023u) == 1023u) {  // a lost copy becomes an error after ~2 s, not a hang
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, int row, unsigned long long* b) {
@@ -647,12 +670,8 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_tile_tma(const __grid_con
 //       BS_MID_REDUCE     open block: the two rows left after eliminating everything inside -> top8 = (a,c,s,f) x 2
 //       BS_MID_BACKSOLVE  open block whose end unknowns (us, ue) are now known -> out[0..m)
 template <int P1, int SRC, int MODE, bool ACCUM>
-__global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict__ p0, const double* __restrict__ p1,
-                                                        const double* __restrict__ p2, const double* __restrict__ p3, int m,
-                                                        double* __restrict__ out, int flags, double* __restrict__ top8,
-                                                        double us, double ue) {
-  extern __shared__ double4 mid_smem[];
-  Pyramid<P1>& pyr = *reinterpret_cast<Pyramid<P1>*>(mid_smem);
+__device__ __forceinline__ void mid_body(Pyramid<P1>& pyr, const double* p0, const double* p1, const double* p2, const double* p3,
+                                         int m, double* out, int flags, double* top8, double us, double ue) {
   const int t = threadIdx.x;
   const bool open_left = flags & BS_OPEN_LEFT, open_right = flags & BS_OPEN_RIGHT;
   LevelPtr l1 = pyr.level(0);
@@ -683,12 +702,53 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict
   pyr.backsolve(t, m);
   for (int r = t; r < m; r += BS_THREADS) {
     double v = l1.d[row_slot(r, m, lvl_stride(P1))];
-    if (SRC == BS_SRC_BANDS) {  // exact Dirichlet end rows, as in k_tri_tile
+    if (SRC == BS_SRC_BANDS) {  // exact Dirichlet end rows, as in the tile kernels
       if (r == 0 && !open_left && p2[0] == 0.0) v = p3[0] / p1[0];
       if (r == m - 1 && !open_right && p0[m - 1] == 0.0) v = p3[m - 1] / p1[m - 1];
     }
     out[r] = ACCUM ? out[r] + v : v;
   }
+}
+template <int P1, int SRC, int MODE, bool ACCUM>
+__global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict__ p0, const double* __restrict__ p1,
+                                                        const double* __restrict__ p2, const double* __restrict__ p3, int m,
+                                                        double* __restrict__ out, int flags, double* __restrict__ top8,
+                                                        double us, double ue) {
+  extern __shared__ double4 mid_smem[];
+  mid_body<P1, SRC, MODE, ACCUM>(*reinterpret_cast<Pyramid<P1>*>(mid_smem), p0, p1, p2, p3, m, out, flags, top8, us, ue);
+}
+
+// ---- one launch for a closed system of 2049 .. 2048 BS_FUSED_MAX_TILES rows ------------------------------------------
+// Up to a few hundred thousand rows a solve is three dependent launches (reduce, k_tri_mid, solve) of a few microseconds
+// each, and the third one reads the bands and redoes the forward sweeps only because the first could not wait for the
+// second.  In a cooperative launch it can: every CTA keeps its tile's multipliers in registers and shared memory across
+// two grid-wide barriers, between which CTA 0 solves the 2-rows-per-tile system.  22.7 -> ~15 us per solve (measured).
+template <bool ACCUM>
+__global__ void __launch_bounds__(BS_THREADS, 2) k_tri_fused(const TileArgs k) {
+  constexpr int SRC = BS_SRC_BANDS;
+  __shared__ Pyramid<BS_THREADS / 4> pyr;
+  __shared__ Pyramid<BS_FUSED_MAX_TILES / 4> mid;  // 2 rows per tile = 8 rows per BS_FUSED_MAX_TILES / 4 chunks
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int t = threadIdx.x;
+  const long long tile = blockIdx.x;
+  long long tile0;
+  const int rows0 = tile_rows(tile, k.m, BS_TILE, &tile0);
+  const int rows1 = 2 * ((rows0 + BS_R - 1) / BS_R);
+  const ChunkGeom gm = chunk_geom(rows0, t, tile0);
+  double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
+  const bool vec = chunk_load_direct<SRC, true>(k, gm.g0, gm.len, A, C, S, F);
+  const Pyramid<BS_THREADS / 4>::Left left = tile_forward<SRC, true, 0>(pyr, k, A, C, S, F, gm.len, gm.g0, t, rows1);
+  if (t < 2) {
+    const int q = left.pos(t);
+    k.red_a[2 * tile + t] = pyr.a[q], k.red_c[2 * tile + t] = pyr.c[q], k.red_s[2 * tile + t] = pyr.s[q], k.red_f[2 * tile + t] = pyr.d[q];
+  }
+  grid.sync();
+  if (blockIdx.x == 0)
+    mid_body<BS_FUSED_MAX_TILES / 4, BS_SRC_ROWS, BS_MID_SOLVE, false>(mid, k.red_a, k.red_c, k.red_s, k.red_f, 2 * (int)gridDim.x,
+                                                                      const_cast<double*>(k.ured), 0, nullptr, 0.0, 0.0);
+  grid.sync();
+  if (t < 2) pyr.d[left.pos(t)] = __ldcg(k.ured + 2 * tile + t);
+  tile_backward<SRC, ACCUM, 0>(pyr, k, A, C, S, F, gm.len, gm.g0, vec, t, rows1);
 }
 
 // ---- iterative refinement: r = f - K u with a double-double accumulator -------------------------------------------
@@ -791,7 +851,8 @@ struct BigLevel {
 struct BigSys {
   size_t n = 0;
   size_t shallow_min_tiles = BS_SHALLOW_MIN_TILES;  // applications with at least this many tiles stop after one level
-  bool tma = true;  // big systems go through k_tri_tile_tma (DZB_NO_TMA=1: always k_tri_tile)
+  bool tma = true;    // big systems go through k_tri_tile_tma (DZB_NO_TMA=1: always k_tri_tile)
+  bool fused = true;  // closed systems of <= BS_FUSED_MAX_TILES tiles: one cooperative launch (DZB_NO_FUSED=1: three launches)
   size_t tma_min_tiles = BS_TMA_MIN_TILES;
   struct Map {
     const double* p;
@@ -838,6 +899,7 @@ inline int bigsys_prepare(BigSys* s, size_t n) {
   s->n = n;
   if (const char* v = std::getenv("DZB_SHALLOW_MIN_TILES")) s->shallow_min_tiles = (size_t)std::atoll(v);  // tuning knob
   if (const char* v = std::getenv("DZB_NO_TMA")) s->tma = std::atoi(v) == 0;
+  if (const char* v = std::getenv("DZB_NO_FUSED")) s->fused = std::atoi(v) == 0;
   if (const char* v = std::getenv("DZB_TMA_MIN_TILES")) s->tma_min_tiles = (size_t)std::atoll(v);  // tuning knob
   s->maps.clear();
   cudaError_t e;
@@ -1005,11 +1067,42 @@ inline int bigsys_backward(BigSys* s, const double* lo, const double* di, const 
   return 0;
 }
 
+// Can the whole solve be ONE cooperative launch?  One grid level with the full pyramid, few enough tiles for k_tri_fused's
+// in-kernel middle solve, and all of them co-resident (a grid-wide barrier needs that; checked once per instantiation).
+template <bool ACCUM>
+inline bool bigsys_fused_fits(size_t tiles) {
+  static int capacity = [] {
+    int dev = 0, coop = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tri_fused<ACCUM>, BS_THREADS, 0) != cudaSuccess) return 0;
+    return per_sm * bigsys_sm_count();
+  }();
+  return tiles <= (size_t)BS_FUSED_MAX_TILES && tiles <= (size_t)capacity;
+}
+template <bool ACCUM>
+inline int bigsys_fused_launch(BigSys* s, const double* lo, const double* di, const double* up, const double* f, double* out,
+                               cudaStream_t st, unsigned long long* launches) {
+  BigLevel& L = s->levels[0];
+  TileArgs k{lo, di, up, f, (long long)s->n, L.a, L.c, L.s, L.f, L.u, out, 0};
+  void* args[] = {&k};
+  const size_t tiles = (s->n + BS_TILE - 1) / BS_TILE;
+  ++*launches;
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tri_fused<ACCUM>, dim3((unsigned)tiles), dim3(BS_THREADS), args, 0, st);
+  return e == cudaSuccess ? 0 : bigsys_fail(e, "k_tri_fused");
+}
+
 // out (+)= A^{-1} f for the closed n-row system (lo, di, up); inputs are not modified.
 inline int bigsys_solve_once(BigSys* s, const double* lo, const double* di, const double* up, const double* f, double* out,
                              bool accum, cudaStream_t st, unsigned long long* launches) {
   if (s->levels.empty())
     return bigsys_mid<BS_SRC_BANDS, BS_MID_SOLVE>(lo, di, up, f, s->n, out, accum, 0, nullptr, 0.0, 0.0, st, launches);
+  if (s->fused && s->levels.size() == 1 && s->levels[0].nlev == 0) {
+    const size_t tiles = (s->n + BS_TILE - 1) / BS_TILE;
+    if (accum ? bigsys_fused_fits<true>(tiles) : bigsys_fused_fits<false>(tiles))
+      return accum ? bigsys_fused_launch<true>(s, lo, di, up, f, out, st, launches)
+                   : bigsys_fused_launch<false>(s, lo, di, up, f, out, st, launches);
+  }
   if (bigsys_forward(s, lo, di, up, f, 0, st, launches)) return 1;
   BigLevel& L = s->levels.back();
   if (bigsys_mid<BS_SRC_ROWS, BS_MID_SOLVE>(L.a, L.c, L.s, L.f, L.m, L.u, false, 0, nullptr, 0.0, 0.0, st, launches)) return 1;
