@@ -5,6 +5,7 @@ StokesParams, DiffussionParams, the three solvers, DiffEquationSolver, Solver, p
 ensemble driver.  All compute is hand-written CUDA reached through the C ABI in include/dzahui_b200.h."""
 from . import _lib
 from .ensemble import EnsembleTimeDependent
+from .euler import EulerEnsemble, EulerSolver
 from .errors import CudaError, Error, Integration, Invalid, Io, MeshParse, PieceWiseDims, WrongDims
 from .mesh import Mesh, Mesh2D, MeshBuilder
 from .params import (BuilderPanic, DiffussionParams, DiffussionParamsTimeDependent, DiffussionParamsTimeIndependent,

@@ -93,6 +93,12 @@ SIGNATURES = {
     "dzb_ensemble_bands": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, c_double_p, c_double_p, c_double_p, C.c_size_t]),
     "dzb_ensemble_dims": (C.c_int, [C.c_void_p, c_size_p, c_size_p]),
     "dzb_ensemble_destroy": (None, [C.c_void_p]),
+    "dzb_euler_create": (C.c_int, [C.c_size_t, C.c_size_t, c_double_p, c_double_p, C.POINTER(C.c_void_p)]),
+    "dzb_euler_set_values": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
+    "dzb_euler_step": (C.c_int, [C.c_void_p, C.c_double, C.c_size_t]),
+    "dzb_euler_values": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
+    "dzb_euler_values_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dzb_euler_destroy": (None, [C.c_void_p]),
 }
 
 _lib = None

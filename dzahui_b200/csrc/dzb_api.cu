@@ -17,6 +17,7 @@
 #include "../../include/dzahui_b200.h"
 #include "assembly_kernels.cuh"
 #include "bigsys_kernels.cuh"
+#include "euler_kernels.cuh"
 #include "gl_quadrature.h"
 #include "mesh2d_kernels.cuh"
 #include "mesh_ingest.h"
@@ -265,6 +266,11 @@ struct dzb_mesh {
   double* d_minmax = nullptr;
   double max_length = 0.0, prom_width = 0.0;
   float translation[3] = {0.f, 0.f, 0.f};
+};
+
+struct dzb_euler {
+  size_t T = 0, W = 0;                // trajectories, entries per state (incl. t)
+  double *v = nullptr, *c = nullptr;  // SoA [W][T] state, [W + 1][T] coefficients
 };
 
 struct dzb_ensemble {
@@ -1360,5 +1366,79 @@ int dzb_ensemble_dims(const dzb_ensemble* e, size_t* n_bars, size_t* n) {
   return DZB_OK;
 }
 void dzb_ensemble_destroy(dzb_ensemble* e) { ensemble_free(e); }
+
+// ---- EulerSolver ensembles ---------------------------------------------------------------------------------------------
+int dzb_euler_create(size_t n_traj, size_t width, const double* coeffs, const double* values, dzb_euler** out) {
+  if (!out || !coeffs || !values) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  if (width < 2 || width > 5) return fail(DZB_INVALID, "EulerSolver takes [f64; 2] .. [f64; 5] (solvers/euler/mod.rs:19-22)");
+  if (n_traj == 0) return fail(DZB_INVALID, "no trajectories");
+  dzb_euler* e = new dzb_euler;
+  e->T = n_traj, e->W = width;
+  int rc;
+  if ((rc = dalloc(&e->v, n_traj * width)) || (rc = dalloc(&e->c, n_traj * (width + 1)))) {
+    dzb_euler_destroy(e);
+    return rc;
+  }
+  // host AoS -> device SoA
+  std::vector<double> hv(n_traj * width), hc(n_traj * (width + 1));
+  for (size_t i = 0; i < n_traj; ++i) {
+    for (size_t j = 0; j < width; ++j) hv[j * n_traj + i] = values[i * width + j];
+    for (size_t j = 0; j <= width; ++j) hc[j * n_traj + i] = coeffs[i * (width + 1) + j];
+  }
+  if (cudaMemcpyAsync(e->v, hv.data(), hv.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess ||
+      cudaMemcpyAsync(e->c, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess ||
+      (rc = sync_stream())) {
+    dzb_euler_destroy(e);
+    return rc ? rc : fail(DZB_CUDA, "H2D euler state");
+  }
+  *out = e;
+  return DZB_OK;
+}
+int dzb_euler_set_values(dzb_euler* e, const double* values, size_t len) {
+  if (!e || !values) return fail(DZB_INVALID, "null pointer");
+  if (len != e->T * e->W) return fail(DZB_WRONG_DIMS, "length != n_traj * width");
+  std::vector<double> hv(len);
+  for (size_t i = 0; i < e->T; ++i)
+    for (size_t j = 0; j < e->W; ++j) hv[j * e->T + i] = values[i * e->W + j];
+  CK(cudaMemcpyAsync(e->v, hv.data(), len * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  return sync_stream();
+}
+int dzb_euler_step(dzb_euler* e, double step, size_t steps) {
+  if (!e) return fail(DZB_INVALID, "null pointer");
+  if (steps == 0) return DZB_OK;
+  const unsigned blocks = (unsigned)((e->T + 255) / 256);
+  const long long T = (long long)e->T, k = (long long)steps;
+  switch (e->W) {
+    case 2: dzb::k_euler_steps<2><<<blocks, 256, 0, g_stream>>>(e->v, e->c, T, step, k); break;
+    case 3: dzb::k_euler_steps<3><<<blocks, 256, 0, g_stream>>>(e->v, e->c, T, step, k); break;
+    case 4: dzb::k_euler_steps<4><<<blocks, 256, 0, g_stream>>>(e->v, e->c, T, step, k); break;
+    default: dzb::k_euler_steps<5><<<blocks, 256, 0, g_stream>>>(e->v, e->c, T, step, k); break;
+  }
+  LAUNCHED();
+  return DZB_OK;
+}
+int dzb_euler_values(const dzb_euler* e, double* out_host, size_t len) {
+  if (!e || !out_host) return fail(DZB_INVALID, "null pointer");
+  if (len != e->T * e->W) return fail(DZB_WRONG_DIMS, "output length != n_traj * width");
+  std::vector<double> hv(len);
+  CK(cudaMemcpyAsync(hv.data(), e->v, len * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  int rc = sync_stream();
+  if (rc) return rc;
+  for (size_t i = 0; i < e->T; ++i)
+    for (size_t j = 0; j < e->W; ++j) out_host[i * e->W + j] = hv[j * e->T + i];
+  return DZB_OK;
+}
+int dzb_euler_values_device(const dzb_euler* e, const double** device_ptr) {
+  if (!e || !device_ptr) return fail(DZB_INVALID, "null pointer");
+  *device_ptr = e->v;
+  return DZB_OK;
+}
+void dzb_euler_destroy(dzb_euler* e) {
+  if (!e) return;
+  dfree(e->v);
+  dfree(e->c);
+  delete e;
+}
 
 }  // extern "C"

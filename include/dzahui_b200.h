@@ -200,6 +200,21 @@ int dzb_ensemble_bands(const dzb_ensemble* e, size_t bar, int which, double* lo,
 int dzb_ensemble_dims(const dzb_ensemble* e, size_t* n_bars, size_t* n);
 void dzb_ensemble_destroy(dzb_ensemble* e);
 
+/* ---- EulerSolver (reference solvers/euler/mod.rs:26-59; integration tests tests/euler.rs) for many trajectories ------ */
+/* The reference steps ONE trajectory with a host closure f(&values): values = [y^(n-1), ..., y, t], `width` = 2..5 entries
+ * (FunctionArguments, mod.rs:17-22).  Here every trajectory carries an affine derivative function
+ *     f(values) = coeffs[0] + coeffs[1] * values[0] + ... + coeffs[width] * values[width - 1]   (left to right)
+ * and do_step's arithmetic is the reference's, operation for operation.  coeffs: host [n_traj][width + 1], values: host
+ * [n_traj][width].  DZB_INVALID unless 2 <= width <= 5. */
+typedef struct dzb_euler dzb_euler;
+int dzb_euler_create(size_t n_traj, size_t width, const double* coeffs, const double* values, dzb_euler** out);
+/* `steps` successive do_step(values, step) on every trajectory; the states stay on the device */
+int dzb_euler_step(dzb_euler* e, double step, size_t steps);
+int dzb_euler_set_values(dzb_euler* e, const double* values, size_t len);     /* [n_traj][width]: restart from these states */
+int dzb_euler_values(const dzb_euler* e, double* out_host, size_t len);      /* [n_traj][width] */
+int dzb_euler_values_device(const dzb_euler* e, const double** device_ptr);  /* SoA [width][n_traj] */
+void dzb_euler_destroy(dzb_euler* e);
+
 #ifdef __cplusplus
 }
 #endif

@@ -430,5 +430,86 @@ class Writer {
   }
 };
 
+// ---- EulerSolver (solvers/euler/mod.rs:26-59) ------------------------------------------------------------------------
+// The reference's EulerSolver<A, F> steps one trajectory with a closure F: Fn(&A) -> f64, A = [f64; 2..5].  A host closure
+// cannot run on the device: the derivative function is given by its affine coefficients instead,
+//   f(values) = c[0] + c[1] * values[0] + ... + c[W] * values[W - 1],
+// and many trajectories step together.  `EulerSolver<W>::affine({0, -lambda, 0}).do_step({quantity, time}, 0.5)` is the
+// reference's `EulerSolver::new(|val: &[f64; 2]| -lambda * val[0]).do_step([quantity, time], 0.5)`.
+class EulerEnsemble {
+  dzb_euler* h_ = nullptr;
+  size_t n_traj_ = 0, width_ = 0;
+  EulerEnsemble() = default;
+
+ public:
+  EulerEnsemble(EulerEnsemble&& o) noexcept : h_(o.h_), n_traj_(o.n_traj_), width_(o.width_) { o.h_ = nullptr; }
+  EulerEnsemble& operator=(EulerEnsemble&& o) noexcept {
+    if (this != &o) {
+      dzb_euler_destroy(h_);
+      h_ = o.h_, n_traj_ = o.n_traj_, width_ = o.width_, o.h_ = nullptr;
+    }
+    return *this;
+  }
+  EulerEnsemble(const EulerEnsemble&) = delete;
+  EulerEnsemble& operator=(const EulerEnsemble&) = delete;
+  ~EulerEnsemble() { dzb_euler_destroy(h_); }
+  // coeffs: [n_traj][width + 1], values: [n_traj][width], both row-major
+  static Result<EulerEnsemble> create(size_t n_traj, size_t width, const std::vector<double>& coeffs, const std::vector<double>& values) {
+    if (coeffs.size() != n_traj * (width + 1) || values.size() != n_traj * width) return Error{Error::WrongDims, ""};
+    EulerEnsemble e;
+    const int rc = dzb_euler_create(n_traj, width, coeffs.data(), values.data(), &e.h_);
+    if (rc) return Error::from_status(rc);
+    e.n_traj_ = n_traj, e.width_ = width;
+    return e;
+  }
+  // `steps` x do_step(values, step) on every trajectory; returns the new values, [n_traj][width]
+  Result<std::vector<double>> do_step(double step, size_t steps = 1) {
+    int rc = dzb_euler_step(h_, step, steps);
+    if (rc) return Error::from_status(rc);
+    std::vector<double> out(n_traj_ * width_);
+    rc = dzb_euler_values(h_, out.data(), out.size());
+    if (rc) return Error::from_status(rc);
+    return out;
+  }
+  Result<bool> set_values(const std::vector<double>& values) {
+    const int rc = dzb_euler_set_values(h_, values.data(), values.size());
+    if (rc) return Error::from_status(rc);
+    return true;
+  }
+};
+
+template <size_t W>
+class EulerSolver {
+  static_assert(W >= 2 && W <= 5, "FunctionArguments is implemented for [f64; 2] .. [f64; 5] (solvers/euler/mod.rs:19-22)");
+  std::array<double, W + 1> coeffs_;
+  std::unique_ptr<EulerEnsemble> ens_;
+  std::array<double, W> last_{};
+
+ public:
+  explicit EulerSolver(const std::array<double, W + 1>& coeffs) : coeffs_(coeffs) {}
+  static EulerSolver affine(const std::array<double, W + 1>& coeffs) { return EulerSolver(coeffs); }
+  static EulerSolver constant(double value) {
+    std::array<double, W + 1> c{};
+    c[0] = value;
+    return EulerSolver(c);
+  }
+  // do_step(values, step) -> next values (mod.rs:37-59); panics like the reference's `panic!("Nooo")` on failure
+  std::array<double, W> do_step(const std::array<double, W>& values, double step) {
+    const std::vector<double> v(values.begin(), values.end());
+    if (!ens_) {
+      auto r = EulerEnsemble::create(1, W, std::vector<double>(coeffs_.begin(), coeffs_.end()), v);
+      if (r.is_err()) throw Panic("Nooo");
+      ens_ = std::make_unique<EulerEnsemble>(std::move(r.unwrap()));
+    } else if (values != last_) {
+      if (ens_->set_values(v).is_err()) throw Panic("Nooo");
+    }
+    auto r = ens_->do_step(step);
+    if (r.is_err()) throw Panic("Nooo");
+    const std::vector<double> next = r.unwrap();
+    std::copy(next.begin(), next.end(), last_.begin());
+    return last_;
+  }
+};
+
 }  // namespace dzahui
 #endif  // DZAHUI_B200_HPP

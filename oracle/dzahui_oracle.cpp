@@ -1097,3 +1097,47 @@ void dzo_update_gradient_1d(double* vertices, size_t len, const double* velocity
 }
 
 }  // extern "C"
+
+// ============================================================== EulerSolver (solvers/euler/mod.rs:26-59)
+// do_step with the caller's closure: values = [y^(n-1), ..., y, t], width 2..5 (FunctionArguments, :19-22).
+extern "C" {
+int dzo_euler_do_step(const double* values, size_t width, double step, double (*f)(const double* values, void* ctx), void* ctx,
+                      double* next) {
+  if (width < 2 || width > 5) return dzo::WRONG_DIMS;
+  const double f_eval = f(values, ctx);                        // :38
+  double value = values[0] + step * f_eval;                    // :43
+  const double t_new = values[width - 1] + step;               // :44
+  next[0] = value;                                             // :46
+  for (size_t j = 1; j + 1 < width; ++j) {                     // :48-52
+    const double new_val = values[j] + step * value;
+    value = new_val;
+    next[j] = new_val;
+  }
+  next[width - 1] = t_new;                                     // :53
+  return dzo::OK;
+}
+// the closure  c[0] + c[1]*v[0] + ... + c[width]*v[width-1]  (left to right), stepped `steps` times on every trajectory;
+// coeffs [n_traj][width + 1], values [n_traj][width] (updated in place)
+static double dzo_affine_closure(const double* v, void* ctx) {
+  const double* c = static_cast<const double*>(ctx);
+  const size_t width = (size_t)c[-1];
+  double f = c[0];
+  for (size_t j = 0; j < width; ++j) f = f + c[j + 1] * v[j];
+  return f;
+}
+int dzo_euler_affine_run(const double* coeffs, double* values, size_t n_traj, size_t width, double step, size_t steps) {
+  if (width < 2 || width > 5) return dzo::WRONG_DIMS;
+  for (size_t i = 0; i < n_traj; ++i) {
+    double ctx[7];
+    ctx[0] = (double)width;
+    for (size_t j = 0; j <= width; ++j) ctx[1 + j] = coeffs[i * (width + 1) + j];
+    double* v = values + i * width;
+    for (size_t s = 0; s < steps; ++s) {
+      double next[5];
+      dzo_euler_do_step(v, width, step, dzo_affine_closure, ctx + 1, next);
+      for (size_t j = 0; j < width; ++j) v[j] = next[j];
+    }
+  }
+  return dzo::OK;
+}
+}  // extern "C"

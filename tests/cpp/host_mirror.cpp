@@ -141,6 +141,22 @@ static void gpu_tests(const std::string& assets) {
     Solver none = None{};
     CHECK(instantiate(none, mesh, 150).unwrap()->solve(0.0).unwrap().empty());
   }
+  {  // EulerSolver: the reference's integration tests (tests/euler.rs), closures given by their affine coefficients
+    auto first = EulerSolver<2>::constant(1.0);  // EulerSolver::new(|_: &[f64; 2]| 1.0)
+    std::array<double, 2> s2{0.0, 0.0};          // [pos, time]
+    while (s2[1] <= 10.0) s2 = first.do_step(s2, 0.01);
+    CHECK(s2[0] <= 10.1 && s2[0] >= 9.9);
+    auto gravity = EulerSolver<3>::constant(-9.81);  // EulerSolver::new(|_: &[f64; 3]| -9.81)
+    std::array<double, 3> s3{0.0, 100.0, 0.0};       // [vel, pos, time]
+    while (s3[2] <= 10.0) s3 = gravity.do_step(s3, 0.01);
+    CHECK(s3[0] >= -100.0 && s3[0] <= -97.0 && s3[1] >= -400.0 && s3[1] <= -389.0);
+    const double lambda = std::log(2.0) / 1600.0;
+    auto decay = EulerSolver<2>::affine({0.0, -lambda, 0.0});  // EulerSolver::new(|val: &[f64; 2]| -lambda * val[0])
+    std::array<double, 2> q{1000.0, -1600.0};                  // [quantity, time]
+    while (q[1] <= 0.0) q = decay.do_step(q, 0.5);
+    CHECK(q[1] <= 0.5 && q[1] >= -0.5 && q[0] >= 490.0 && q[0] <= 510.0);
+    CHECK(EulerEnsemble::create(2, 6, std::vector<double>(14, 0.0), std::vector<double>(12, 0.0)).is_err());  // no [f64; 6]
+  }
 }
 
 int main(int argc, char** argv) {

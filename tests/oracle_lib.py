@@ -245,3 +245,24 @@ def boundary_vertices(triangles):
     _chk(lib().dzo_boundary_vertices(t.ctypes.data_as(u32p), C.c_size_t(t.shape[0]), out.ctypes.data_as(u32p), C.c_size_t(out.size),
                                      C.byref(n)))
     return out[:n.value].copy()
+
+
+_EULER_FN = C.CFUNCTYPE(C.c_double, _dp, C.c_void_p)
+
+
+def euler_do_step(values, step, f):
+    """EulerSolver::new(f).do_step(values, step) (solvers/euler/mod.rs:37-59); f takes the list of old values"""
+    v = _arr(values)
+    out = np.empty_like(v)
+    cb = _EULER_FN(lambda p, _ctx: float(f([p[j] for j in range(v.size)])))
+    _chk(lib().dzo_euler_do_step(_p(v), C.c_size_t(v.size), C.c_double(step), cb, None, _p(out)))
+    return out
+
+
+def euler_affine_run(coeffs, values, step, steps):
+    """`steps` do_step calls per trajectory with the closure c[0] + c[1]*v[0] + ...; returns the new [n_traj][width] array"""
+    c, v = _arr(coeffs), _arr(values).copy()
+    n_traj, width = v.shape
+    assert c.shape == (n_traj, width + 1)
+    _chk(lib().dzo_euler_affine_run(_p(c), _p(v), C.c_size_t(n_traj), C.c_size_t(width), C.c_double(step), C.c_size_t(steps)))
+    return v
