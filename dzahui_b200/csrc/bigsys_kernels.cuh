@@ -54,7 +54,7 @@ constexpr int BS_THREADS = 256;               // tile kernel
 constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
 constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
 constexpr int BS_TMA_MIN_TILES = 64;          // smaller systems are launch-latency bound: plain k_tri_tile
-constexpr int BS_FUSED_MAX_TILES = 256;        // closed systems of up to this many tiles are solved by ONE cooperative launch
+constexpr int BS_FUSED_MAX_TILES = 512;       // most tiles k_tri_fused's in-kernel middle solve has room for
 constexpr int BS_SHALLOW_MIN_TILES = 592;     // 4 tiles per SM: from here on an application is throughput bound
 #ifndef BS_MIN_CTAS
 #define BS_MIN_CTAS 3
@@ -718,16 +718,23 @@ __global__ void __launch_bounds__(BS_THREADS) k_tri_mid(const double* __restrict
   mid_body<P1, SRC, MODE, ACCUM>(*reinterpret_cast<Pyramid<P1>*>(mid_smem), p0, p1, p2, p3, m, out, flags, top8, us, ue);
 }
 
-// ---- one launch for a closed system of 2049 .. 2048 BS_FUSED_MAX_TILES rows ------------------------------------------
+// ---- one launch for a closed system of up to a few hundred tiles -----------------------------------------------------------
 // Up to a few hundred thousand rows a solve is three dependent launches (reduce, k_tri_mid, solve) of a few microseconds
-// each, and the third one reads the bands and redoes the forward sweeps only because the first could not wait for the
+// each, and the third one reads the system and redoes the forward sweeps only because the first could not wait for the
 // second.  In a cooperative launch it can: every CTA keeps its tile's multipliers in registers and shared memory across
-// two grid-wide barriers, between which CTA 0 solves the 2-rows-per-tile system.  22.7 -> ~15 us per solve (measured).
-template <bool ACCUM>
-__global__ void __launch_bounds__(BS_THREADS, 2) k_tri_fused(const TileArgs k) {
-  constexpr int SRC = BS_SRC_BANDS;
-  __shared__ Pyramid<BS_THREADS / 4> pyr;
-  __shared__ Pyramid<BS_FUSED_MAX_TILES / 4> mid;  // 2 rows per tile = 8 rows per BS_FUSED_MAX_TILES / 4 chunks
+// two grid-wide barriers, between which CTA 0 solves the 2-rows-per-tile system.  Used for a whole solve of 2049 .. ~900 000
+// rows (SRC = bands: 22.7 -> 12-17 us), and for the LAST grid level of a bigger one (SRC = rows: the 625 000-row system a
+// 10^7-row solve leaves after its shallow first application).  MAXT: tiles the in-kernel middle solve has room for
+// (256: two CTAs per SM with all registers; 512: three, up to the co-residency limit of 444 on a B200).
+template <int MAXT>
+struct FusedSmem {
+  Pyramid<BS_THREADS / 4> pyr;
+  Pyramid<MAXT / 4> mid;  // 2 rows per tile = 8 rows per MAXT / 4 chunks
+};
+template <int SRC, bool ACCUM, int MAXT>
+__global__ void __launch_bounds__(BS_THREADS, MAXT > 256 ? 3 : 2) k_tri_fused(const TileArgs k) {
+  extern __shared__ double4 fused_smem[];
+  FusedSmem<MAXT>& sm = *reinterpret_cast<FusedSmem<MAXT>*>(fused_smem);
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const int t = threadIdx.x;
   const long long tile = blockIdx.x;
@@ -737,18 +744,19 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_fused(const TileArgs k) {
   const ChunkGeom gm = chunk_geom(rows0, t, tile0);
   double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
   const bool vec = chunk_load_direct<SRC, true>(k, gm.g0, gm.len, A, C, S, F);
-  const Pyramid<BS_THREADS / 4>::Left left = tile_forward<SRC, true, 0>(pyr, k, A, C, S, F, gm.len, gm.g0, t, rows1);
+  const Pyramid<BS_THREADS / 4>::Left left = tile_forward<SRC, true, 0>(sm.pyr, k, A, C, S, F, gm.len, gm.g0, t, rows1);
   if (t < 2) {
     const int q = left.pos(t);
-    k.red_a[2 * tile + t] = pyr.a[q], k.red_c[2 * tile + t] = pyr.c[q], k.red_s[2 * tile + t] = pyr.s[q], k.red_f[2 * tile + t] = pyr.d[q];
+    k.red_a[2 * tile + t] = sm.pyr.a[q], k.red_c[2 * tile + t] = sm.pyr.c[q], k.red_s[2 * tile + t] = sm.pyr.s[q],
+                       k.red_f[2 * tile + t] = sm.pyr.d[q];
   }
   grid.sync();
   if (blockIdx.x == 0)
-    mid_body<BS_FUSED_MAX_TILES / 4, BS_SRC_ROWS, BS_MID_SOLVE, false>(mid, k.red_a, k.red_c, k.red_s, k.red_f, 2 * (int)gridDim.x,
-                                                                      const_cast<double*>(k.ured), 0, nullptr, 0.0, 0.0);
+    mid_body<MAXT / 4, BS_SRC_ROWS, BS_MID_SOLVE, false>(sm.mid, k.red_a, k.red_c, k.red_s, k.red_f, 2 * (int)gridDim.x,
+                                                        const_cast<double*>(k.ured), 0, nullptr, 0.0, 0.0);
   grid.sync();
-  if (t < 2) pyr.d[left.pos(t)] = __ldcg(k.ured + 2 * tile + t);
-  tile_backward<SRC, ACCUM, 0>(pyr, k, A, C, S, F, gm.len, gm.g0, vec, t, rows1);
+  if (t < 2) sm.pyr.d[left.pos(t)] = __ldcg(k.ured + 2 * tile + t);
+  tile_backward<SRC, ACCUM, 0>(sm.pyr, k, A, C, S, F, gm.len, gm.g0, vec, t, rows1);
 }
 
 // ---- iterative refinement: r = f - K u with a double-double accumulator -------------------------------------------
@@ -1031,9 +1039,9 @@ inline cudaError_t bigsys_launch_tile(BigSys* s, int nlev, size_t m, const doubl
 
 // forward sweeps of every grid level: each application of k_tri_tile leaves 2 rows per tile
 inline int bigsys_forward(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
-                          cudaStream_t st, unsigned long long* launches) {
+                          cudaStream_t st, unsigned long long* launches, size_t kend = (size_t)-1) {  // levels [0, kend)
   cudaError_t e;
-  for (size_t k = 0; k < s->levels.size(); ++k) {
+  for (size_t k = 0; k < std::min(kend, s->levels.size()); ++k) {
     BigLevel& L = s->levels[k];
     if (k == 0) {
       e = bigsys_launch_tile<BS_SRC_BANDS, false, false>(s, L.nlev, s->n, lo, di, up, f, L.a, L.c, L.s, L.f, nullptr, nullptr, flags, st);
@@ -1048,9 +1056,10 @@ inline int bigsys_forward(BigSys* s, const double* lo, const double* di, const d
 }
 // back-substitution of every grid level; levels.back().u must hold the solved top-level unknowns
 inline int bigsys_backward(BigSys* s, const double* lo, const double* di, const double* up, const double* f, int flags,
-                           double* out, bool accum, cudaStream_t st, unsigned long long* launches) {
+                           double* out, bool accum, cudaStream_t st, unsigned long long* launches,
+                           size_t kend = (size_t)-1) {  // levels [0, kend), from the top
   cudaError_t e;
-  for (size_t k = s->levels.size(); k-- > 0;) {
+  for (size_t k = std::min(kend, s->levels.size()); k-- > 0;) {
     BigLevel& L = s->levels[k];
     if (k == 0) {
       if (accum)
@@ -1067,29 +1076,34 @@ inline int bigsys_backward(BigSys* s, const double* lo, const double* di, const 
   return 0;
 }
 
-// Can the whole solve be ONE cooperative launch?  One grid level with the full pyramid, few enough tiles for k_tri_fused's
-// in-kernel middle solve, and all of them co-resident (a grid-wide barrier needs that; checked once per instantiation).
-template <bool ACCUM>
-inline bool bigsys_fused_fits(size_t tiles) {
+// One cooperative launch for the closed m-row system (p0..p3) whose tiles each leave 2 rows in L: possible while the tiles
+// are few enough for the in-kernel middle solve and all co-resident (a grid-wide barrier needs that; the capacity of
+// each instantiation is asked once).  Returns -1 when it does not apply (the caller takes the three-launch path).
+template <int SRC, bool ACCUM, int MAXT>
+inline int bigsys_fused_try_n(const TileArgs& k, size_t tiles, cudaStream_t st, unsigned long long* launches) {
+  constexpr size_t smem = sizeof(FusedSmem<MAXT>);
   static int capacity = [] {
     int dev = 0, coop = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tri_fused<ACCUM>, BS_THREADS, 0) != cudaSuccess) return 0;
+    if (!coop) return 0;
+    if (cudaFuncSetAttribute(k_tri_fused<SRC, ACCUM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tri_fused<SRC, ACCUM, MAXT>, BS_THREADS, smem) != cudaSuccess) return 0;
     return per_sm * bigsys_sm_count();
   }();
-  return tiles <= (size_t)BS_FUSED_MAX_TILES && tiles <= (size_t)capacity;
-}
-template <bool ACCUM>
-inline int bigsys_fused_launch(BigSys* s, const double* lo, const double* di, const double* up, const double* f, double* out,
-                               cudaStream_t st, unsigned long long* launches) {
-  BigLevel& L = s->levels[0];
-  TileArgs k{lo, di, up, f, (long long)s->n, L.a, L.c, L.s, L.f, L.u, out, 0};
-  void* args[] = {&k};
-  const size_t tiles = (s->n + BS_TILE - 1) / BS_TILE;
+  if (tiles > (size_t)MAXT || tiles > (size_t)capacity) return -1;
+  TileArgs args = k;
+  void* params[] = {&args};
   ++*launches;
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tri_fused<ACCUM>, dim3((unsigned)tiles), dim3(BS_THREADS), args, 0, st);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tri_fused<SRC, ACCUM, MAXT>, dim3((unsigned)tiles), dim3(BS_THREADS), params,
+                                              smem, st);
   return e == cudaSuccess ? 0 : bigsys_fail(e, "k_tri_fused");
+}
+template <int SRC, bool ACCUM>
+inline int bigsys_fused_try(const TileArgs& k, cudaStream_t st, unsigned long long* launches) {
+  const size_t tiles = ((size_t)k.m + BS_TILE - 1) / BS_TILE;
+  if (tiles <= 256) return bigsys_fused_try_n<SRC, ACCUM, 256>(k, tiles, st, launches);
+  return bigsys_fused_try_n<SRC, ACCUM, BS_FUSED_MAX_TILES>(k, tiles, st, launches);
 }
 
 // out (+)= A^{-1} f for the closed n-row system (lo, di, up); inputs are not modified.
@@ -1097,14 +1111,38 @@ inline int bigsys_solve_once(BigSys* s, const double* lo, const double* di, cons
                              bool accum, cudaStream_t st, unsigned long long* launches) {
   if (s->levels.empty())
     return bigsys_mid<BS_SRC_BANDS, BS_MID_SOLVE>(lo, di, up, f, s->n, out, accum, 0, nullptr, 0.0, 0.0, st, launches);
-  if (s->fused && s->levels.size() == 1 && s->levels[0].nlev == 0) {
-    const size_t tiles = (s->n + BS_TILE - 1) / BS_TILE;
-    if (accum ? bigsys_fused_fits<true>(tiles) : bigsys_fused_fits<false>(tiles))
-      return accum ? bigsys_fused_launch<true>(s, lo, di, up, f, out, st, launches)
-                   : bigsys_fused_launch<false>(s, lo, di, up, f, out, st, launches);
+  const size_t K = s->levels.size();
+  BigLevel& L = s->levels.back();
+  // the last grid level (full pyramid, leaves 2 rows per tile) together with the middle solve in one cooperative launch
+  if (s->fused && L.nlev == 0) {
+    int rc = -1;
+    if (K == 1) {
+      const TileArgs k{lo, di, up, f, (long long)s->n, L.a, L.c, L.s, L.f, L.u, out, 0};
+      rc = accum ? bigsys_fused_try<BS_SRC_BANDS, true>(k, st, launches) : bigsys_fused_try<BS_SRC_BANDS, false>(k, st, launches);
+      if (rc >= 0) return rc;
+    } else {
+      BigLevel& Q = s->levels[K - 2];
+      const size_t tiles = (Q.m + BS_TILE - 1) / BS_TILE;
+      // (checked before the forward sweeps are launched; co-residency inside.)  Only up to 256 tiles: beyond that the
+      // three-launch path with its TMA-staged tiles is as fast (measured at 306 tiles, the 10^7-row case: 167 vs 162 us)
+      if (tiles <= 256) {
+        if (bigsys_forward(s, lo, di, up, f, 0, st, launches, K - 1)) return 1;
+        const TileArgs k{Q.a, Q.c, Q.s, Q.f, (long long)Q.m, L.a, L.c, L.s, L.f, L.u, Q.u, 0};
+        rc = bigsys_fused_try<BS_SRC_ROWS, false>(k, st, launches);
+        if (rc > 0) return rc;
+        if (rc < 0) {  // not co-resident after all: the last level the ordinary way
+          cudaError_t e = bigsys_launch_tile<BS_SRC_ROWS, false, false>(s, L.nlev, Q.m, Q.a, Q.c, Q.s, Q.f, L.a, L.c, L.s, L.f, nullptr,
+                                                                       nullptr, 0, st);
+          ++*launches;
+          if (e != cudaSuccess) return bigsys_fail(e, "k_tri_tile<reduce>");
+          if (bigsys_mid<BS_SRC_ROWS, BS_MID_SOLVE>(L.a, L.c, L.s, L.f, L.m, L.u, false, 0, nullptr, 0.0, 0.0, st, launches)) return 1;
+          return bigsys_backward(s, lo, di, up, f, 0, out, accum, st, launches, K);
+        }
+        return bigsys_backward(s, lo, di, up, f, 0, out, accum, st, launches, K - 1);
+      }
+    }
   }
   if (bigsys_forward(s, lo, di, up, f, 0, st, launches)) return 1;
-  BigLevel& L = s->levels.back();
   if (bigsys_mid<BS_SRC_ROWS, BS_MID_SOLVE>(L.a, L.c, L.s, L.f, L.m, L.u, false, 0, nullptr, 0.0, 0.0, st, launches)) return 1;
   return bigsys_backward(s, lo, di, up, f, 0, out, accum, st, launches);
 }
