@@ -55,7 +55,7 @@ constexpr int BS_TILE = BS_R * BS_THREADS;    // 2048 rows per CTA
 constexpr int BS_MID_CAP = 2048;              // rows the single-CTA kernel k_tri_mid solves directly
 constexpr int BS_TMA_MIN_TILES = 64;          // smaller systems are launch-latency bound: plain k_tri_tile
 constexpr int BS_FUSED_MAX_TILES = 512;       // most tiles k_tri_fused's in-kernel middle solve has room for
-constexpr int BS_SHALLOW_MIN_TILES = 592;     // 4 tiles per SM: from here on an application is throughput bound
+constexpr int BS_SHALLOW_MIN_TILES = 445;     // more tiles than one cooperative launch can hold (3 per SM): throughput bound from here on
 #ifndef BS_MIN_CTAS
 #define BS_MIN_CTAS 3
 #endif
