@@ -189,11 +189,32 @@ def run_reference(args, rank):
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly one JSON line.  Libraries write to fd 1 behind Python's back (NCCL prints its version banner
+    there whenever NCCL_DEBUG is VERSION or louder, whatever NCCL_DEBUG_FILE says — the GPU boxes export NCCL_DEBUG=VERSION):
+    keep a private duplicate of the real stdout for the line and point fd 1 at stderr for everybody else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -220,8 +241,6 @@ def main():
         pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -382,7 +401,7 @@ def main():
         line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                 "single_thread_value": v_one}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
