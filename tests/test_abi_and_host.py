@@ -192,3 +192,11 @@ def test_exact_division_sequence_is_correctly_rounded():
     spec.loader.exec_module(mod)
     bad, inexact = mod.run(seed=2026, cases=30000)
     assert bad == 0 and inexact == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/dzahui_b200.h must compile as C99 (no C++-isms, no torch types)"""
+    src = tmp_path / "consumer.c"
+    src.write_text('#include "dzahui_b200.h"\nint main(void) { dzb_options o; dzb_mesh* m = 0; (void)o; (void)m; return DZB_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           str(src)])
