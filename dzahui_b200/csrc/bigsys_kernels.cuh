@@ -198,8 +198,7 @@ __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int l
 }
 
 // Shared-memory pyramid below a level-1 system of up to 8*P1 rows: level capacities P1, ceil(P1/4), ... , 1 chunks, then the
-// final 2 rows.  WARP: the pyramid belongs to one warp (tile of 256 rows) and synchronises with __syncwarp, so the warps
-// of a CTA run their tiles independently; otherwise it belongs to the CTA (__syncthreads).
+// final 2 rows.  It belongs to the CTA: the levels are separated by __syncthreads.
 template <int P>
 struct PyramidRows {
   static constexpr int value = 8 * lvl_stride(P) + PyramidRows<(P + 3) / 4>::value;
@@ -208,14 +207,12 @@ template <>
 struct PyramidRows<1> {
   static constexpr int value = 8 * lvl_stride(1) + 2;
 };
-template <int P1, bool WARP = false>
+template <int P1>
 struct Pyramid {
   static constexpr int ROWS = PyramidRows<P1>::value;
   double a[ROWS], c[ROWS], s[ROWS], d[ROWS];
   __device__ __forceinline__ LevelPtr level(int off) { return {a + off, c + off, s + off, d + off}; }
-  __device__ __forceinline__ static void sync() {
-    if (WARP) __syncwarp(); else __syncthreads();
-  }
+  __device__ __forceinline__ static void sync() { __syncthreads(); }
   // Forward sweeps from level 1 (holding rows1 rows); every thread of the tile must call.  NLEV == 0: down to the final 2
   // rows.  NLEV > 0: only NLEV level reductions.  The level that is left starts at row `off` of the arrays, holds `rows`
   // rows and is chunk-interleaved with row stride `cap` (row r at off + lvl_pos(r, cap); cap == 0: the final pair, at off + r).
@@ -428,8 +425,8 @@ __device__ __forceinline__ bool chunk_load_direct(const TileArgs& k, long long g
 // shared-memory pyramid; returns the level the pyramid stopped at (see Pyramid::Left).  tile_backward: that level's d[] now
 // holds its solved unknowns; back-substitution through the pyramid and the chunk, out[].  Every thread of the tile must
 // call both.  vec: out[] takes 128-bit stores.  tile_body strings them together for the two-pass kernels.
-template <int SRC, bool KEEP, int NLEV, int P1, bool WARP>
-__device__ __forceinline__ typename Pyramid<P1, WARP>::Left tile_forward(Pyramid<P1, WARP>& pyr, const TileArgs& k, double (&A)[BS_R],
+template <int SRC, bool KEEP, int NLEV, int P1>
+__device__ __forceinline__ typename Pyramid<P1>::Left tile_forward(Pyramid<P1>& pyr, const TileArgs& k, double (&A)[BS_R],
                                                                          double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R],
                                                                          int len, long long g0, int t, int rows1) {
   const long long m = k.m;
@@ -458,8 +455,8 @@ __device__ __forceinline__ typename Pyramid<P1, WARP>::Left tile_forward(Pyramid
   return pyr.template reduce_to<NLEV, KEEP>(t, rows1);
 }
 
-template <int SRC, bool ACCUM, int NLEV, int P1, bool WARP>
-__device__ __forceinline__ void tile_backward(Pyramid<P1, WARP>& pyr, const TileArgs& k, const double (&A)[BS_R],
+template <int SRC, bool ACCUM, int NLEV, int P1>
+__device__ __forceinline__ void tile_backward(Pyramid<P1>& pyr, const TileArgs& k, const double (&A)[BS_R],
                                               const double (&C)[BS_R], const double (&S)[BS_R], const double (&F)[BS_R], int len,
                                               long long g0, bool vec, int t, int rows1) {
   const long long m = k.m;
@@ -509,20 +506,20 @@ __device__ __forceinline__ void tile_backward(Pyramid<P1, WARP>& pyr, const Tile
   }
 }
 
-template <int SRC, bool SOLVE, bool ACCUM, int NLEV, int P1, bool WARP>
-__device__ __forceinline__ void tile_body(Pyramid<P1, WARP>& pyr, const TileArgs& k, double (&A)[BS_R], double (&C)[BS_R],
+template <int SRC, bool SOLVE, bool ACCUM, int NLEV, int P1>
+__device__ __forceinline__ void tile_body(Pyramid<P1>& pyr, const TileArgs& k, double (&A)[BS_R], double (&C)[BS_R],
                                           double (&S)[BS_R], double (&F)[BS_R], int len, long long g0, bool vec, int t,
                                           long long tile, int rows1) {
   constexpr int ROUT = bs_rows_left(P1, NLEV);  // rows a full tile leaves
-  static_assert(ROUT <= 32 || !WARP, "one unknown per thread");
+  static_assert(ROUT <= BS_THREADS, "one unknown per thread");
   const long long obase = (long long)ROUT * tile;
   // SOLVE: the solved unknowns of the level the pyramid stops at are fetched now (one per thread) and land while the
   // sweeps run; read after the forward sweeps they would put an L2 round trip on every tile's critical path
   double u_left = 0.0;
   if (SOLVE && t < bs_rows_left_of(rows1, P1, NLEV)) u_left = k.ured[obase + t];
-  const typename Pyramid<P1, WARP>::Left left = tile_forward<SRC, SOLVE, NLEV>(pyr, k, A, C, S, F, len, g0, t, rows1);
+  const typename Pyramid<P1>::Left left = tile_forward<SRC, SOLVE, NLEV>(pyr, k, A, C, S, F, len, g0, t, rows1);
   if (!SOLVE) {
-    for (int r = t; r < left.rows; r += WARP ? 32 : BS_THREADS) {
+    for (int r = t; r < left.rows; r += BS_THREADS) {
       const int q = left.pos(r);
       k.red_a[obase + r] = pyr.a[q], k.red_c[obase + r] = pyr.c[q], k.red_s[obase + r] = pyr.s[q], k.red_f[obase + r] = pyr.d[q];
     }
