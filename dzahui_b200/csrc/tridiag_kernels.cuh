@@ -147,7 +147,7 @@ struct WarpStage3 {  // three input streams, chunk by chunk, double-buffered thr
 __global__ void __launch_bounds__(32) k_thomas_factor_warp(const double* __restrict__ lo, const double* __restrict__ di,
                                                            const double* __restrict__ up, double* __restrict__ c,
                                                            double* __restrict__ den, double* __restrict__ rden, long long n) {
-  __shared__ double s_lo[TW_CH], s_di[TW_CH], s_up[TW_CH], s_c[TW_CH], s_den[TW_CH];
+  __shared__ double s_lo[TW_CH + 2], s_di[TW_CH + 2], s_up[TW_CH + 2], s_c[TW_CH], s_den[TW_CH], s_r[TW_CH];
   const int lane = threadIdx.x;
   const long long o = (long long)blockIdx.x * n;
   lo += o, di += o, up += o, c += o, den += o, rden += o;
@@ -163,18 +163,25 @@ __global__ void __launch_bounds__(32) k_thomas_factor_warp(const double* __restr
       int j = 0;
       if (base == 0) {  // row 0
         cp = s_up[0] / s_di[0];
-        s_c[0] = cp, s_den[0] = s_di[0];
+        s_c[0] = cp, s_den[0] = s_di[0], s_r[0] = __drcp_rn(s_di[0]);
         j = 1;
       }
       const int jend = (base + len == n) ? len - 1 : len;  // the last row of the bar is handled below
+      // den_i = di_i - lo_i c'_{i-1}, c'_i = up_i / den_i: the quotient through the correctly rounded reciprocal (which the
+      // solve kernels want anyway) and exact_div's correction sequence; operands of row j + 1 are read during row j
+      double a = s_lo[j], b = s_di[j], u = s_up[j];
 #pragma unroll 4
       for (; j < jend; ++j) {
-        const double dn = s_di[j] - s_lo[j] * cp;
-        cp = s_up[j] / dn;
-        s_c[j] = cp, s_den[j] = dn;
+        const double na = s_lo[j + 1], nb = s_di[j + 1], nu = s_up[j + 1];
+        const double dn = b - a * cp;
+        const double r = __drcp_rn(dn);
+        cp = exact_div(u, dn, r, den_in_safe_range(dn));
+        s_c[j] = cp, s_den[j] = dn, s_r[j] = r;
+        a = na, b = nb, u = nu;
       }
       if (base + len == n && (n > 1)) {
-        s_den[len - 1] = s_di[len - 1] - s_lo[len - 1] * cp;
+        const double dn = s_di[len - 1] - s_lo[len - 1] * cp;
+        s_den[len - 1] = dn, s_r[len - 1] = __drcp_rn(dn);
         s_c[len - 1] = 0.0;
       }
     }
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(32) k_thomas_factor_warp(const double* __restr
 #pragma unroll
     for (int k = 0; k < TW_K; ++k) {
       const int j = k * 32 + lane;
-      if (j < len) c[base + j] = s_c[j], den[base + j] = s_den[j], rden[base + j] = __drcp_rn(s_den[j]);
+      if (j < len) c[base + j] = s_c[j], den[base + j] = s_den[j], rden[base + j] = s_r[j];
     }
     __syncwarp();
   }
