@@ -3,10 +3,14 @@
 
 #include <algorithm>
 #include <cctype>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include <unordered_set>
+#include <cstring>
+#include <functional>
+#include <string_view>
+#include <thread>
 #include <utility>
 
 namespace dzb {
@@ -44,82 +48,171 @@ bool parse_rust_float(const char* b, const char* e, double* value) {
     }
     if (p != e) return false;
   }
-  std::string tmp(b, e);
+  if (!special) {  // the common case without a heap copy: from_chars is correctly rounded too and takes a bounded range
+    const char* q = *b == '+' ? b + 1 : b;
+    const std::from_chars_result r = std::from_chars(q, e, *value, std::chars_format::general);
+    if (r.ec == std::errc() && r.ptr == e) return true;
+  }
+  std::string tmp(b, e);  // inf / nan words, and over/underflow (strtod returns +-inf / 0 like Rust)
   *value = std::strtod(tmp.c_str(), nullptr);
   return true;
 }
 
 struct VertexLine {
-  std::string token[3];
   double value[3];
 };
 
-}  // namespace
-
-IngestStatus ingest_obj_1d(const char* path, bool has_multiplier, double multiplier, Ingested1D* out) {
-  std::FILE* f = std::fopen(path, "rb");
-  if (!f) {
-    out->message = std::string("cannot open ") + path;
-    return IngestStatus::Io;
+// check_for_constant_coordinates (:140-190) keeps a HashMap of the coordinate STRINGS of every axis (keys starting with
+// "0.0" or "-0.0" collapsed to "0.0") and only ever asks whether an axis has exactly one key: remember the first key and
+// whether a different one turned up.
+struct AxisKeys {
+  std::string_view first;
+  bool any = false, several = false;
+  void add(std::string_view t) {
+    if (t.substr(0, 3) == "0.0" || t.substr(0, 4) == "-0.0") t = "0.0";
+    if (!any) first = t, any = true;
+    else if (t != first) several = true;
   }
-  std::string text;
-  char buf[1 << 16];
-  size_t got;
-  while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, got);
-  std::fclose(f);
+  bool constant() const { return any && !several; }
+};
 
-  // One pass over the lines: keep those starting with "v " and split them on single blanks (`split(" ")`),
-  // exactly 3 fields after the tag, each a Rust-parsable float (mesh_builder.rs:58-84 and :159-178).
+
+// ---- the line pass, shared by the 1-D and 2-D builders and run on several threads for big files ------------------------
+// A chunk is a run of whole lines.  Every chunk parses its `v` lines (and, for 2-D, its `f` lines) independently; the
+// results are concatenated in file order, and the first error in file order is the one reported, so the outcome is
+// that of the single sequential pass the reference makes.
+struct Chunk {
   std::vector<VertexLine> vs;
-  size_t pos = 0;
-  while (pos < text.size()) {
-    size_t eol = text.find('\n', pos);
-    if (eol == std::string::npos) eol = text.size();
+  std::vector<unsigned> triangles;
+  AxisKeys keys[3];
+  IngestStatus status = IngestStatus::Ok;
+  const char* message = nullptr;
+};
+
+void parse_chunk(const std::string& text, size_t pos, size_t stop, bool faces, Chunk* out) {
+  const char* const base = text.data();
+  auto fail = [&](const char* msg) { out->status = IngestStatus::Parse, out->message = msg; };
+  std::pair<size_t, size_t> fl[4];
+  while (pos < stop) {
+    const char* nl = static_cast<const char*>(std::memchr(base + pos, '\n', stop - pos));
+    const size_t eol = nl ? (size_t)(nl - base) : stop;
     size_t end = eol;
     if (end > pos && text[end - 1] == '\r') --end;  // BufRead::lines strips "\r\n"
-    if (end - pos >= 2 && text[pos] == 'v' && text[pos + 1] == ' ') {
-      VertexLine vl;
-      int nf = 0;
-      size_t s = pos + 2;
+    const bool vline = end - pos >= 2 && text[pos] == 'v' && text[pos + 1] == ' ';
+    const bool fline = faces && end - pos >= 2 && text[pos] == 'f' && text[pos + 1] == ' ';
+    if (vline || fline) {
+      // str::split(" ") after the tag: the first three fields are kept, the rest only counted (and, for `v`, parsed)
+      size_t nf = 0, s = pos + 2;
       bool ok = true;
+      VertexLine vl{};
       for (;;) {
-        size_t sp = text.find(' ', s);
-        if (sp == std::string::npos || sp > end) sp = end;
-        double v;
-        if (!parse_rust_float(text.data() + s, text.data() + sp, &v)) ok = false;
-        if (nf < 3) {
-          vl.token[nf].assign(text, s, sp - s);
-          vl.value[nf] = v;
+        const char* bl = static_cast<const char*>(std::memchr(base + s, ' ', end - s));
+        const size_t sp = bl ? (size_t)(bl - base) : end;
+        if (vline) {
+          double v = 0.0;
+          if (!parse_rust_float(base + s, base + sp, &v)) ok = false;
+          if (nf < 3) vl.value[nf] = v;
         }
+        if (nf < 3) fl[nf] = {s, sp};
         ++nf;
         if (sp == end) break;
         s = sp + 1;
       }
-      if (!ok) {
-        out->message = "Error while parsing vertex coordinate from obj";
-        return IngestStatus::Parse;
+      if (vline) {
+        if (!ok) return fail("Error while parsing vertex coordinate from obj");
+        if (nf != 3) return fail("A vertex line should contain 3 elements only");
+        for (int a = 0; a < 3; ++a) out->keys[a].add(std::string_view(base + fl[a].first, fl[a].second - fl[a].first));
+        out->vs.push_back(vl);
+      } else {
+        if (nf != 3) return fail("Amount of face specificating elements should be 3.");
+        for (size_t k = 0; k < 3; ++k) {  // a/b/c: the first field is the vertex, exactly two more must follow
+          const size_t b = fl[k].first, e = fl[k].second;
+          const char* sl = static_cast<const char*>(std::memchr(base + b, '/', e - b));
+          const size_t slash = sl ? (size_t)(sl - base) : e;
+          unsigned long long v = 0;
+          size_t i = b;
+          if (i < slash && text[i] == '+') ++i;
+          bool okf = i < slash;
+          for (; i < slash; ++i) {
+            if (text[i] < '0' || text[i] > '9') { okf = false; break; }
+            v = v * 10 + (unsigned)(text[i] - '0');
+            if (v > 0xffffffffULL) { okf = false; break; }
+          }
+          if (!okf) return fail("Error while parsing face coordinate");
+          size_t extra = 0;
+          for (size_t j = slash; j < e; ++j) extra += text[j] == '/';
+          if (extra != 2) return fail("Amount of elements per face specification should be 3 in format a/b/c.");
+          out->triangles.push_back((unsigned)v - 1u);
+        }
       }
-      if (nf != 3) {
-        out->message = "A vertex line should contain 3 elements only";
-        return IngestStatus::Parse;
-      }
-      vs.push_back(std::move(vl));
     }
     pos = eol + 1;
   }
+}
 
-  // Axis detection (check_for_constant_coordinates, :140-190): distinct coordinate STRINGS per axis, every key
-  // starting with "0.0" or "-0.0" collapsed to "0.0"; an axis with one key is constant.
-  std::unordered_set<std::string> keys[3];
-  for (const VertexLine& vl : vs)
-    for (int a = 0; a < 3; ++a) {
-      const std::string& t = vl.token[a];
-      if (t.compare(0, 3, "0.0") == 0 || t.compare(0, 4, "-0.0") == 0)
-        keys[a].insert("0.0");
-      else
-        keys[a].insert(t);
+// Reads the file and runs the line pass; vertices / triangles / per-axis keys in file order, or the first error.
+IngestStatus read_and_parse(const char* path, bool faces, std::string* text, Chunk* all, std::string* message) {
+  std::FILE* f = std::fopen(path, "rb");
+  if (!f) {
+    *message = std::string("cannot open ") + path;
+    return IngestStatus::Io;
+  }
+  char buf[1 << 16];
+  size_t got;
+  while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text->append(buf, got);
+  std::fclose(f);
+
+  const size_t size = text->size();
+  size_t nthreads = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+  nthreads = std::min(nthreads, size / (1u << 20) + 1);  // at least ~1 MB of text per thread
+  std::vector<size_t> cut(nthreads + 1, size);
+  cut[0] = 0;
+  for (size_t k = 1; k < nthreads; ++k) {  // chunk boundaries on line starts
+    size_t p = std::max(cut[k - 1], size * k / nthreads);
+    const char* nl = p < size ? static_cast<const char*>(std::memchr(text->data() + p, '\n', size - p)) : nullptr;
+    cut[k] = nl ? (size_t)(nl - text->data()) + 1 : size;
+  }
+  std::vector<Chunk> chunks(nthreads);
+  std::vector<std::thread> pool;
+  for (size_t k = 1; k < nthreads; ++k) pool.emplace_back(parse_chunk, std::cref(*text), cut[k], cut[k + 1], faces, &chunks[k]);
+  parse_chunk(*text, cut[0], cut[1], faces, &chunks[0]);
+  for (std::thread& t : pool) t.join();
+
+  size_t nv = 0, nt = 0;
+  for (const Chunk& c : chunks) {
+    if (c.status != IngestStatus::Ok) {  // chunks before this one parsed cleanly: this is the first error of the file
+      *message = c.message;
+      return c.status;
     }
-  const bool cx = keys[0].size() == 1, cy = keys[1].size() == 1, cz = keys[2].size() == 1;
+    nv += c.vs.size(), nt += c.triangles.size();
+  }
+  all->vs.reserve(nv), all->triangles.reserve(nt);
+  for (const Chunk& c : chunks) {
+    all->vs.insert(all->vs.end(), c.vs.begin(), c.vs.end());
+    all->triangles.insert(all->triangles.end(), c.triangles.begin(), c.triangles.end());
+    for (int a = 0; a < 3; ++a) {
+      if (!c.keys[a].any) continue;
+      all->keys[a].add(c.keys[a].first);  // (already collapsed; add() is idempotent on it)
+      if (c.keys[a].several) all->keys[a].several = true;
+    }
+  }
+  return IngestStatus::Ok;
+}
+
+}  // namespace
+
+IngestStatus ingest_obj_1d(const char* path, bool has_multiplier, double multiplier, Ingested1D* out) {
+  // One pass over the lines: keep those starting with "v " and split them on single blanks (`split(" ")`),
+  // exactly 3 fields after the tag, each a Rust-parsable float (mesh_builder.rs:58-84 and :159-178).
+  std::string text;
+  Chunk all;
+  const IngestStatus st = read_and_parse(path, false, &text, &all, &out->message);
+  if (st != IngestStatus::Ok) return st;
+  const std::vector<VertexLine>& vs = all.vs;
+  const AxisKeys* keys = all.keys;
+
+  // Axis detection (check_for_constant_coordinates, :140-190): an axis with one distinct coordinate string is constant.
+  const bool cx = keys[0].constant(), cy = keys[1].constant(), cz = keys[2].constant();
   int kept;  // the pair [1,0] / [2,1] / [2,0] of removed axes leaves z / x / y (:217-227, :244-247)
   if (cx && cy)
     kept = 2;
@@ -175,96 +268,17 @@ IngestStatus ingest_obj_1d(const char* path, bool has_multiplier, double multipl
 }
 
 IngestStatus ingest_obj_2d(const char* path, Ingested2D* out) {
-  std::FILE* f = std::fopen(path, "rb");
-  if (!f) {
-    out->message = std::string("cannot open ") + path;
-    return IngestStatus::Io;
-  }
   std::string text;
-  char buf[1 << 16];
-  size_t got;
-  while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, got);
-  std::fclose(f);
-
-  std::vector<VertexLine> vs;
-  std::unordered_set<std::string> keys[3];
-  size_t pos = 0;
-  auto fields = [&](size_t s, size_t end, std::vector<std::pair<size_t, size_t>>* out_f) {  // str::split(" ") after the tag
-    out_f->clear();
-    for (;;) {
-      size_t sp = text.find(' ', s);
-      if (sp == std::string::npos || sp > end) sp = end;
-      out_f->push_back({s, sp});
-      if (sp == end) break;
-      s = sp + 1;
-    }
-  };
-  std::vector<std::pair<size_t, size_t>> fl;
-  while (pos < text.size()) {
-    size_t eol = text.find('\n', pos);
-    if (eol == std::string::npos) eol = text.size();
-    size_t end = eol;
-    if (end > pos && text[end - 1] == '\r') --end;
-    if (end - pos >= 2 && text[pos] == 'v' && text[pos + 1] == ' ') {
-      fields(pos + 2, end, &fl);
-      VertexLine vl;
-      bool ok = true;
-      for (size_t k = 0; k < fl.size(); ++k) {
-        double v;
-        if (!parse_rust_float(text.data() + fl[k].first, text.data() + fl[k].second, &v)) ok = false;
-        if (k < 3) vl.token[k].assign(text, fl[k].first, fl[k].second - fl[k].first), vl.value[k] = v;
-      }
-      if (!ok) {
-        out->message = "Error while parsing vertex coordinate from obj";
-        return IngestStatus::Parse;
-      }
-      if (fl.size() != 3) {
-        out->message = "A vertex line should contain 3 elements only";
-        return IngestStatus::Parse;
-      }
-      for (int a = 0; a < 3; ++a) {
-        const std::string& t = vl.token[a];
-        keys[a].insert((t.compare(0, 3, "0.0") == 0 || t.compare(0, 4, "-0.0") == 0) ? std::string("0.0") : t);
-      }
-      vs.push_back(std::move(vl));
-    } else if (end - pos >= 2 && text[pos] == 'f' && text[pos + 1] == ' ') {
-      fields(pos + 2, end, &fl);
-      if (fl.size() != 3) {
-        out->message = "Amount of face specificating elements should be 3.";
-        return IngestStatus::Parse;
-      }
-      for (size_t k = 0; k < 3; ++k) {  // a/b/c: the first field is the vertex, exactly two more must follow
-        const size_t b = fl[k].first, e = fl[k].second;
-        size_t slash = text.find('/', b);
-        if (slash == std::string::npos || slash > e) slash = e;
-        unsigned long long v = 0;
-        size_t i = b;
-        if (i < slash && text[i] == '+') ++i;
-        bool ok = i < slash;
-        for (; i < slash; ++i) {
-          if (text[i] < '0' || text[i] > '9') { ok = false; break; }
-          v = v * 10 + (unsigned)(text[i] - '0');
-          if (v > 0xffffffffULL) { ok = false; break; }
-        }
-        if (!ok) {
-          out->message = "Error while parsing face coordinate";
-          return IngestStatus::Parse;
-        }
-        size_t extra = 0;
-        for (size_t j = slash; j < e; ++j) extra += text[j] == '/';
-        if (extra != 2) {
-          out->message = "Amount of elements per face specification should be 3 in format a/b/c.";
-          return IngestStatus::Parse;
-        }
-        out->triangles.push_back((unsigned)v - 1u);
-      }
-    }
-    pos = eol + 1;
-  }
+  Chunk all;
+  const IngestStatus st = read_and_parse(path, true, &text, &all, &out->message);
+  if (st != IngestStatus::Ok) return st;
+  const std::vector<VertexLine>& vs = all.vs;
+  const AxisKeys* keys = all.keys;
+  out->triangles = std::move(all.triangles);
   int cc;  // :355-363
-  if (keys[0].size() == 1) cc = 0;
-  else if (keys[1].size() == 1) cc = 1;
-  else if (keys[2].size() == 1) cc = 2;
+  if (keys[0].constant()) cc = 0;
+  else if (keys[1].constant()) cc = 1;
+  else if (keys[2].constant()) cc = 2;
   else {
     out->message = "Only coordinates over a plane paralell to x, y or z plane are accepted. Check .obj file.";
     return IngestStatus::Parse;
