@@ -157,7 +157,12 @@ IngestStatus read_and_parse(const char* path, bool faces, std::string* text, Chu
     *message = std::string("cannot open ") + path;
     return IngestStatus::Io;
   }
-  char buf[1 << 16];
+  if (std::fseek(f, 0, SEEK_END) == 0) {  // one allocation of the file's size when it is known (regular files)
+    const long len = std::ftell(f);
+    if (len > 0) text->reserve((size_t)len);
+    std::rewind(f);
+  }
+  char buf[1 << 18];
   size_t got;
   while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text->append(buf, got);
   std::fclose(f);
