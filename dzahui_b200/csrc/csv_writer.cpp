@@ -7,7 +7,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include <dirent.h>
 #include <sys/stat.h>
@@ -17,37 +20,53 @@
 
 namespace dzb {
 
-std::string rust_f64_to_string(double v) {
-  if (std::isnan(v)) return "NaN";
-  if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
-  if (v == 0.0) return std::signbit(v) ? "-0" : "0";
-  char buf[64];
-  auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);  // shortest round-trip digits
-  std::string sci(buf, res.ptr);
-  std::string out;
-  size_t pos = 0;
-  if (sci[0] == '-') out.push_back('-'), pos = 1;
-  const size_t epos = sci.find('e');
-  std::string digits;
-  for (size_t i = pos; i < epos; ++i)
-    if (sci[i] != '.') digits.push_back(sci[i]);
-  const int exp10 = std::atoi(sci.c_str() + epos + 1);  // value = d.ddd x 10^exp10
-  const int nd = (int)digits.size();
+// Writes the digits into out (at least RUST_F64_MAX bytes) and returns their count; no allocation.
+constexpr size_t RUST_F64_MAX = 352;  // "-0." + 323 zeros + 17 digits, or 309 integer digits
+size_t rust_f64_format(double v, char* out) {
+  auto lit = [&](const char* t) {
+    const size_t n = std::strlen(t);
+    std::memcpy(out, t, n);
+    return n;
+  };
+  if (std::isnan(v)) return lit("NaN");
+  if (std::isinf(v)) return lit(v < 0 ? "-inf" : "inf");
+  if (v == 0.0) return lit(std::signbit(v) ? "-0" : "0");
+  char sci[64];
+  const char* end = std::to_chars(sci, sci + sizeof sci, v, std::chars_format::scientific).ptr;  // shortest round-trip digits
+  const char* p = sci;
+  char* o = out;
+  if (*p == '-') *o++ = '-', ++p;
+  char digits[24];
+  int nd = 0;
+  for (; p < end && *p != 'e'; ++p)
+    if (*p != '.') digits[nd++] = *p;
+  int exp10 = 0;  // value = d.ddd x 10^exp10
+  {
+    ++p;  // 'e'
+    const bool neg = *p == '-';
+    if (*p == '-' || *p == '+') ++p;
+    for (; p < end; ++p) exp10 = exp10 * 10 + (*p - '0');
+    if (neg) exp10 = -exp10;
+  }
   if (exp10 >= 0) {
     if (exp10 + 1 >= nd) {  // integer: pad with zeros
-      out += digits;
-      out.append((size_t)(exp10 + 1 - nd), '0');
+      std::memcpy(o, digits, (size_t)nd), o += nd;
+      std::memset(o, '0', (size_t)(exp10 + 1 - nd)), o += exp10 + 1 - nd;
     } else {
-      out.append(digits, 0, (size_t)exp10 + 1);
-      out.push_back('.');
-      out.append(digits, (size_t)exp10 + 1, std::string::npos);
+      std::memcpy(o, digits, (size_t)exp10 + 1), o += exp10 + 1;
+      *o++ = '.';
+      std::memcpy(o, digits + exp10 + 1, (size_t)(nd - exp10 - 1)), o += nd - exp10 - 1;
     }
   } else {
-    out += "0.";
-    out.append((size_t)(-exp10 - 1), '0');
-    out += digits;
+    *o++ = '0', *o++ = '.';
+    std::memset(o, '0', (size_t)(-exp10 - 1)), o += -exp10 - 1;
+    std::memcpy(o, digits, (size_t)nd), o += nd;
   }
-  return out;
+  return (size_t)(o - out);
+}
+std::string rust_f64_to_string(double v) {
+  char buf[RUST_F64_MAX];
+  return std::string(buf, rust_f64_format(v, buf));
 }
 
 }  // namespace dzb
@@ -95,15 +114,33 @@ int dzb_csv_write(const char* dir, const char* prefix, double id, const char* co
     block += variable_names[k];
     block.push_back(k + 1 < n_vars ? ',' : '\n');
   }
-  for (size_t i = 0; i < n_vals; ++i) {
-    block += dzb::rust_f64_to_string(vals[i]);
-    block.push_back(((i + 1) % n_vars == 0 || i + 1 == n_vals) ? '\n' : ',');
-    if (block.size() > (1u << 20)) {
-      if (std::fwrite(block.data(), 1, block.size(), f) != block.size()) { std::fclose(f); return DZB_IO; }
-      block.clear();
-    }
+  if (std::fwrite(block.data(), 1, block.size(), f) != block.size()) { std::fclose(f); return DZB_IO; }
+  // the values: formatted on all host threads, slab by slab (each thread a contiguous run of a slab), written in order
+  const size_t SLAB = (size_t)1 << 22;
+  const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::string> parts;
+  bool ok = true;
+  for (size_t s0 = 0; s0 < n_vals && ok; s0 += SLAB) {
+    const size_t s1 = std::min(n_vals, s0 + SLAB);
+    const size_t nt = std::min(std::min<size_t>(hw, 32), (s1 - s0) / 65536 + 1);
+    parts.assign(nt, std::string());
+    auto work = [&](size_t k) {
+      const size_t b = s0 + (s1 - s0) * k / nt, e = s0 + (s1 - s0) * (k + 1) / nt;
+      std::string& out = parts[k];
+      out.reserve((e - b) * 24);
+      char buf[dzb::RUST_F64_MAX + 1];
+      for (size_t i = b; i < e; ++i) {
+        size_t len = dzb::rust_f64_format(vals[i], buf);
+        buf[len++] = ((i + 1) % n_vars == 0 || i + 1 == n_vals) ? '\n' : ',';
+        out.append(buf, len);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < nt; ++k) pool.emplace_back(work, k);
+    work(0);
+    for (std::thread& t : pool) t.join();
+    for (const std::string& part : parts) ok = ok && std::fwrite(part.data(), 1, part.size(), f) == part.size();
   }
-  const bool ok = std::fwrite(block.data(), 1, block.size(), f) == block.size();
   return (std::fclose(f) == 0 && ok) ? DZB_OK : DZB_IO;
 }
 
