@@ -121,3 +121,30 @@ def test_random_stokes(gpu, oracle, seed):
         assert glo.tobytes() == lo.tobytes() and gdi.tobytes() == di.tobytes() and gup.tobytes() == up.tobytes()
         assert grhs.tobytes() == rhs.tobytes()
         assert np.array_equal(s.solve(0.0), ref, equal_nan=True)
+
+
+@pytest.mark.parametrize("scale", [1e-75, 1e-30, 1e-3, 1.0, 1e3, 1e30, 1e75])
+@pytest.mark.parametrize("bc0", [0.0, -0.0, 1.0])
+def test_reference_arithmetic_bits_across_magnitudes(gpu, oracle, scale, bc0):
+    """The warp-per-bar sweeps divide by a stored correctly rounded reciprocal (exact_div) inside a safe range and fall back
+    to the division outside it: bars whose element lengths span 150 decades put the pivots (~1/h for the stiffness, ~h
+    for the mass matrix) on both sides of that range, zero left boundary values make every forward numerator a signed zero.
+    Static and time-dependent FAITHFUL results must keep the oracle's bits in all of them."""
+    rng = np.random.default_rng(int(abs(np.log10(scale)) * 7) + (3 if bc0 else 0))
+    n = 777
+    mesh = np.cumsum(rng.uniform(0.5, 1.5, n)) * scale
+    opt = gpu.make_options(gpu.ASSEMBLY_FAITHFUL, gpu.SOLVE_FAITHFUL)
+    mu, b = 1.0, 0.25 / scale  # keeps the cell Peclet number b h / (2 mu) of order 0.1 at every scale
+    p = gpu.DiffussionParams.time_independent().mu(mu).b(b).boundary_conditions(bc0, 15.0).build()
+    s = gpu.DiffussionSolverTimeIndependent(p, mesh, 40, opt)
+    want = oracle.thomas(*oracle.ti_assemble(mesh, mu, b, (bc0, 15.0), 40))
+    got = s.solve(0.0)
+    assert got.tobytes() == want.tobytes()
+    ic = rng.uniform(-1.0, 1.0, n - 2)
+    q = gpu.DiffussionParams.time_dependent().mu(mu).b(b).boundary_conditions(bc0, 15.0).initial_conditions(ic).build()
+    td = gpu.DiffussionSolverTimeDependent(q, mesh, 40, opt)
+    dt = 1e-3 * scale * scale
+    for _ in range(5):
+        u = td.solve(dt)
+    wantu = oracle.td_run(oracle.td_assemble(mesh, mu, b, 40), oracle.td_initial_state(ic, n, (bc0, 15.0)), dt, (bc0, 15.0), 5)
+    assert u.tobytes() == wantu.tobytes()
