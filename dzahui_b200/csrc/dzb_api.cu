@@ -268,6 +268,15 @@ struct dzb_mesh {
   float translation[3] = {0.f, 0.f, 0.f};
 };
 
+// ensembles of up to this many bars run the FAITHFUL kernels with a warp per bar (DZB_TW_MAX_BARS: tuning knob)
+static long long tw_max_bars() {
+  static const long long v = [] {
+    const char* e = std::getenv("DZB_TW_MAX_BARS");
+    return e ? std::atoll(e) : dzb::TW_MAX_BARS;
+  }();
+  return v;
+}
+
 struct dzb_euler {
   size_t T = 0, W = 0;                // trajectories, entries per state (incl. t)
   double *v = nullptr, *c = nullptr;  // SoA [W][T] state, [W + 1][T] coefficients
@@ -469,7 +478,7 @@ int ensemble_step_once(dzb_ensemble* e, double dt) {
     }
     if (rc) return rc;
   } else {
-    if ((long long)e->B <= dzb::TW_MAX_BARS)  // few bars: a warp per bar (same arithmetic, operands staged through shared memory)
+    if ((long long)e->B <= tw_max_bars())  // few bars: a warp per bar (same arithmetic, operands staged through shared memory)
       dzb::k_td_step_faithful_warp<<<(unsigned)e->B, 32, 0, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->mlo, e->mdi, e->mup, e->slo,
                                                                         e->sdi, e->sup, e->c, e->den, e->rden, (long long)e->n, dt, e->bc0, e->bc1);
     else
@@ -507,8 +516,8 @@ int ensemble_assemble(dzb_ensemble* e) {
     e->use_big = ok;
   }
   if (!e->use_big) {
-    if ((long long)e->B <= dzb::TW_MAX_BARS && !e->rden && (rc = dalloc(&e->rden, e->B * e->n))) return rc;
-    if ((long long)e->B <= dzb::TW_MAX_BARS)
+    if ((long long)e->B <= tw_max_bars() && !e->rden && (rc = dalloc(&e->rden, e->B * e->n))) return rc;
+    if ((long long)e->B <= tw_max_bars())
       dzb::k_thomas_factor_warp<<<(unsigned)e->B, 32, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, e->rden, (long long)e->n);
     else
       dzb::k_thomas_factor<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)e->n,
