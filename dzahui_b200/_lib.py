@@ -92,6 +92,7 @@ SIGNATURES = {
     "dzb_ensemble_state_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "dzb_ensemble_bands": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, c_double_p, c_double_p, c_double_p, C.c_size_t]),
     "dzb_ensemble_dims": (C.c_int, [C.c_void_p, c_size_p, c_size_p]),
+    "dzb_ensemble_step_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "dzb_ensemble_destroy": (None, [C.c_void_p]),
     "dzb_euler_create": (C.c_int, [C.c_size_t, C.c_size_t, c_double_p, c_double_p, C.POINTER(C.c_void_p)]),
     "dzb_euler_set_values": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),

@@ -1412,6 +1412,16 @@ int dzb_ensemble_dims(const dzb_ensemble* e, size_t* n_bars, size_t* n) {
   if (n) *n = e->n;
   return DZB_OK;
 }
+int dzb_ensemble_step_kernel(const dzb_ensemble* e, char* buf, size_t cap) {
+  if (!e || !buf || cap == 0) return fail(DZB_INVALID, "null pointer");
+  char name[96];
+  if (e->use_big) std::snprintf(name, sizeof name, "k_td_rhs + k_tri_* (one long bar)");
+  else if (e->fast && e->lean_ok) std::snprintf(name, sizeof name, "k_td_step_lean<%d,%d>", e->lean_L, e->lean_wpb);
+  else if (e->fast) std::snprintf(name, sizeof name, "k_td_step_fast<%d,4>", e->L);
+  else std::snprintf(name, sizeof name, (long long)e->B <= tw_max_bars() ? "k_td_step_faithful_warp" : "k_td_step_faithful");
+  std::snprintf(buf, cap, "%s", name);
+  return DZB_OK;
+}
 void dzb_ensemble_destroy(dzb_ensemble* e) { ensemble_free(e); }
 
 // ---- EulerSolver ensembles ---------------------------------------------------------------------------------------------

@@ -75,6 +75,12 @@ class EnsembleTimeDependent:
             res += [lo, di, up]
         return tuple(res)
 
+    def step_kernel(self):
+        """name of the kernel one step dispatches to (final after the first step)"""
+        buf = C.create_string_buffer(96)
+        check(self._lib.dzb_ensemble_step_kernel(self._h, buf, 96), self._lib)
+        return buf.value.decode()
+
     def close(self):
         if self._h:
             self._lib.dzb_ensemble_destroy(self._h)

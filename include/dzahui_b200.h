@@ -198,6 +198,9 @@ int dzb_ensemble_read_bars(const dzb_ensemble* e, const size_t* bar_ids, size_t 
 int dzb_ensemble_state_device(const dzb_ensemble* e, const double** device_ptr); /* bar-major [n_bars][n] */
 int dzb_ensemble_bands(const dzb_ensemble* e, size_t bar, int which, double* lo, double* di, double* up, size_t n);
 int dzb_ensemble_dims(const dzb_ensemble* e, size_t* n_bars, size_t* n);
+/* name of the kernel one step of this ensemble dispatches to (decided by the options, the sizes and, for the on-chip
+ * operator rebuild, by the first step's check of every row): what bench.py prints as roofline.kernel */
+int dzb_ensemble_step_kernel(const dzb_ensemble* e, char* buf, size_t cap);
 void dzb_ensemble_destroy(dzb_ensemble* e);
 
 /* ---- EulerSolver (reference solvers/euler/mod.rs:26-59; integration tests tests/euler.rs) for many trajectories ------ */

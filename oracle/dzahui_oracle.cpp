@@ -876,6 +876,51 @@ int dzo_ensemble_td_run(const double* mlo, const double* mdi, const double* mup,
   return err;
 }
 
+// ---- a resident ensemble for the timed CPU legs of bench.py: the matrices of every bar are built ONCE (what
+// DiffussionSolverTimeDependent::new leaves in the struct, time_dependent.rs:49-58), the states live in the session and
+// `advance` is `steps` x solve(dt) per bar inside one parallel region — no per-call band or state copies.
+struct DzoEnsemble {
+  size_t B = 0, n = 0;
+  double bc[2] = {0, 0};
+  std::vector<Banded> M, S;
+  std::vector<double> state;
+};
+void* dzo_ensemble_td_open(const double* mlo, const double* mdi, const double* mup, const double* slo, const double* sdi,
+                           const double* sup, const double* state, size_t B, size_t n, double bc0, double bc1) {
+  DzoEnsemble* e = new DzoEnsemble;
+  e->B = B, e->n = n, e->bc[0] = bc0, e->bc[1] = bc1;
+  e->M.reserve(B), e->S.reserve(B);
+  for (size_t b = 0; b < B; ++b) {
+    const size_t o = b * n;
+    e->M.push_back(from_bands(mlo + o, mdi + o, mup + o, n));
+    e->S.push_back(from_bands(slo + o, sdi + o, sup + o, n));
+  }
+  e->state.assign(state, state + B * n);
+  return e;
+}
+int dzo_ensemble_td_advance(void* h, double dt, size_t steps, int threads) {
+  DzoEnsemble* e = (DzoEnsemble*)h;
+  int err = OK;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1) if (threads > 1)
+  for (long long bb = 0; bb < (long long)e->B; ++bb) {
+    double* st = e->state.data() + (size_t)bb * e->n;
+    for (size_t s = 0; s < steps; ++s) {
+      int rc = td_solve(e->M[(size_t)bb], e->S[(size_t)bb], st, e->n, dt, e->bc);
+      if (rc) {
+        err = rc;
+        break;
+      }
+    }
+  }
+  return err;
+}
+int dzo_ensemble_td_read(const void* h, double* out) {
+  const DzoEnsemble* e = (const DzoEnsemble*)h;
+  std::memcpy(out, e->state.data(), e->state.size() * sizeof(double));
+  return OK;
+}
+void dzo_ensemble_td_close(void* h) { delete (DzoEnsemble*)h; }
+
 // ---- extended-precision Thomas ("truth" for the conditioning study of the 10^7-node bar, SURVEY §7 hard part 1).
 // Same recurrences as solve_by_thomas, evaluated in __float128 (113-bit) or x87 long double (64-bit mantissa).
 }  // extern "C"

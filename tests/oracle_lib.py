@@ -188,6 +188,42 @@ def ensemble_td_run(bands, state, dt, bc, steps, threads=1):
     return st
 
 
+class EnsembleSession:
+    """Resident CPU ensemble for timed legs: matrices built once, states advanced in place (no per-call copies)."""
+
+    def __init__(self, bands, state, bc):
+        b = [_arr(x) for x in bands]
+        st = _arr(state)
+        self.B, self.n = st.shape
+        L = lib()
+        L.dzo_ensemble_td_open.restype = C.c_void_p
+        L.dzo_ensemble_td_advance.argtypes = [C.c_void_p, C.c_double, C.c_size_t, C.c_int]
+        L.dzo_ensemble_td_read.argtypes = [C.c_void_p, _dp]
+        L.dzo_ensemble_td_close.argtypes = [C.c_void_p]
+        L.dzo_ensemble_td_close.restype = None
+        self._h = L.dzo_ensemble_td_open(*[_p(x) for x in b], _p(st), C.c_size_t(self.B), C.c_size_t(self.n),
+                                         C.c_double(bc[0]), C.c_double(bc[1]))
+
+    def advance(self, dt, steps, threads=1):
+        _chk(lib().dzo_ensemble_td_advance(self._h, float(dt), int(steps), int(threads)))
+
+    def state(self):
+        out = np.empty((self.B, self.n))
+        _chk(lib().dzo_ensemble_td_read(self._h, _p(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().dzo_ensemble_td_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def mesh_ingest_1d(path, height_multiplier=None):
     n = C.c_size_t(0)
     has = 0 if height_multiplier is None else 1
