@@ -62,6 +62,7 @@ SIGNATURES = {
     "dzb_solver_solve": (C.c_int, [C.c_void_p, C.c_double, c_double_p, C.c_size_t]),
     "dzb_solver_solve_device": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_void_p)]),
     "dzb_solver_node_count": (C.c_int, [C.c_void_p, c_size_p]),
+    "dzb_solver_path": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "dzb_solver_bands": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_size_t]),
     "dzb_solver_state": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
     "dzb_solver_destroy": (None, [C.c_void_p]),

@@ -60,7 +60,7 @@ constexpr int BS_SHALLOW_MIN_TILES = 445;     // more tiles than one cooperative
 #define BS_MIN_CTAS 3
 #endif
 
-enum { BS_SRC_BANDS = 0, BS_SRC_ROWS = 1 };   // inputs are (lo, di, up, f) or already (a, c, s, f)
+enum { BS_SRC_BANDS = 0, BS_SRC_ROWS = 1, BS_SRC_NODES = 2 };  // inputs are (lo, di, up, f), already (a, c, s, f), or rows formed on chip from node coordinates (onelaunch_kernels.cuh)
 enum { BS_OPEN_LEFT = 1, BS_OPEN_RIGHT = 2 }; // the system is a block of a longer one: end couplings are kept
 enum { BS_MID_SOLVE = 0, BS_MID_REDUCE = 1, BS_MID_BACKSOLVE = 2 };
 
@@ -360,6 +360,7 @@ struct TileArgs {
   const double* ured;
   double* out;
   int flags;
+  double bc0 = 0.0, bc1 = 0.0;  // BS_SRC_NODES: the Dirichlet values (the bands are never materialised)
 };
 struct ChunkGeom {
   int len;       // rows of the chunk (0: idle thread)
@@ -469,14 +470,17 @@ __device__ __forceinline__ void tile_backward(Pyramid<P1>& pyr, const TileArgs& 
     double o[BS_R];
     // A decoupled end row of the caller's system (a Dirichlet row: lo = up = 0) is returned exactly as Thomas returns it,
     // f / di (matrix_solver/mod.rs:36-39 with a zero coupling); the scaled sweeps would be off by an ulp.
-    const bool fix_first = SRC == BS_SRC_BANDS && g0 == 0 && !(flags & BS_OPEN_LEFT) && k.p2[0] == 0.0;
-    const bool fix_last = SRC == BS_SRC_BANDS && g0 + len == m && !(flags & BS_OPEN_RIGHT) && k.p0[m - 1] == 0.0;
+    // (BS_SRC_NODES: the end rows of a closed end ARE the Dirichlet rows (0, 1, 0, bc), whose Thomas value is bc / 1)
+    const bool fix_first = g0 == 0 && !(flags & BS_OPEN_LEFT) && (SRC == BS_SRC_NODES || (SRC == BS_SRC_BANDS && k.p2[0] == 0.0));
+    const bool fix_last = g0 + len == m && !(flags & BS_OPEN_RIGHT) && (SRC == BS_SRC_NODES || (SRC == BS_SRC_BANDS && k.p0[m - 1] == 0.0));
+    const double v_first = !fix_first ? 0.0 : (SRC == BS_SRC_NODES ? k.bc0 / 1.0 : k.p3[0] / k.p1[0]);
+    const double v_last = !fix_last ? 0.0 : (SRC == BS_SRC_NODES ? k.bc1 / 1.0 : k.p3[m - 1] / k.p1[m - 1]);
     if (vec) {
       o[0] = us, o[BS_R - 1] = ue;
 #pragma unroll
       for (int j = BS_R - 2; j >= 1; --j) o[j] = fma(-C[j], o[j + 1], fma(-A[j], us, F[j])) * S[j];
-      if (fix_first) o[0] = k.p3[0] / k.p1[0];
-      if (fix_last) o[BS_R - 1] = k.p3[m - 1] / k.p1[m - 1];
+      if (fix_first) o[0] = v_first;
+      if (fix_last) o[BS_R - 1] = v_last;
       double2* po = reinterpret_cast<double2*>(out + g0);
 #pragma unroll
       for (int j = 0; j < BS_R / 2; ++j) {
@@ -496,10 +500,10 @@ __device__ __forceinline__ void tile_backward(Pyramid<P1>& pyr, const TileArgs& 
         else if (j < len - 1) nxt = fma(-C[j], nxt, fma(-A[j], us, F[j])) * S[j], o[j] = nxt;
         else o[j] = 0.0;
       }
-      if (fix_first) o[0] = k.p3[0] / k.p1[0];
+      if (fix_first) o[0] = v_first;
 #pragma unroll
       for (int j = 0; j < BS_R; ++j) {
-        if (fix_last && j == len - 1) o[j] = k.p3[m - 1] / k.p1[m - 1];
+        if (fix_last && j == len - 1) o[j] = v_last;
         if (j < len) out[g0 + j] = ACCUM ? out[g0 + j] + o[j] : o[j];
       }
     }

@@ -21,6 +21,7 @@
 #include "gl_quadrature.h"
 #include "mesh2d_kernels.cuh"
 #include "mesh_ingest.h"
+#include "onelaunch_kernels.cuh"
 #include "tridiag_kernels.cuh"
 
 namespace {
@@ -266,6 +267,9 @@ struct dzb_mesh {
   double* d_minmax = nullptr;
   double max_length = 0.0, prom_width = 0.0;
   float translation[3] = {0.f, 0.f, 0.f};
+  // solvers that assemble on the fly from d_nodes (one-launch path): they take a private copy of the coordinates before
+  // these change or go away, so a solver keeps solving the system it was built for, like the reference's owned matrices
+  std::vector<dzb_solver*> dependents;
 };
 
 // ensembles of up to this many bars run the FAITHFUL kernels with a warp per bar (DZB_TW_MAX_BARS: tuning knob)
@@ -313,8 +317,8 @@ struct dzb_solver {
   double *lo = nullptr, *di = nullptr, *up = nullptr, *rhs = nullptr, *c = nullptr, *den = nullptr, *rden = nullptr, *out = nullptr;
   bool parallel = false;       // the partitioned solver is in use (requested and the matrix allows it)
   bool want_parallel = false;  // DZB_SOLVE_PARALLEL requested / chosen by AUTO
-  const dzb_mesh* classified_mesh = nullptr;  // the matrix class (M-matrix / dominant) was decided for this mesh ...
-  unsigned long long classified_version = 0;  // ... at this version of its coordinates (same mesh => same bands => same class)
+  bool classified_valid = false;              // the matrix class (M-matrix / dominant) was decided ...
+  unsigned long long classified_version = 0;  // ... for the coordinates with this process-unique stamp (same coordinates => same bands => same class)
   bool classified_ok = false;
   int refine_steps = 0;
   dzb::BigSys big;
@@ -330,6 +334,18 @@ struct dzb_solver {
   int assembly_mode = 0;
   // time dependent: an ensemble of one bar
   dzb_ensemble* td = nullptr;
+  // one-launch path (closed-form assembly fused into the partitioned solve, onelaunch_kernels.cuh): the bands are only
+  // materialised when somebody asks for them (dzb_solver_bands) or the matrix turns out not to allow the partitioned solver
+  bool fused = false;            // this handle may take the one-launch path
+  bool bands_stale = false;      // lo/di/up/rhs do not describe the coordinates of the last rebuild
+  dzb_mesh* src_mesh = nullptr;  // mesh whose d_nodes x_view points at (nullptr: x_view is the private copy x_own)
+  const double* x_view = nullptr;
+  double* x_own = nullptr;
+  unsigned long long x_version = 0;  // coordinate stamp of x_view, for the matrix-class cache
+  double* ol_red = nullptr;      // 4 x [8 OL_P1M]: the two interface rows of every CTA
+  int* d_cls = nullptr;          // [0] matrix-class bits of the last classifying launch, [1] rows that took the quadrature loop
+  int ol_caps[2] = {-1, -1};
+  int last_path = 0;             // 0 materialised + partitioned / serial, 1 one launch from the node coordinates
 };
 
 namespace {
@@ -354,6 +370,39 @@ void ensemble_free(dzb_ensemble* e) {
   if (e->d_bad) cudaFree(e->d_bad), e->d_bad = nullptr;
   dzb::bigsys_free(&e->big);
   delete e;
+}
+
+// ---- one-launch path: a solver that assembles on the fly reads the mesh's coordinates in place -----------------------
+void solver_detach(dzb_solver* s) {
+  if (!s->src_mesh) return;
+  std::vector<dzb_solver*>& d = s->src_mesh->dependents;
+  d.erase(std::remove(d.begin(), d.end(), s), d.end());
+  s->src_mesh = nullptr;
+}
+void solver_attach(dzb_solver* s, const dzb_mesh* cm) {
+  dzb_mesh* m = const_cast<dzb_mesh*>(cm);
+  if (s->src_mesh != m) {
+    solver_detach(s);
+    m->dependents.push_back(s);
+    s->src_mesh = m;
+  }
+  s->x_view = m->d_nodes, s->x_version = m->version;
+}
+// m's coordinates are about to change or go away: every dependent keeps a private copy of the ones it was built for
+int mesh_release_dependents(dzb_mesh* m) {
+  int rc = DZB_OK;
+  for (dzb_solver* s : m->dependents) {
+    s->src_mesh = nullptr;
+    if (!s->x_own && (rc = dalloc(&s->x_own, s->n))) {
+      s->x_view = nullptr;
+      continue;
+    }
+    if (cudaMemcpyAsync(s->x_own, m->d_nodes, s->n * sizeof(double), cudaMemcpyDeviceToDevice, g_stream) != cudaSuccess)
+      rc = fail(DZB_CUDA, "D2D node coordinates");
+    s->x_view = s->x_own;
+  }
+  m->dependents.clear();
+  return rc;
 }
 
 template <int L>
@@ -710,6 +759,10 @@ int dzb_mesh_set_nodes(dzb_mesh* m, const double* x, size_t n) {
   if (!m || !x) return fail(DZB_INVALID, "null pointer");
   if (n != m->n) return fail(DZB_WRONG_DIMS, "node count");
   if (m->from_obj) return fail(DZB_INVALID, "only meshes made by dzb_mesh_from_nodes can be re-pointed");
+  if (!m->dependents.empty()) {
+    int rc = mesh_release_dependents(m);
+    if (rc) return rc;
+  }
   m->h_stale = true;  // refreshed from the device only if a later call needs host coordinates
   m->version = ++g_mesh_stamp;
   m->max_length = -x[0] + x[n - 1];
@@ -777,6 +830,10 @@ int dzb_mesh_update_gradient_1d(dzb_mesh* m, const double* d_solution, size_t n,
 }
 void dzb_mesh_destroy(dzb_mesh* m) {
   if (!m) return;
+  if (!m->dependents.empty()) {
+    mesh_release_dependents(m);
+    cudaStreamSynchronize(g_stream);
+  }
   dfree(m->d_nodes), dfree(m->d_vertices), dfree(m->d_indices), dfree(m->d_elements), dfree(m->d_vertices_f32), dfree(m->d_minmax);
   delete m;
 }
@@ -936,16 +993,16 @@ static int static_alloc(dzb_solver* s, size_t n) {
   return DZB_OK;
 }
 // Per-matrix work after (re)assembly: pick the solver the matrix allows, then factor for the serial path.
-static int static_factor(dzb_solver* s, const dzb_mesh* m) {
+static int static_factor(dzb_solver* s, unsigned long long version) {
   int rc;
   s->parallel = s->want_parallel;
   if (s->want_parallel) {
     bool ok = false;
-    if (m && s->classified_mesh == m && s->classified_version == m->version) {
+    if (version && s->classified_valid && s->classified_version == version) {
       ok = s->classified_ok;  // re-assembly of unchanged coordinates: identical bands, identical answer
     } else {
       if ((rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok))) return rc;
-      s->classified_mesh = m, s->classified_version = m ? m->version : 0, s->classified_ok = ok;
+      s->classified_valid = version != 0, s->classified_version = version, s->classified_ok = ok;
     }
     if (!ok) s->parallel = false;  // indefinite / convection-dominated system: the reference's serial recurrence
   }
@@ -969,9 +1026,56 @@ static int static_finish(dzb_solver* s, const dzb_options& opt, const dzb_mesh* 
   s->want_parallel = solve_mode == DZB_SOLVE_PARALLEL;
   s->refine_steps = opt.refine_steps >= 0 ? opt.refine_steps : 0;  // 1e-11 of the exact solution at 10^7 rows without any
   (void)n;
-  int rc = static_factor(s, m);
+  int rc = static_factor(s, m ? m->version : 0);
   if (rc) return rc;
   return sync_stream();
+}
+
+// bands of the coordinates the handle currently stands for, and the per-matrix choice of solver that goes with them
+static int static_materialise(dzb_solver* s) {
+  const double* x = s->x_view ? s->x_view : (s->src_mesh ? s->src_mesh->d_nodes : nullptr);
+  if (!x) return fail(DZB_INVALID, "the solver has lost its node coordinates");
+  dzb::AsmParams P{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
+  dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
+  int rc = launch_assembly<dzb::KIND_TI>(x, s->n, 1, s->G, s->assembly_mode, P, o, nullptr);
+  if (rc) return rc;
+  s->bands_stale = false;
+  return static_factor(s, s->x_version);
+}
+// Assemble + solve in one launch straight from the node coordinates.  *done = false: the path does not apply to this
+// system (matrix class, size, no cooperative launch) and the caller goes on with materialised bands.
+static int static_solve_onelaunch(dzb_solver* s, bool* done) {
+  *done = false;
+  const bool known = s->classified_valid && s->classified_version == s->x_version;
+  if (known && !s->classified_ok) return DZB_OK;
+  dzb::OneLaunchArgs a{};
+  int rc = get_rule(s->G, &a.rule);
+  if (rc) return rc;
+  if (a.rule.m <= 0) return DZB_OK;
+  double* r = s->ol_red;
+  constexpr size_t RS = 8 * dzb::OL_P1M;
+  a.k = dzb::TileArgs{s->x_view, nullptr, nullptr, nullptr, (long long)s->n, r, r + RS, r + 2 * RS, r + 3 * RS, nullptr, s->out, 0};
+  a.k.bc0 = s->bc0, a.k.bc1 = s->bc1;
+  a.P = dzb::AsmParams{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
+  a.n_local = (long long)s->n, a.halo_left = 0;
+  a.class_flags = known ? nullptr : s->d_cls;
+  a.bad_rows = reinterpret_cast<unsigned*>(s->d_cls + 1);
+  if (!known) CK(cudaMemsetAsync(s->d_cls, 0, 2 * sizeof(int), g_stream));
+  const int lr = dzb::onelaunch_run<dzb::BS_SRC_NODES, false>(&s->big, a, s->ol_caps, g_stream, &g_launches);
+  if (lr > 0) return fail(DZB_CUDA, dzb::bigsys_error());
+  if (lr < 0) {
+    s->fused = false;
+    return DZB_OK;
+  }
+  if (!known) {  // first solve of these coordinates: is the matrix one the partitioned elimination is reliable on?
+    int f[2] = {0, 0};
+    CK(cudaMemcpyAsync(f, s->d_cls, sizeof f, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    s->classified_valid = true, s->classified_version = s->x_version, s->classified_ok = f[0] != 3;
+    if (!s->classified_ok) return DZB_OK;
+  }
+  *done = true;
+  return DZB_OK;
 }
 
 int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_left, double bc_right, size_t G,
@@ -991,6 +1095,17 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
     rc = launch_assembly<dzb::KIND_TI>(m->d_nodes, s->n, 1, G, opt.assembly_mode, P, o, nullptr);
   }
   if (!rc) rc = static_finish(s, opt, m);
+  // closed-form assembly + partitioned solver on a bar of at least two tiles: from now on one launch per assemble + solve
+  if (!rc && opt.assembly_mode == DZB_ASSEMBLY_FAST && s->want_parallel && s->refine_steps == 0 && s->n >= 2 * (size_t)dzb::BS_TILE &&
+      !std::getenv("DZB_NO_ONELAUNCH")) {
+    rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
+    if (!rc) rc = dalloc(&s->d_cls, 2);
+    if (!rc) {
+      s->fused = true;
+      solver_attach(s, m);
+    }
+  }
+  if (!rc) s->x_version = m->version;
   if (rc) {
     dzb_solver_destroy(s);
     return rc;
@@ -1068,11 +1183,18 @@ int dzb_solver_rebuild(dzb_solver* s, const dzb_mesh* m) {
   if (m->n != s->n) return fail(DZB_WRONG_DIMS, "rebuild needs a mesh with the solver's node count");
   if (s->is_block) return fail(DZB_INVALID, "block solvers are not rebuildable");
   if (s->kind == dzb::KIND_TI) {
+    if (s->fused) {  // nothing to do yet: the rows are formed inside the solve, from these coordinates
+      solver_attach(s, m);
+      s->bands_stale = true;
+      if (!(s->classified_valid && s->classified_version == m->version && !s->classified_ok)) return DZB_OK;
+      return static_materialise(s);  // known not to allow the partitioned solver: bands + serial recurrence
+    }
     dzb::AsmParams P{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
     dzb::AsmOut o{s->lo, s->di, s->up, s->rhs, nullptr, nullptr, nullptr};
     int rc = launch_assembly<dzb::KIND_TI>(m->d_nodes, s->n, 1, s->G, s->assembly_mode, P, o, nullptr);
     if (rc) return rc;
-    return static_factor(s, m);
+    s->x_version = m->version;
+    return static_factor(s, m->version);
   }
   if (s->kind == dzb::KIND_TD) {
     dzb_ensemble* e = s->td;
@@ -1091,6 +1213,21 @@ int dzb_solver_solve_device(dzb_solver* s, double dt, const double** dev) {
     return DZB_OK;
   }
   if (s->is_block) return fail(DZB_INVALID, "a block solver is driven through dzb_solver_block_* (it needs its neighbours)");
+  if (s->fused && s->x_view) {
+    bool done = false;
+    int rc = static_solve_onelaunch(s, &done);
+    if (rc) return rc;
+    if (done) {
+      s->last_path = 1;
+      *dev = s->out;
+      return DZB_OK;
+    }
+  }
+  if (s->bands_stale) {  // the one-launch path did not apply: bands for the current coordinates, then the ordinary solvers
+    int rc = static_materialise(s);
+    if (rc) return rc;
+  }
+  s->last_path = 0;
   if (s->parallel) {
     if (dzb::bigsys_solve(&s->big, s->lo, s->di, s->up, s->rhs, s->out, s->refine_steps, g_stream, &g_launches))
       return fail(DZB_CUDA, dzb::bigsys_error());
@@ -1110,6 +1247,15 @@ int dzb_solver_solve(dzb_solver* s, double dt, double* out_host, size_t n) {
   CK(cudaMemcpyAsync(out_host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   return sync_stream();
 }
+int dzb_solver_path(const dzb_solver* s, char* buf, size_t cap) {
+  if (!s || !buf || cap == 0) return fail(DZB_INVALID, "null pointer");
+  const char* name = "k_thomas_solve_faithful_warp (serial recurrence)";
+  if (s->kind == dzb::KIND_TD) name = "time dependent: see dzb_ensemble_step_kernel";
+  else if (s->last_path == 1) name = "k_tri_onelaunch<NODES> (assembly fused into the partitioned solve)";
+  else if (s->parallel) name = "k_assemble_* + k_tri_* (materialised bands, partitioned solve)";
+  std::snprintf(buf, cap, "%s", name);
+  return DZB_OK;
+}
 int dzb_solver_node_count(const dzb_solver* s, size_t* n) {
   if (!s || !n) return fail(DZB_INVALID, "null pointer");
   *n = s->n;
@@ -1125,6 +1271,10 @@ int dzb_solver_bands(const dzb_solver* s, int which, double* lo, double* di, dou
     else return fail(DZB_INVALID, "which must be 0 (stiffness) or 1 (mass)");
   } else {
     if (which != 0) return fail(DZB_INVALID, "static solvers only have a stiffness matrix");
+    if (s->bands_stale) {  // one-launch path: the bands only exist when somebody asks for them
+      int rc = static_materialise(const_cast<dzb_solver*>(s));
+      if (rc) return rc;
+    }
     dl = s->lo, dd = s->di, du = s->up, dr = s->rhs;
   }
   const size_t bytes = n * sizeof(double);
@@ -1147,7 +1297,9 @@ void dzb_solver_destroy(dzb_solver* s) {
     if (*p) *p -= s->off;
     dfree(*p);
   }
-  for (double** p : {&s->c, &s->den, &s->rden, &s->out, &s->d_top8}) dfree(*p);
+  for (double** p : {&s->c, &s->den, &s->rden, &s->out, &s->d_top8, &s->x_own, &s->ol_red}) dfree(*p);
+  solver_detach(s);
+  if (s->d_cls) cudaFree(s->d_cls), s->d_cls = nullptr;
   dzb::bigsys_free(&s->big);
   ensemble_free(s->td);
   delete s;

@@ -86,6 +86,12 @@ class DiffEquationSolver:
         check(self._lib.dzb_solver_solve_device(self._h, float(time_step), C.byref(p)), self._lib)
         return p.value
 
+    def path(self):
+        """which kernels the last solve ran through"""
+        buf = C.create_string_buffer(128)
+        check(self._lib.dzb_solver_path(self._h, buf, 128), self._lib)
+        return buf.value.decode()
+
     def _bands(self, which, with_rhs):
         lo, di, up = (np.empty(self.n) for _ in range(3))
         rhs = np.empty(self.n) if with_rhs else None

@@ -140,6 +140,8 @@ int dzb_solver_solve(dzb_solver* s, double time_step, double* out_host, size_t n
  * reads back when it draws. */
 int dzb_solver_solve_device(dzb_solver* s, double time_step, const double** device_ptr);
 int dzb_solver_node_count(const dzb_solver* s, size_t* n);
+/* which kernels the last dzb_solver_solve[_device] of this handle ran through (what bench.py prints next to its numbers) */
+int dzb_solver_path(const dzb_solver* s, char* buf, size_t cap);
 /* `stiffness_matrix` / `mass_matrix` / `b_vector` (pub(crate) fields the reference tests index as [[i,j]]):
  * which = 0 -> stiffness (K or S), 1 -> mass (time-dependent only).  lo[i] = A[i][i-1], up[i] = A[i][i+1];
  * rhs may be NULL (and is ignored for the time-dependent solver). */

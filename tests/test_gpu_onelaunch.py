@@ -1,0 +1,138 @@
+"""GPU tests of the one-launch path (onelaunch_kernels.cuh): static diffusion assembled on chip from the node coordinates and
+solved by the partitioned elimination in a single cooperative launch (DZB_ASSEMBLY_FAST + DZB_SOLVE_PARALLEL on bars of at
+least two tiles).  Checked against a __float128 Thomas (oracle) of the bands the same closed form materialises on request,
+against the multi-launch path (DZB_NO_ONELAUNCH=1), and through the handle's life cycle (rebuild, set_nodes, mesh gone).
+The reference's sequence is time_independent.rs:57-71,91-196 (new = assemble, solve = solve_by_thomas)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_NODAL = 1e-10
+ONE = "k_tri_onelaunch"
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope="module")
+def gpu(dz):
+    assert dz.device_count() >= 1, "GPU tests need a CUDA device (there is no CPU fallback)"
+    dz.set_device(0)
+    return dz
+
+
+def jittered(n, seed):
+    rng = np.random.default_rng(seed)
+    return np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, n - 1))]) / n
+
+
+def fast_parallel(gpu):
+    return gpu.make_options(gpu.ASSEMBLY_FAST, gpu.SOLVE_PARALLEL, 0)
+
+
+# two tiles exactly, ragged tails (7 + 2 split, single left-over row), fewer tiles than CTAs, exactly one tile per CTA on a
+# 148-SM part (296), more tiles than CTAs with uneven tile counts per CTA, the (TILE - 1) + 2 split of the last two tiles
+@pytest.mark.parametrize("n", [4096, 4097, 4105, 6000, 2048 * 37 + 1, 2048 * 296, 2048 * 296 + 1, 2048 * 297 + 1234, 1_000_003,
+                               2048 * 1000 + 9, 5_000_001])
+def test_onelaunch_vs_f128_and_multilaunch(gpu, oracle, n):
+    mesh = jittered(n, n)
+    p = gpu.DiffussionParams.time_independent().mu(1.0).b(0.5).boundary_conditions(-2.0, 7.0).build()
+    s = gpu.DiffussionSolverTimeIndependent(p, mesh, 20, fast_parallel(gpu))
+    u = s.solve(0.0)
+    assert ONE in s.path()
+    lo, di, up, rhs = s.bands()                       # materialised on request by k_assemble_fast: the same closed form
+    truth = oracle.thomas(lo, di, up, rhs, kind="f128")
+    assert rel_l2(u, truth) <= TOL_NODAL
+    assert u[0] == -2.0 and u[-1] == 7.0
+    u2 = s.solve(0.0)                                  # again, now that the bands exist: still the one-launch path, same bits
+    assert ONE in s.path() and u2.tobytes() == u.tobytes()
+    os.environ["DZB_NO_ONELAUNCH"] = "1"
+    try:
+        m = gpu.DiffussionSolverTimeIndependent(p, mesh, 20, fast_parallel(gpu))
+        um = m.solve(0.0)
+        assert ONE not in m.path()
+    finally:
+        del os.environ["DZB_NO_ONELAUNCH"]
+    assert rel_l2(u, um) <= 1e-11
+    assert [a.tobytes() for a in m.bands()] == [lo.tobytes(), di.tobytes(), up.tobytes(), rhs.tobytes()]
+
+
+def test_onelaunch_regular_bar_c4_parameters(gpu, oracle):
+    """BASELINE config 4's parameters at a size the __float128 check finishes quickly on"""
+    from dzahui_b200 import synthetic
+    n = 3_000_000
+    mesh = synthetic.regular_bar(n)
+    p = gpu.DiffussionParams.time_independent().mu(1.0).b(1.0).boundary_conditions(1.0, 15.0).build()
+    s = gpu.DiffussionSolverTimeIndependent(p, mesh, 150, gpu.make_options(gpu.ASSEMBLY_FAST, gpu.SOLVE_AUTO))
+    u = s.solve(0.0)
+    assert ONE in s.path()
+    truth = oracle.thomas(*s.bands(), kind="f128")
+    assert rel_l2(u, truth) <= TOL_NODAL
+    assert u[0] == 1.0 and u[-1] == 15.0
+
+
+def test_onelaunch_handle_life_cycle(gpu, oracle):
+    """rebuild re-points the handle without launching anything; set_nodes / destroying the mesh leaves the handle solving
+    the system it was last built for (the reference's solver owns its matrices)"""
+    n = 300_007
+    x0, x1 = jittered(n, 1), jittered(n, 2)
+    p = gpu.DiffussionParams.time_independent().mu(2.0).b(0.5).boundary_conditions(-1.0, 3.0).build()
+
+    def want(x):
+        q = gpu.DiffussionSolverTimeIndependent(p, x, 150, fast_parallel(gpu))
+        return oracle.thomas(*q.bands(), kind="f128")
+
+    w0, w1 = want(x0), want(x1)
+    m = gpu.Mesh.from_nodes(x0)
+    s = gpu.DiffussionSolverTimeIndependent(p, m, 150, fast_parallel(gpu))
+    assert rel_l2(s.solve(0.0), w0) <= TOL_NODAL and ONE in s.path()
+    m.set_nodes(x1)                                   # the handle was built for x0 and keeps solving x0 ...
+    assert rel_l2(s.solve(0.0), w0) <= TOL_NODAL and ONE in s.path()
+    s.rebuild(m)                                      # ... until it is rebuilt
+    gpu.launch_count(reset=True)
+    s.rebuild(m)
+    assert gpu.launch_count() == 0                    # assembly is part of the solve launch
+    assert rel_l2(s.solve(0.0), w1) <= TOL_NODAL and ONE in s.path()
+    lo, di, up, rhs = s.bands()
+    assert rel_l2(s.solve(0.0), oracle.thomas(lo, di, up, rhs, kind="f128")) <= TOL_NODAL
+    m.close()                                         # the mesh goes away: the handle keeps its own copy of the coordinates
+    assert rel_l2(s.solve(0.0), w1) <= TOL_NODAL and ONE in s.path()
+    s.close()
+
+
+def test_onelaunch_refuses_what_the_partitioned_solver_must_not_touch(gpu, oracle):
+    """a strongly irregular mesh makes the reference's kink-straddling quadrature produce an indefinite K: the in-kernel
+    classification sends the handle to materialised bands + the serial recurrence, like the multi-launch path"""
+    n = 20_000
+    rng = np.random.default_rng(5)
+    mesh = np.concatenate([[0.0], np.cumsum(rng.uniform(0.01, 3.0, n - 1))]) / n
+    p = gpu.DiffussionParams.time_independent().mu(1.0).b(1.0).boundary_conditions(1.0, 15.0).build()
+    good = jittered(n, 3)
+    m = gpu.Mesh.from_nodes(good)
+    s = gpu.DiffussionSolverTimeIndependent(p, m, 150, fast_parallel(gpu))
+    s.solve(0.0)
+    assert ONE in s.path()
+    m.set_nodes(mesh)
+    s.rebuild(m)
+    u = s.solve(0.0)
+    assert ONE not in s.path()
+    lo, di, up, rhs = s.bands()
+    assert rel_l2(u, oracle.thomas(lo, di, up, rhs)) <= TOL_NODAL
+    # degenerate spacing (elements of a few ulps): rows the closed form does not cover are formed by the quadrature loop
+    # inside the kernel exactly as k_assemble_fixup forms them for the multi-launch path
+    bad = jittered(n, 4)
+    bad[5000] = np.nextafter(bad[4999], 1.0)
+    bad[12000] = bad[12001]
+    m.set_nodes(bad)
+    s.rebuild(m)
+    u = s.solve(0.0)
+    lo, di, up, rhs = s.bands()
+    ref = oracle.thomas(lo, di, up, rhs)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(u), ok)
+    if ok.all():
+        assert rel_l2(u, ref) <= 1e-8

@@ -1,4 +1,6 @@
-"""Times the partitioned tridiagonal solve of one long bar at several sizes (device-resident, CUDA events).
+"""Times one long bar at several sizes (device-resident, CUDA events): with the default build the closed-form assembly is
+fused into the partitioned solve (one launch per assemble + solve, onelaunch_kernels.cuh); DZB_NO_ONELAUNCH=1 times the
+partitioned solve of materialised bands alone (bigsys_kernels.cuh).
 Usage: python tools/time_long_solve.py [n ...]   (tuning aid; not part of the test suite)"""
 import os, sys, json, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,7 +26,7 @@ def main():
             s.solve_device(0.0)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        out[n] = {"ms": ms, "ns_per_row": ms * 1e6 / n, "GBps_40B": 40.0 * n / ms / 1e6}
+        out[n] = {"ms": ms, "ns_per_row": ms * 1e6 / n, "GBps_40B": 40.0 * n / ms / 1e6, "GBps_80B": 80.0 * n / ms / 1e6, "path": s.path()}
     print(json.dumps(out))
 
 if __name__ == "__main__":
