@@ -25,8 +25,13 @@ struct RuleView {      // device pointers into one allocation, see gl_quadrature
   int m;               // G - 1
   double t0, t1p, t1m, q;
   const unsigned short* guess;  // [GUESS_BINS + 1]: guess[k] = #{j : x_j >= -1 + 2 k / GUESS_BINS}, a bracket for the kink split
+  // static diffusion, lean closed form (ti_elem / ti_row below)
+  const double4* uv;             // [m + 1]: (u0, u1, v0, v1)[s], one 32-byte entry per split position
+  const unsigned short* guessf;  // [GUESS_BINS + 2]: guess[k] with bit 15 set when a node lies within GUESS_TOL of bin k - 1
+  double kv;                     // element validity factor: h * kv > max(|xa|, |xb|) puts every node image inside the element
 };
 constexpr int GUESS_BINS = 1024;
+constexpr double GUESS_TOL = 0x1p-16;  // what separates a node from the kink for the table alone to decide the split
 
 // ---- the reference's basis pieces, restated -----------------------------------------------------------------
 // FirstDegreePolynomial (polynomials_1d.rs:16-19): evaluate = coefficient*x + independent_term (two roundings).
@@ -84,6 +89,17 @@ __device__ __forceinline__ Hat make_hat(const double* __restrict__ mesh, long lo
 }
 
 enum { KIND_TI = 0, KIND_TD = 1, KIND_STOKES = 2 };
+
+// 1/x by the hardware seed (MUFU.RCP64H, ~2^-23) and two Newton steps: no special cases and therefore no branch.
+// Within an ulp of the correctly rounded value for normal x whose reciprocal is normal; garbage (inf / nan) otherwise.
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 
 struct AsmParams {
   double mu, b;          // diffusion
@@ -407,6 +423,87 @@ __device__ __forceinline__ bool fast_row(const double* __restrict__ mesh, long l
   return true;
 }
 
+// ---- static diffusion, lean closed form ---------------------------------------------------------------------------------
+// The same sums as fast_row<KIND_TI>, arranged per ELEMENT so that a thread owning consecutive rows (the fused assemble +
+// solve kernel, onelaunch_kernels.cuh) forms every element quantity once, and with the two expensive parts of fast_row
+// replaced by cheap sufficient tests:
+//   * validity.  fast_row_ok evaluates the reference's own predicate at the two extreme nodes of all three maps (24 fp64
+//     operations per row).  Here an element [xa, xb] passes when  h kv > M,  M = max(|xa|, |xb|),  2^-899 < h,  M < 2^1000,
+//     with kv = min(delta 2^49, 2^30) and delta = min(1 - x_first, 1 + x_last) the distance of the rule's extreme nodes from
+//     +-1.  Proof sketch: from_m1_p1 gives cm = h/2 exactly and mm = (xa + xb)(1 + e)/2, so the computed image
+//     fl(fl(cm x) + mm) is within 6 u M of mid + half x (u = 2^-53, |x| <= 1); the exact images of the extreme nodes are
+//     half delta inside the element, and h kv > M makes half delta > 6 u M (16 u M / delta < h).  The two-element map of
+//     the diagonal integral has H >= h and M' <= max(M1, M2), so it passes when both elements do.  The range conditions keep
+//     every intermediate normal.  Elements that fail are NOT necessarily bad: their rows simply take the quadrature loop.
+//   * the kink split.  The table over x* = (h1 - h2) / H answers alone unless a node lies within GUESS_TOL of the bin
+//     (bit 15 of guessf): h > 2^-30 M bounds the predicate's rounding to 1.4e-6 in x*, the float arithmetic adds 3e-7.
+//     Flagged bins settle the split with the reference's own predicate, as fast_row does.
+// Reciprocals: rcp_newton (branch-free).  Materialised bands (k_assemble_fast<KIND_TI>) and rows formed on chip use these
+// very functions, so they agree bit for bit.
+struct TiK {  // per (rule, parameters)
+  double mu, b, K0, bhp, bhn, kv;
+};
+__device__ __forceinline__ TiK make_tik(const RuleView& R, const AsmParams& P) {
+  return {P.mu, P.b, -0.5 * R.t0, P.b * (-0.25 * R.t1p), P.b * (0.25 * R.t1m), R.kv};
+}
+struct TiElem {
+  double h, r, r2, k0r;  // length, 1/h, 1/h^2, K0/h
+  bool ok;
+};
+__device__ __forceinline__ TiElem ti_elem(double xa, double xb, const TiK& K) {
+  TiElem e;
+  e.h = xb - xa;
+  e.r = rcp_newton(e.h);
+  e.r2 = e.r * e.r, e.k0r = K.K0 * e.r;
+  const double M = fmax(fabs(xa), fabs(xb));
+  e.ok = (e.h * K.kv > M) && (M < 0x1p1000) && (e.h > 0x1p-899);
+  return e;
+}
+// flagged bin: the reference's predicate decides (kept out of line: the callers unroll eight rows)
+__device__ __noinline__ int ti_split_probe(double xa, double xc, double xe, int s, const double* qx, int m) {
+  const Affine ts = from_m1_p1(xa, xe);
+  while (s < m && !(ts(qx[s]) < xc)) ++s;
+  while (s > 0 && (ts(qx[s - 1]) < xc)) --s;
+  return s;
+}
+// interior row between elements L = [xa, xc] and Rr = [xc, xe], both ok
+__device__ __forceinline__ void ti_row(const TiElem& L, const TiElem& Rr, double xa, double xc, double xe, const TiK& K,
+                                       const double4* __restrict__ uv, const unsigned short* __restrict__ guessf,
+                                       const double* qx, int m, double& lo, double& di, double& up, bool live = true) {
+  // live == false: the caller forms this row unconditionally (straight-line code) but will discard it: never probe for it
+  const double H = xe - xa;
+  const float xs = __fdividef((float)(L.h - Rr.h), (float)H);
+  int bin = (int)((xs + 1.0f) * (0.5f * GUESS_BINS));
+  bin = max(0, min(GUESS_BINS - 1, bin));
+  int s = guessf[bin + 1];
+  if ((s & 0x8000) && live) s = ti_split_probe(xa, xc, xe, s & 0x7fff, qx, m);
+  s &= 0x7fff;
+  const double4 t = uv[s];  // (U0, U1, V0, V1)
+  const double prime_sq = (0.5 * H) * fma(t.x, L.r2, t.z * Rr.r2);
+  const double half_sq = (0.25 * H * H) * fma(t.y, L.r2, -t.w * Rr.r2);
+  lo = fma(K.mu, L.k0r, K.bhp);
+  di = fma(K.mu, prime_sq, K.b * half_sq);
+  up = fma(K.mu, Rr.k0r, K.bhn);
+}
+// whether interior row i takes the closed form: both elements pass, outer neighbours not out of order
+__device__ __forceinline__ bool ti_row_ok(const double* __restrict__ mesh, long long n, long long i, const TiElem& L, const TiElem& Rr,
+                                          double xa, double xe) {
+  bool ok = L.ok && Rr.ok;
+  if (i >= 2) ok = ok && !(xa < mesh[i - 2]);
+  if (i + 2 < n) ok = ok && !(mesh[i + 2] < xe);
+  return ok;
+}
+__device__ __forceinline__ bool fast_row_ti(const double* __restrict__ mesh, long long n, long long i, const RuleView& R,
+                                            const double* qx, const TiK& K, double out[7]) {
+  if (R.m <= 0) return false;
+  const double xa = mesh[i - 1], xc = mesh[i], xe = mesh[i + 1];
+  const TiElem L = ti_elem(xa, xc, K), Rr = ti_elem(xc, xe, K);
+  if (!ti_row_ok(mesh, n, i, L, Rr, xa, xe)) return false;
+  ti_row(L, Rr, xa, xc, xe, K, R.uv, R.guessf, qx, R.m, out[0], out[1], out[2]);
+  out[3] = 0.0, out[4] = out[5] = out[6] = 0.0;
+  return true;
+}
+
 // One thread per row, grid-stride; x table (and nothing else) staged in shared memory for the probes.  Rows the closed
 // form does not cover are counted in *bad and left to k_assemble_fixup, which keeps the quadrature-loop code (and its
 // local-memory frame) out of this kernel.
@@ -422,6 +519,7 @@ __global__ void __launch_bounds__(256) k_assemble_fast(const double* __restrict_
     qx = s_rule;
   }
   const long long total = n * n_bars;
+  const TiK K = make_tik(rule, P);
   unsigned nbad = 0;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
     long long bar, i;
@@ -429,7 +527,7 @@ __global__ void __launch_bounds__(256) k_assemble_fast(const double* __restrict_
     double v[7];
     if (i == 0 || i == n - 1)
       boundary_row<KIND>(i == 0, P, v);
-    else if (!fast_row<KIND>(mesh + bar * n, n, i, rule, qx, P, v)) {
+    else if (!(KIND == KIND_TI ? fast_row_ti(mesh + bar * n, n, i, rule, qx, K, v) : fast_row<KIND>(mesh + bar * n, n, i, rule, qx, P, v))) {
       ++nbad;
       continue;
     }
@@ -445,13 +543,17 @@ __global__ void __launch_bounds__(128) k_assemble_fixup(const double* __restrict
                                                         const unsigned* __restrict__ bad) {
   if (*bad == 0) return;
   const int m = rule.m;
+  const TiK K = make_tik(rule, P);
   const long long total = n * n_bars;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
     long long bar, i;
     split_index(g, n, n_bars, &bar, &i);
     if (i == 0 || i == n - 1) continue;
     const double* bm = mesh + bar * n;
-    if (m > 0 && fast_row_ok(bm, n, i, rule.x[0], rule.x[m - 1], m)) continue;
+    if (KIND == KIND_TI) {
+      const double xa = bm[i - 1], xc = bm[i], xe = bm[i + 1];
+      if (m > 0 && ti_row_ok(bm, n, i, ti_elem(xa, xc, K), ti_elem(xc, xe, K), xa, xe)) continue;
+    } else if (m > 0 && fast_row_ok(bm, n, i, rule.x[0], rule.x[m - 1], m)) continue;
     double v[7];
     faithful_row<KIND>(bm, n, i, rule.x, rule.w, m, P, nullptr, 0, v);
     store_row<KIND>(o, g, v);

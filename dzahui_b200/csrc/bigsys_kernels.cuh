@@ -120,13 +120,26 @@ __device__ __forceinline__ int row_slot(int r, int rows, int P) {
 
 // One chunk (thread t) of a shared-memory level with row stride P, reduced rows -> next level (row stride PN; PN == 0: the
 // next level is the final 2-row system stored at index 0/1).
-template <bool FULL, bool KEEP>  // FULL: len == 8, loops unrolled.  KEEP: leave (alpha~, g~, 1/P, delta~) for level_backsolve
+// PRE: the chunk's rows are all read before the sweep starts.  With KEEP every row-step ends in stores into the very arrays
+// the next step reads, and when the row stride is a runtime value the compiler cannot tell them apart: each step's loads then
+// wait for the previous step's stores, reciprocal included (~125 instead of ~25 cycles per step).  Costs 64 registers.
+template <bool FULL, bool KEEP, bool PRE = false>  // FULL: len == 8, loops unrolled.  KEEP: leave (alpha~, g~, 1/P, delta~) for level_backsolve
 __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int len, const LevelPtr& nx, int PN, int t) {
   const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
+  double ra[BS_R], rc[BS_R], rs[BS_R], rd[BS_R];
+  if (PRE) {
+#pragma unroll
+    for (int j = 0; j < BS_R; ++j) {
+      const bool in = FULL || j < len;
+      const int q = j * P + t;
+      ra[j] = in ? lv.a[q] : 0.0, rc[j] = in ? lv.c[q] : 0.0, rs[j] = in ? lv.s[q] : 1.0, rd[j] = in ? lv.d[q] : 0.0;
+    }
+  }
   int idx = P + t;
-  double alp = lv.a[idx], sig = lv.s[idx], dlt = lv.d[idx], g = lv.c[idx];
+  double alp = PRE ? ra[1] : lv.a[idx], sig = PRE ? rs[1] : lv.s[idx], dlt = PRE ? rd[1] : lv.d[idx], g = PRE ? rc[1] : lv.c[idx];
   const double sc = (FULL || len >= 3) ? pow2_inv((sig - alp) - g) : 1.0;
-  const double A0 = lv.a[t] * sc, C0 = lv.c[t] * sc, S0 = lv.s[t] * sc, F0 = lv.d[t] * sc;
+  const double A0 = (PRE ? ra[0] : lv.a[t]) * sc, C0 = (PRE ? rc[0] : lv.c[t]) * sc, S0 = (PRE ? rs[0] : lv.s[t]) * sc,
+               F0 = (PRE ? rd[0] : lv.d[t]) * sc;
   alp *= sc, sig *= sc, dlt *= sc, g *= sc;
   double s_c = C0, s_s = S0, s_f = F0;  // s-row (its a stays A0)
   double rn = 1.0;                      // normalisation of the e-row
@@ -143,12 +156,12 @@ __device__ __forceinline__ void level_reduce_impl(const LevelPtr& lv, int P, int
       if (FULL || j < len) {
         idx += P;
         // the chunk's power-of-two scale rides on P_{j-1} (exact), so only A_j needs its own scaling
-        const double Ps = Pm * sc, nA = -(lv.a[idx] * sc), Cr = lv.c[idx], Sr = lv.s[idx];
+        const double Ps = Pm * sc, nA = -((PRE ? ra[j] : lv.a[idx]) * sc), Cr = PRE ? rc[j] : lv.c[idx], Sr = PRE ? rs[j] : lv.s[idx];
         const double q = nA * D;
         const double Pn = fma(Sr - Cr, Ps, q);  // P_j by its own two-term recurrence (see chunk0_forward)
         D = fma(Sr, Ps, q);
         sig = fma(Sr, Ps, nA * sig);
-        dlt = fma(lv.d[idx], Ps, nA * dlt);
+        dlt = fma(PRE ? rd[j] : lv.d[idx], Ps, nA * dlt);
         alp = nA * alp;
         g = Cr * Ps;
         if (FULL ? j < BS_R - 1 : j < len - 1) {
@@ -193,6 +206,34 @@ __device__ __forceinline__ void level_backsolve(const LevelPtr& lv, int P, int l
       const int idx = j * P + t;
       nxt = fma(-lv.c[idx], nxt, fma(-lv.a[idx], us, lv.d[idx])) * lv.s[idx];
       lv.d[idx] = nxt;
+    }
+  }
+}
+
+// Out-of-line copies of the two level routines for pyramids that run once per launch (the per-CTA and the middle system of
+// the one-launch kernel): the unrolled per-level instantiations reduce_to / backsolve_from make of them are ~7000 instructions
+// of code executed once, and fetching that cost more than executing it (measured: 19 us for the 592-row middle solve).
+__device__ __noinline__ void level_reduce_cold(LevelPtr lv, int P, int len, LevelPtr nx, int PN, int t) {
+  level_reduce_impl<false, true, true>(lv, P, len, nx, PN, t);
+}
+__device__ __noinline__ void level_backsolve_cold(LevelPtr lv, int P, int len, LevelPtr nx, int PN, int t) {
+  const int p0 = PN ? lvl_pos(2 * t, PN) : 0, p1 = PN ? lvl_pos(2 * t + 1, PN) : 1;
+  const double us = nx.d[p0], ue = nx.d[p1];
+  double a[BS_R], c[BS_R], d[BS_R], r[BS_R];  // every multiplier before the first store (see level_reduce_impl, PRE)
+#pragma unroll
+  for (int j = 1; j < BS_R - 1; ++j) {
+    const bool in = j < len - 1;
+    const int q = j * P + t;
+    a[j] = in ? lv.a[q] : 0.0, c[j] = in ? lv.c[q] : 0.0, d[j] = in ? lv.d[q] : 0.0, r[j] = in ? lv.s[q] : 0.0;
+  }
+  lv.d[t] = us;
+  lv.d[(len - 1) * P + t] = ue;
+  double nxt = ue;
+#pragma unroll
+  for (int j = BS_R - 2; j >= 1; --j) {
+    if (j < len - 1) {
+      nxt = fma(-c[j], nxt, fma(-a[j], us, d[j])) * r[j];
+      lv.d[j * P + t] = nxt;
     }
   }
 }
@@ -269,6 +310,33 @@ struct Pyramid {
     sync();
   }
   __device__ __forceinline__ void backsolve(int t, int rows1) { backsolve_from<0>(t, rows1); }
+  // reduce / backsolve with ONE copy of the level code and a runtime loop over the levels (see level_reduce_cold)
+  __device__ __forceinline__ void reduce_cold(int t, int rows1) {
+    int off = 0, rows = rows1;
+#pragma unroll 1
+    for (int p = P1;; p = (p + 3) / 4) {
+      sync();
+      const int len = chunk_len(rows, t);
+      if (len > 0) level_reduce_cold(level(off), lvl_stride(p), len, level(off + 8 * lvl_stride(p)), p == 1 ? 0 : lvl_stride((p + 3) / 4), t);
+      off += 8 * lvl_stride(p);
+      rows = 2 * ((rows + BS_R - 1) / BS_R);
+      if (p == 1) break;
+    }
+    sync();
+  }
+  __device__ __forceinline__ void backsolve_cold(int t, int rows1) {
+    int nl = 1;
+    for (int p = P1; p != 1; p = (p + 3) / 4) ++nl;
+#pragma unroll 1
+    for (int k = nl - 1; k >= 0; --k) {
+      int p = P1, off = 0, rows = rows1;  // geometry of level k
+      for (int q = 0; q < k; ++q) off += 8 * lvl_stride(p), rows = 2 * ((rows + BS_R - 1) / BS_R), p = (p + 3) / 4;
+      sync();
+      const int len = chunk_len(rows, t);
+      if (len > 0) level_backsolve_cold(level(off), lvl_stride(p), len, level(off + 8 * lvl_stride(p)), p == 1 ? 0 : lvl_stride((p + 3) / 4), t);
+    }
+    sync();
+  }
 };
 // rows a tile holding rows1 level-1 rows leaves after NLEV level reductions (NLEV == 0: all of them)
 __host__ __device__ constexpr int bs_rows_left_of(int rows1, int P1, int NLEV) {
@@ -293,9 +361,10 @@ __host__ __device__ constexpr int bs_rows_left(int P1, int NLEV) {
 
 // Level 0: the forward sweep over a chunk held in registers; KEEP stores (alpha~_j, g~_j, 1/P_j, delta~_j) over
 // (A, C, S, F)[1..len-2] for the back-substitution.  FULL: len == 8.
+// chunk0_sweep leaves the chunk's two reduced rows in o = (a, c, s, f) of the s-row, then of the e-row.
 template <bool KEEP, bool FULL>
-__device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R],
-                                               int len, const LevelPtr& l1, int i0, int i1) {
+__device__ __forceinline__ void chunk0_sweep(double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R], int len,
+                                             double (&o)[8]) {
   double alp = A[1], sig = S[1], dlt = F[1], g = C[1];
   const double sc = (FULL || len >= 3) ? pow2_inv((sig - alp) - g) : 1.0;
   const double A0 = A[0] * sc, C0 = C[0] * sc, S0 = S[0] * sc, F0 = F[0] * sc;
@@ -340,8 +409,34 @@ __device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS
     s_c = G * lastC * rP;
     rn = rP;
   }
-  l1.a[i0] = A0, l1.c[i0] = s_c, l1.s[i0] = s_s, l1.d[i0] = s_f;
-  l1.a[i1] = alp * rn, l1.c[i1] = g * rn, l1.s[i1] = sig * rn, l1.d[i1] = dlt * rn;
+  o[0] = A0, o[1] = s_c, o[2] = s_s, o[3] = s_f;
+  o[4] = alp * rn, o[5] = g * rn, o[6] = sig * rn, o[7] = dlt * rn;
+}
+template <bool KEEP, bool FULL>
+__device__ __forceinline__ void chunk0_forward(double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R],
+                                               int len, const LevelPtr& l1, int i0, int i1) {
+  double o[8];
+  chunk0_sweep<KEEP, FULL>(A, C, S, F, len, o);
+  l1.a[i0] = o[0], l1.c[i0] = o[1], l1.s[i0] = o[2], l1.d[i0] = o[3];
+  l1.a[i1] = o[4], l1.c[i1] = o[5], l1.s[i1] = o[6], l1.d[i1] = o[7];
+}
+// Back-substitution of a chunk whose sweep kept its multipliers: u of its first / last row known, u of all its rows out.
+__device__ __forceinline__ void chunk0_backward(const double (&A)[BS_R], const double (&C)[BS_R], const double (&S)[BS_R],
+                                                const double (&F)[BS_R], int len, double us, double ue, double (&o)[BS_R]) {
+  if (len == BS_R) {
+    o[0] = us, o[BS_R - 1] = ue;
+#pragma unroll
+    for (int j = BS_R - 2; j >= 1; --j) o[j] = fma(-C[j], o[j + 1], fma(-A[j], us, F[j])) * S[j];
+  } else {
+    double nxt = ue;
+#pragma unroll
+    for (int j = BS_R - 1; j >= 0; --j) {
+      if (j == len - 1) o[j] = ue;
+      else if (j == 0) o[j] = us;
+      else if (j < len - 1) nxt = fma(-C[j], nxt, fma(-A[j], us, F[j])) * S[j], o[j] = nxt;
+      else o[j] = 0.0;
+    }
+  }
 }
 
 // ---- tile kernels -------------------------------------------------------------------------------------------------
@@ -611,6 +706,9 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_tile_tma(const __grid_con
   if (t == 0) mbar_init(&sm.mbar, 1);
   __syncthreads();
   auto request = [&](long long tile) {  // thread 0: stage the four 16 KB boxes of a full tile
+    // the stage was just read with ordinary loads (ordered before this point by the CTA barrier) and is about to be written by
+    // the async proxy: the issuing thread fences the two proxies (see onelaunch_kernels.cuh, request_x, for what happens without)
+    asm volatile("fence.proxy.async;" ::: "memory");
     mbar_arrive_expect_tx(&sm.mbar, BS_STAGE_BYTES);
     const int row = (int)(tile * BS_TMA_BOX);
     tma_load_box(sm.rows[0], &map0, row, &sm.mbar);

@@ -70,6 +70,7 @@ inline unsigned blocks_for(long long work, int threads) { return (unsigned)((wor
 struct DeviceRule {
   double* buf = nullptr;
   unsigned short* guess = nullptr;
+  double4* uv = nullptr;
   dzb::RuleView view{};
 };
 std::map<std::pair<int, size_t>, DeviceRule> g_rules;
@@ -118,6 +119,27 @@ int get_rule(size_t G, dzb::RuleView* out) {
     CK(cudaMemcpyAsync(d.guess, gt.data(), gt.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, g_stream));
     CK(cudaStreamSynchronize(g_stream));
     d.view.guess = d.guess;
+    // static diffusion, lean closed form (assembly_kernels.cuh, ti_row): the same table with bit 15 set where a node lies
+    // within GUESS_TOL of the bin, the four moments the row needs packed per split position, the element validity factor
+    std::vector<unsigned short> gf(dzb::GUESS_BINS + 2, 0);
+    for (int k = 0; k < dzb::GUESS_BINS; ++k) {
+      const double lo_edge = -1.0 + 2.0 * (double)k / (double)dzb::GUESS_BINS - dzb::GUESS_TOL;
+      const double hi_edge = -1.0 + 2.0 * (double)(k + 1) / (double)dzb::GUESS_BINS + dzb::GUESS_TOL;
+      bool near = m > 32767;  // the count must leave bit 15 free: larger rules always probe
+      for (size_t j = 0; j < m && !near; ++j) near = r.x[j] >= lo_edge && r.x[j] <= hi_edge;
+      gf[(size_t)k + 1] = (unsigned short)((gt[(size_t)k + 1] & 0x7fff) | (near ? 0x8000 : 0));
+    }
+    unsigned short* d_gf = nullptr;
+    CK(cudaMalloc((void**)&d_gf, gf.size() * sizeof(unsigned short)));
+    CK(cudaMemcpyAsync(d_gf, gf.data(), gf.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, g_stream));
+    std::vector<double4> uv(m + 1);
+    for (size_t j = 0; j <= m; ++j) uv[j] = make_double4(r.u0[j], r.u1[j], r.v0[j], r.v1[j]);
+    CK(cudaMalloc((void**)&d.uv, uv.size() * sizeof(double4)));
+    CK(cudaMemcpyAsync(d.uv, uv.data(), uv.size() * sizeof(double4), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    d.view.guessf = d_gf, d.view.uv = d.uv;
+    const double delta = m ? std::min(1.0 - r.x[0], 1.0 + r.x[m - 1]) : 0.0;
+    d.view.kv = delta > 0.0 ? std::min(delta * 0x1p49, 0x1p30) : 0.0;
   }
   g_rules[{dev, G}] = d;
   *out = d.view;
@@ -343,7 +365,11 @@ struct dzb_solver {
   double* x_own = nullptr;
   unsigned long long x_version = 0;  // coordinate stamp of x_view, for the matrix-class cache
   double* ol_red = nullptr;      // 4 x [8 OL_P1M]: the two interface rows of every CTA
-  int* d_cls = nullptr;          // [0] matrix-class bits of the last classifying launch, [1] rows that took the quadrature loop
+  double *ol_r = nullptr, *ol_s = nullptr;  // [n] each: what pass 1 leaves per row for pass 2 (1/h, row-sum excess)
+  double* ol_pool = nullptr;               // levels B and C of the one-launch kernel: 4 + 1 arrays each (rows and their solutions)
+  bool fused_bad_valid = false;            // the coordinates stamped fused_bad_version hold a row outside the closed form:
+  unsigned long long fused_bad_version = 0;  // materialised bands (with the quadrature loop on such rows) for them
+  int* d_cls = nullptr;          // [0] matrix-class bits of the last classifying launch, [1] != 0: a row outside the closed form
   int ol_caps[2] = {-1, -1};
   int last_path = 0;             // 0 materialised + partitioned / serial, 1 one launch from the node coordinates
 };
@@ -1048,6 +1074,7 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done) {
   *done = false;
   const bool known = s->classified_valid && s->classified_version == s->x_version;
   if (known && !s->classified_ok) return DZB_OK;
+  if (s->fused_bad_valid && s->fused_bad_version == s->x_version) return DZB_OK;
   dzb::OneLaunchArgs a{};
   int rc = get_rule(s->G, &a.rule);
   if (rc) return rc;
@@ -1058,19 +1085,71 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done) {
   a.k.bc0 = s->bc0, a.k.bc1 = s->bc1;
   a.P = dzb::AsmParams{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
   a.n_local = (long long)s->n, a.halo_left = 0;
+  a.r_el = s->ol_r, a.s_ex = s->ol_s;
+  {
+    const size_t rb = dzb::onelaunch_rows_b(s->n), rc = dzb::onelaunch_rows_c(s->n);
+    double* q = s->ol_pool;
+    for (int i = 0; i < 4; ++i) a.gb[i] = q, q += rb;
+    a.ub = q, q += rb;
+    for (int i = 0; i < 4; ++i) a.gc[i] = q, q += rc;
+    a.uc = q;
+  }
+  static const bool trace_on = std::getenv("DZB_OL_TRACE") != nullptr;  // tuning aid: phase timeline of every CTA to stderr
+  static unsigned long long* d_trace = nullptr;
+  if (trace_on && !d_trace) CK(cudaMalloc((void**)&d_trace, 8 * 1024 * sizeof(unsigned long long)));
+  a.trace = trace_on ? d_trace : nullptr;
   a.class_flags = known ? nullptr : s->d_cls;
-  a.bad_rows = reinterpret_cast<unsigned*>(s->d_cls + 1);
   if (!known) CK(cudaMemsetAsync(s->d_cls, 0, 2 * sizeof(int), g_stream));
-  const int lr = dzb::onelaunch_run<dzb::BS_SRC_NODES, false>(&s->big, a, s->ol_caps, g_stream, &g_launches);
+  int ol_grid = 0;
+  const int lr = dzb::onelaunch_run(&s->big, a, s->ol_caps, g_stream, &g_launches, &ol_grid);
   if (lr > 0) return fail(DZB_CUDA, dzb::bigsys_error());
   if (lr < 0) {
     s->fused = false;
     return DZB_OK;
   }
+  if (trace_on) {
+    std::vector<unsigned long long> h(8 * 1024);
+    CK(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    const int ctas = std::max(1, std::min(1024, ol_grid));
+    unsigned long long t0 = ~0ULL;
+    for (int c = 0; c < ctas; ++c) t0 = std::min(t0, h[8 * c]);
+    if (const char* path = std::getenv("DZB_OL_RED_FILE")) {  // the middle system (2 rows per CTA), appended per solve
+      constexpr size_t RS = 8 * dzb::OL_P1M;
+      std::vector<double> red(4 * RS);
+      CK(cudaMemcpy(red.data(), s->ol_red, red.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      if (FILE* f = std::fopen(path, "a")) {
+        for (int r = 0; r < 2 * ctas; ++r) std::fprintf(f, "%.17g %.17g %.17g %.17g\n", red[r], red[RS + r], red[2 * RS + r], red[3 * RS + r]);
+        std::fclose(f);
+      }
+    }
+    if (const char* path = std::getenv("DZB_OL_TRACE_FILE")) {  // one line per CTA: the six stamps in microseconds
+      if (FILE* f = std::fopen(path, "w")) {
+        for (int c = 0; c < ctas; ++c) {
+          for (int k = 0; k < 6; ++k) std::fprintf(f, "%.3f ", (double)(h[8 * c + k] - t0) * 1e-3);
+          std::fprintf(f, "\n");
+        }
+        std::fclose(f);
+      }
+    }
+    const char* names[] = {"start", "pass1 end", "cta level reduced", "after grid sync", "middle solved", "pass2 end", "middle rows loaded", "middle reduced"};
+    for (int k = 0; k < 8; ++k) {
+      double lo = 1e30, hi = 0, sum = 0;
+      for (int c = 0; c < ctas; ++c) {
+        const double v = (double)(h[8 * c + k] - t0) * 1e-3;
+        lo = std::min(lo, v), hi = std::max(hi, v), sum += v;
+      }
+      std::fprintf(stderr, "[ol trace] %-18s min %8.2f avg %8.2f max %8.2f us (%d CTAs)\n", names[k], lo, sum / ctas, hi, ctas);
+    }
+  }
   if (!known) {  // first solve of these coordinates: is the matrix one the partitioned elimination is reliable on?
     int f[2] = {0, 0};
     CK(cudaMemcpyAsync(f, s->d_cls, sizeof f, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
+    if (f[1]) {  // some row needs the quadrature loop: its values never existed on chip, nothing is known about the class
+      s->fused_bad_valid = true, s->fused_bad_version = s->x_version;
+      return DZB_OK;
+    }
     s->classified_valid = true, s->classified_version = s->x_version, s->classified_ok = f[0] != 3;
     if (!s->classified_ok) return DZB_OK;
   }
@@ -1099,6 +1178,9 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
   if (!rc && opt.assembly_mode == DZB_ASSEMBLY_FAST && s->want_parallel && s->refine_steps == 0 && s->n >= 2 * (size_t)dzb::BS_TILE &&
       !std::getenv("DZB_NO_ONELAUNCH")) {
     rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
+    if (!rc) rc = dalloc(&s->ol_r, s->n);
+    if (!rc) rc = dalloc(&s->ol_s, s->n);
+    if (!rc) rc = dalloc(&s->ol_pool, 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n)));
     if (!rc) rc = dalloc(&s->d_cls, 2);
     if (!rc) {
       s->fused = true;
@@ -1297,7 +1379,7 @@ void dzb_solver_destroy(dzb_solver* s) {
     if (*p) *p -= s->off;
     dfree(*p);
   }
-  for (double** p : {&s->c, &s->den, &s->rden, &s->out, &s->d_top8, &s->x_own, &s->ol_red}) dfree(*p);
+  for (double** p : {&s->c, &s->den, &s->rden, &s->out, &s->d_top8, &s->x_own, &s->ol_red, &s->ol_r, &s->ol_s, &s->ol_pool}) dfree(*p);
   solver_detach(s);
   if (s->d_cls) cudaFree(s->d_cls), s->d_cls = nullptr;
   dzb::bigsys_free(&s->big);

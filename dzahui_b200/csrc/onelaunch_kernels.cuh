@@ -1,159 +1,156 @@
-// onelaunch_kernels.cuh — assemble + solve of one long bar in ONE launch, the bands never leave the chip.
+// onelaunch_kernels.cuh — assemble + solve of one long bar in ONE launch, the bands never exist in memory.
 //
 // The reference builds K with its quadrature loop and then runs solve_by_thomas over it (diffusion_solver/
 // time_independent.rs:91-196, matrix_solver/mod.rs:17-48).  The multi-launch path of bigsys_kernels.cuh mirrors that
 // split: k_assemble_fast writes four bands (32 B/row), the reduce pass reads them, two or three small launches solve the
-// reduced system, the solve pass reads the bands again (112 B/row moved for 80 B/row of algorithmic traffic, five
-// dependent launches).  Here the whole thing is one persistent cooperative kernel:
+// reduced system, the solve pass reads the bands again (112 B/row moved for 80 B/row of algorithmic traffic, seven
+// dependent launches).  Here the whole thing is one persistent cooperative kernel in which every CTA owns a CONTIGUOUS
+// range of 2048-row tiles, so that what its chunks leave behind is a contiguous piece of the next, four times smaller
+// system and can be reduced further by the same CTA without waiting for anybody:
 //
-//   * every CTA owns a CONTIGUOUS range of 2048-row tiles (not a strided one), so that what its tiles leave behind is a
-//     contiguous piece of the reduced system and can be reduced further inside the CTA;
-//   * pass 1, per tile: the node coordinates arrive through the TMA (one 16 KB box, SWIZZLE_128B, prefetched one tile
-//     ahead), every thread forms the 8 rows of its chunk in registers with the closed form of assembly_kernels.cuh
-//     (same operations, bit-identical to k_assemble_fast's bands), sweeps them (level 0 in registers, two shared-memory
-//     levels: 2048 -> 512 -> 128 -> 32 rows) and the 32 rows that are left join the CTA's own level (32 rows per tile);
-//   * the CTA reduces that level to its 2 interface rows (shared memory, multipliers kept), writes them to global memory,
-//     ONE grid-wide barrier, then every CTA solves the 2-rows-per-CTA system redundantly in shared memory (592 rows on a
-//     B200: 19 KB from L2) — no second barrier, no CTA waits for another one again;
-//   * back-substitution through the CTA's level, then pass 2 over the CTA's tiles in reverse order (the most recently
-//     read coordinates are the likeliest to still be in L2): rows formed again, swept again with the multipliers kept,
-//     back-substituted, u written.
+//   level A (the bar itself, ~34 000 rows per CTA at n = 10^7), per tile: the node coordinates arrive through the TMA (one
+//            16 KB box, SWIZZLE_128B, prefetched one tile ahead; the two coordinates either side as bulk copies), every
+//            thread forms the 8 rows of its chunk in registers with the lean closed form of assembly_kernels.cuh (ti_elem /
+//            ti_row: bit-identical to k_assemble_fast's bands), leaves TWO numbers per row in memory — 1/h of the element to
+//            the row's right and the row-sum excess s = lo + di + up — sweeps the chunk and writes its two reduced rows to
+//            level B.  No shared-memory pyramid per tile: a pyramid level is ~1 us of single-warp latency during which
+//            the rest of the CTA waits (measured: 2 us of every 7 us tile in pass 1, 3.4 of 4.9 us in pass 2);
+//   level B (rows / 4) and level C (rows / 16): the same chunk sweep by all 256 threads over the CTA's slice of the
+//            previous level's rows (global scratch, L2 resident), no barrier inside a level;
+//   level D (rows / 64 <= 576): the CTA's shared-memory pyramid down to its 2 interface rows, ONE grid-wide barrier, then
+//            every CTA solves the 2-rows-per-CTA system redundantly in shared memory (592 rows on a B200) — no second
+//            barrier, no CTA waits for another one again;
+//   and back: D in shared memory, then C, B, A: each chunk is swept again with its multipliers kept in registers and
+//            back-substituted from the two values the level above left for it.  Level A reads its two numbers per row through
+//            the TMA, tiles in reverse order (what was written last is the likeliest to still be in L2): the off-diagonals
+//            are one multiply-add away from 1/h (lo = mu K0/h_left + b hp, up = mu K0/h_right + b hn).
 //
-// HBM traffic: x twice (the second time mostly from L2) + u once = 16-24 B/row instead of 112; the price is forming the
-// rows twice, which makes the kernel fp64-issue bound rather than HBM bound.  The same kernel also takes materialised
-// bands (BS_SRC_BANDS: the reference-arithmetic assembly writes them once, 72 B/row here instead of 72 B/row + four launches).
+// HBM traffic: x in (8) + (1/h, s) out and in again (32) + u out (8) = 48 B/row, plus the level-B rows and solutions
+// (~20 B/row, mostly L2 hits), instead of 112; one launch instead of seven; the rows are formed once.  A mesh with a row the
+// closed form does not cover (degenerate spacing: ti_elem's sufficient test fails) is reported through class_flags[1] and
+// the caller goes back to materialised bands.
 #pragma once
 #include "assembly_kernels.cuh"
 #include "bigsys_kernels.cuh"
 
 namespace dzb {
 
-constexpr int OL_NLEV = 2;                                         // shared-memory levels a tile goes through
-constexpr int OL_ROUT = bs_rows_left(BS_THREADS / 4, OL_NLEV);     // rows a full tile leaves: 32
-constexpr int OL_P1M = 96;                                         // middle system: 2 rows per CTA, up to 768 rows (384 CTAs)
-constexpr int OL_QX_CAP = 512;                                     // quadrature nodes kept in shared memory for the kink probes
-static_assert(OL_ROUT == 32, "tile -> CTA level hand-over");
+constexpr int OL_P1M = 112;                                        // middle system: 2 rows per CTA, up to 896 rows (448 CTAs)
+constexpr int OL_TAB_CAP = 256;                                    // rule tables live in shared memory: at most this many nodes
+constexpr int OL_ROWS_B = BS_TILE / 4, OL_ROWS_C = BS_TILE / 16, OL_ROWS_D = BS_TILE / 64;  // rows a full tile leaves at each level
 
 struct OneLaunchArgs {
-  TileArgs k;        // NODES: p0 = x with x[r] the node of row r; BANDS / ROWS: the four arrays.  red_* : [2 gridDim.x] scratch
-  RuleView rule;     // NODES
-  AsmParams P;       // NODES
-  long long n_local; // NODES: nodes of the local coordinate array (rows + halo nodes of an open block)
-  int halo_left;     // NODES: 1 when x[-1] exists (open left end): local node index of row r = r + halo_left
-  int* class_flags;  // NODES: k_tri_classify's bits, or'ed over every interior row (bit 0: not M-like, bit 1: not mass-like)
-  unsigned* bad_rows; // NODES: rows that needed the quadrature loop (statistics only)
+  TileArgs k;        // p0 = x with x[r] the node of row r; m rows; red_* : [2 gridDim.x] scratch; out; flags; bc0 / bc1
+  RuleView rule;
+  AsmParams P;
+  long long n_local; // nodes of the local coordinate array (rows + halo nodes of an open block)
+  int halo_left;     // 1 when x[-1] exists (open left end): local node index of row r = r + halo_left
+  double* r_el;      // [m] scratch: 1/h of the element to the right of row r
+  double* s_ex;      // [m] scratch: row-sum excess of row r
+  double* gb[4];     // [OL_ROWS_B tiles] x (a, c, s, f): level B rows
+  double* gc[4];     // [OL_ROWS_C tiles] x (a, c, s, f): level C rows
+  double *ub, *uc;   // their solutions
+  unsigned long long* trace;  // tuning aid (DZB_OL_TRACE=1): [8 gridDim.x] %globaltimer at the phase boundaries of every CTA; nullptr normally
+  int* class_flags;  // [0]: k_tri_classify's bits or'ed over every interior row (bit 0: not M-like, bit 1: not mass-like);
+                     // [1]: != 0 when some row is outside the closed form.  nullptr: already known for these coordinates
 };
 
-template <int NARR, int P1C>
+template <int P1C>
 struct OneLaunchSmem {
   union Work {
-    struct Tile {
-      alignas(1024) double rows[NARR][BS_TILE];   // TMA stage
-      Pyramid<BS_THREADS / 4> pyr;
-    } tile;
+    alignas(1024) double stage[2][BS_TILE];       // TMA stage.  level A forward: x in [0]; backward: 1/h in [0], excess in [1]
     Pyramid<OL_P1M> mid;                          // only between the two passes, when no copy is in flight
   } w;
-  Pyramid<P1C> cta;
-  double qx[OL_QX_CAP];
+  Pyramid<P1C> cta;                               // level D
+  double4 uv[OL_TAB_CAP + 1];
+  double qx[OL_TAB_CAP];
+  unsigned short guessf[GUESS_BINS + 2];
+  alignas(16) double halo[4];                     // the two values either side of a staged tile (forward: x; backward: [0..1] = 1/h)
   alignas(8) unsigned long long mbar;
 };
+// 16 or 32 bytes next to a staged tile, through the same mbarrier (plain bulk copy: 16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<unsigned long long>(src)), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
 
 // element e (0 .. 2047) of a staged tile: 128-byte tensor rows, 16-byte columns XOR-swizzled with the row (SWIZZLE_128B)
 __device__ __forceinline__ double stage_elem(const double* stage, int e) {
   const int row = e >> 4, col = (e >> 1) & 7;
   return *reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(stage) + row * 128 + ((col ^ (row & 7)) << 4) + (e & 1) * 8);
 }
-
-__device__ __noinline__ void ol_quadrature_row(const double* xl, long long n_local, long long i, RuleView rule, AsmParams P, double* out7) {
-  double v[7];
-  faithful_row<KIND_TI>(xl, n_local, i, rule.x, rule.w, rule.m, P, nullptr, 0, v);
-#pragma unroll
-  for (int q = 0; q < 7; ++q) out7[q] = v[q];
-}
-
-// Rows i0 .. i0+7 (local node indices) of the static diffusion system in row-excess form (a, c, s, f), from the
-// coordinates X[k] = x_local[i0 - 2 + k] (entries outside [0, n_local) are never used).  The arithmetic is fast_row<KIND_TI>'s
-// (assembly_kernels.cuh), shared between the two rows that touch an element: bands bit-identical to k_assemble_fast's.
-template <bool CLASSIFY>
-__device__ __forceinline__ void ti_rows_from_nodes(const double (&X)[12], long long i0, int len, const OneLaunchArgs& a,
-                                                   const double* __restrict__ qx, double (&A)[BS_R], double (&C)[BS_R],
-                                                   double (&S)[BS_R], double (&F)[BS_R], int& cls, unsigned& nbad) {
-  const RuleView& R = a.rule;
-  const int m = R.m;
-  const double x_hi = qx[0], x_lo = qx[m - 1];
-  const double K0 = -0.5 * R.t0;                       // prime_{prev,next} = K0 * (1/h)
-  const double bhp = a.P.b * (-0.25 * R.t1p), bhn = a.P.b * (0.25 * R.t1m);
-  // per element el = 0..8 between X[el+1] and X[el+2]
-  double h[BS_R + 1], r[BS_R + 1];
-  bool ok_el[BS_R + 1];
-#pragma unroll
-  for (int el = 0; el <= BS_R; ++el) {
-    const double xa = X[el + 1], xb = X[el + 2];
-    h[el] = xb - xa;
-    r[el] = __drcp_rn(h[el]);
-    const Affine tm = from_m1_p1(xa, xb);
-    ok_el[el] = (xa < xb) && (tm(x_hi) < xb) && !(tm(x_lo) < xa);
-  }
-#pragma unroll
-  for (int j = 0; j < BS_R; ++j) {
-    const long long i = i0 + j;
-    double lo = 0.0, di = 1.0, up = 0.0, f = 0.0, ex = 1.0;  // padding and Dirichlet rows: (0, 1, 0, f), excess 1
-    if (j < len) {
-      if (i == 0) f = a.P.bc0;
-      else if (i == a.n_local - 1) f = a.P.bc1;
-      else {
-        const double xa = X[j + 1], xc = X[j + 2], xe = X[j + 3];
-        const Affine ts = from_m1_p1(xa, xe);
-        bool ok = ok_el[j] && ok_el[j + 1] && (ts(x_hi) < xe) && !(ts(x_lo) < xa);
-        if (i >= 2) ok = ok && !(xa < X[j]);
-        if (i + 2 < a.n_local) ok = ok && !(X[j + 4] < xe);
-        if (ok) {
-          const double h1 = h[j], h2 = h[j + 1], H = xe - xa;
-          int s;
-          {  // first node whose image is left of the kink: bracket table + probes with the reference's own predicate
-            const float xs = __fdividef((float)(h1 - h2), (float)H);
-            int bin = (int)((xs + 1.0f) * (0.5f * GUESS_BINS));
-            bin = max(0, min(GUESS_BINS - 1, bin));
-            s = R.guess[bin + 1];
-            while (s < m && !(ts(qx[s]) < xc)) ++s;
-            while (s > 0 && (ts(qx[s - 1]) < xc)) --s;
-          }
-          const double r1 = r[j], r2 = r[j + 1];
-          const double ih1sq = r1 * r1, ih2sq = r2 * r2;
-          const double U0 = R.u0[s], U1 = R.u1[s], V0 = R.v0[s], V1 = R.v1[s];
-          const double prime_sq = (0.5 * H) * fma(U0, ih1sq, V0 * ih2sq);
-          const double half_sq = (0.25 * H * H) * fma(U1, ih1sq, -V1 * ih2sq);
-          lo = fma(a.P.mu, K0 * r1, bhp);
-          di = fma(a.P.mu, prime_sq, a.P.b * half_sq);
-          up = fma(a.P.mu, K0 * r2, bhn);
-        } else {  // degenerate / unsorted spacing: the reference's quadrature loop decides which piece every node hits
-          double v[7];
-          ol_quadrature_row(a.k.p0 - a.halo_left, a.n_local, i, R, a.P, v);
-          lo = v[0], di = v[1], up = v[2], f = v[3];
-          ++nbad;
-        }
-        ex = excess3(lo, di, up);
-        if (CLASSIFY) {
-          if (!(lo <= 0.0 && up <= 0.0 && ex >= -1e-6 * di)) cls |= 1;
-          if (!(lo >= 0.0 && up >= 0.0 && di >= 1.25 * (lo + up))) cls |= 2;
-        }
-      }
-    }
-    A[j] = lo, C[j] = up, S[j] = ex, F[j] = f;  // row-excess form: tile_forward<BS_SRC_ROWS> takes it as it is
-  }
-}
-
-// The chunk of thread t: rows g0 .. g0+len of the system.  Staged tiles hand over the 8 own coordinates from shared
-// memory and the 2 + 2 halo coordinates from the neighbouring lanes; everything else reads global memory directly.
-__device__ __forceinline__ void nodes_from_stage(const double* stage, const OneLaunchArgs& a, long long g0, int t, double (&X)[12]) {
+// the 8 consecutive elements 8 t .. 8 t + 7 of a staged tile (chunk t = bytes [64 t, 64 t + 64) = 16-byte columns 4 (t & 1) + j
+// of tensor row t / 2): four conflict-free LDS.128
+__device__ __forceinline__ void stage_chunk(const double* stage, int t, double* v) {
   const int row = t >> 1;
   const unsigned char* base = reinterpret_cast<const unsigned char*>(stage) + row * 128;
 #pragma unroll
   for (int j = 0; j < BS_R / 2; ++j) {
     const int col = ((((t & 1) << 2) + j) ^ (row & 7)) << 4;
-    const double2 v = *reinterpret_cast<const double2*>(base + col);
-    X[2 + 2 * j] = v.x, X[3 + 2 * j] = v.y;
+    const double2 q = *reinterpret_cast<const double2*>(base + col);
+    v[2 * j] = q.x, v[2 * j + 1] = q.y;
   }
+}
+
+__device__ __forceinline__ void ol_stamp(const OneLaunchArgs& a, int slot) {
+  if (a.trace && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    a.trace[8 * blockIdx.x + slot] = ns;
+  }
+}
+
+struct OlTables {  // rule tables, in shared memory (the launcher refuses rules with more than OL_TAB_CAP nodes)
+  const double4* __restrict__ uv;
+  const unsigned short* __restrict__ guessf;
+  const double* __restrict__ qx;
+  int m;
+};
+
+// Rows i0 .. i0+7 (local node indices) of the static diffusion system in row-excess form (a, c, s, f), from the
+// coordinates X[k] = x_local[i0 - 2 + k] (entries outside [0, n_local) are zero and never reach a result).  Rv[j] = 1/h of
+// the element to the right of row j.  Straight-line code: rows that do not exist, Dirichlet rows and rows outside the closed
+// form are sorted out with selects, so the eight rows of a chunk interleave freely.
+template <bool CLASSIFY>
+__device__ __forceinline__ void ti_rows_from_nodes(const double (&X)[12], long long i0, int len, const OneLaunchArgs& a, const TiK& K,
+                                                   const OlTables& tb, double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R],
+                                                   double (&F)[BS_R], double (&Rv)[BS_R], int& cls, bool& bad) {
+  TiElem E[BS_R + 1];  // element el between X[el + 1] and X[el + 2]
+#pragma unroll
+  for (int el = 0; el <= BS_R; ++el) E[el] = ti_elem(X[el + 1], X[el + 2], K);
+  // j-ranges instead of 64-bit comparisons per row: rows [jd0] / [jd1] are the Dirichlet rows when they fall into this chunk,
+  // rows jlo <= j < jhi are interior rows, the outer-neighbour tests apply from jl2 on / below jh2
+  const long long nl = a.n_local;
+  const int jd0 = (int)max(-1LL, min(8LL, -i0)), jd1 = (int)max(-1LL, min(8LL, nl - 1 - i0));
+  const int jlo = max(0, jd0 + 1), jhi = min(len, jd1);
+  const int jl2 = (int)max(0LL, min(9LL, 2 - i0)), jh2 = (int)max(-1LL, min(8LL, nl - 2 - i0));  // i >= 2 / i + 2 < nl
+#pragma unroll
+  for (int j = 0; j < BS_R; ++j) {
+    const bool inter = j >= jlo && j < jhi;
+    bool ok = E[j].ok && E[j + 1].ok;
+    ok = ok && (j < jl2 || !(X[j + 1] < X[j]));
+    ok = ok && (j >= jh2 || !(X[j + 4] < X[j + 3]));
+    bad = bad || (inter && !ok);
+    double lo, di, up;
+    ti_row(E[j], E[j + 1], X[j + 1], X[j + 2], X[j + 3], K, tb.uv, tb.guessf, tb.qx, tb.m, lo, di, up, inter && ok);
+    const double ex = excess3(lo, di, up);
+    if (CLASSIFY && inter) {
+      if (!(lo <= 0.0 && up <= 0.0 && ex >= -1e-6 * di)) cls |= 1;
+      if (!(lo >= 0.0 && up >= 0.0 && di >= 1.25 * (lo + up))) cls |= 2;
+    }
+    // padding and Dirichlet rows: (0, 1, 0, f), excess 1
+    A[j] = inter ? lo : 0.0, C[j] = inter ? up : 0.0, S[j] = inter ? ex : 1.0;
+    F[j] = (j == jd0 && j < len) ? a.P.bc0 : ((j == jd1 && j < len) ? a.P.bc1 : 0.0);
+    Rv[j] = E[j + 1].r;
+  }
+}
+
+// The chunk of thread t: rows g0 .. g0+len of the system.  Staged tiles hand over the 8 own coordinates from shared
+// memory and the 2 + 2 halo coordinates from the neighbouring lanes; everything else reads global memory directly.
+__device__ __forceinline__ void nodes_from_stage(const double* stage, const double* halo, bool has_halo, const OneLaunchArgs& a,
+                                                 long long g0, int t, double (&X)[12]) {
+  stage_chunk(stage, t, &X[2]);
   const int lane = t & 31;
   X[0] = __shfl_up_sync(0xffffffffu, X[8], 1);
   X[1] = __shfl_up_sync(0xffffffffu, X[9], 1);
@@ -163,10 +160,12 @@ __device__ __forceinline__ void nodes_from_stage(const double* stage, const OneL
   const double* xl = a.k.p0 - a.halo_left;
   if (lane == 0) {
     if (t > 0) X[0] = stage_elem(stage, 8 * t - 2), X[1] = stage_elem(stage, 8 * t - 1);
+    else if (has_halo) X[0] = halo[0], X[1] = halo[1];
     else X[0] = i0 >= 2 ? xl[i0 - 2] : 0.0, X[1] = i0 >= 1 ? xl[i0 - 1] : 0.0;
   }
   if (lane == 31) {
     if (t < BS_THREADS - 1) X[10] = stage_elem(stage, 8 * t + 8), X[11] = stage_elem(stage, 8 * t + 9);
+    else if (has_halo) X[10] = halo[2], X[11] = halo[3];
     else X[10] = i0 + 8 < a.n_local ? xl[i0 + 8] : 0.0, X[11] = i0 + 9 < a.n_local ? xl[i0 + 9] : 0.0;
   }
 }
@@ -180,22 +179,100 @@ __device__ __forceinline__ void nodes_direct(const OneLaunchArgs& a, long long g
   }
 }
 
-template <int SRC>
-struct OlSrc {  // what tile_forward / tile_backward are told: NODES hands them freshly formed rows (a, c, s, f)
-  static constexpr int FWD = SRC == BS_SRC_NODES ? BS_SRC_ROWS : SRC;
-  static constexpr int BWD = SRC;
-  static constexpr int NARR = SRC == BS_SRC_NODES ? 1 : 4;
-};
+// Pass 2: rows g0 .. g0+len again, from the two numbers per row pass 1 left behind.  rprev = 1/h of the element to the
+// left of the chunk's first row.
+__device__ __forceinline__ void ti_rows_from_scratch(const double (&Rv)[BS_R], const double (&Sv)[BS_R], double rprev, long long i0, int len,
+                                                     const OneLaunchArgs& a, const TiK& K, double (&A)[BS_R], double (&C)[BS_R],
+                                                     double (&S)[BS_R], double (&F)[BS_R]) {
+  const long long nl = a.n_local;
+  const int jd0 = (int)max(-1LL, min(8LL, -i0)), jd1 = (int)max(-1LL, min(8LL, nl - 1 - i0));
+  const int jlo = max(0, jd0 + 1), jhi = min(len, jd1);
+#pragma unroll
+  for (int j = 0; j < BS_R; ++j) {
+    const bool inter = j >= jlo && j < jhi;
+    const double rl = j == 0 ? rprev : Rv[j - 1];
+    const double lo = fma(K.mu, K.K0 * rl, K.bhp), up = fma(K.mu, K.K0 * Rv[j], K.bhn);  // ti_row's expressions
+    A[j] = inter ? lo : 0.0, C[j] = inter ? up : 0.0, S[j] = inter ? Sv[j] : 1.0;
+    F[j] = (j == jd0 && j < len) ? a.P.bc0 : ((j == jd1 && j < len) ? a.P.bc1 : 0.0);
+  }
+}
 
-template <int SRC, bool ACCUM, int P1C>
-__global__ void __launch_bounds__(BS_THREADS, 2) k_tri_onelaunch(const __grid_constant__ CUtensorMap map0,
-                                                                 const __grid_constant__ CUtensorMap map1,
-                                                                 const __grid_constant__ CUtensorMap map2,
-                                                                 const __grid_constant__ CUtensorMap map3, const OneLaunchArgs a,
+
+// ---- levels B and C: rows (a, c, s, f) in global scratch ---------------------------------------------------------------
+// rows r0 .. r0+len of the arrays g[0..3] -> registers (L2 loads: the rows were written by this CTA moments ago)
+__device__ __forceinline__ void rows_load(double* const (&g)[4], long long r0, int len, double (&A)[BS_R], double (&C)[BS_R],
+                                          double (&S)[BS_R], double (&F)[BS_R]) {
+  if (len == BS_R && !(r0 & 1)) {
+    const double2* q0 = reinterpret_cast<const double2*>(g[0] + r0);
+    const double2* q1 = reinterpret_cast<const double2*>(g[1] + r0);
+    const double2* q2 = reinterpret_cast<const double2*>(g[2] + r0);
+    const double2* q3 = reinterpret_cast<const double2*>(g[3] + r0);
+#pragma unroll
+    for (int j = 0; j < BS_R / 2; ++j) {
+      const double2 v0 = __ldcg(q0 + j), v1 = __ldcg(q1 + j), v2 = __ldcg(q2 + j), v3 = __ldcg(q3 + j);
+      A[2 * j] = v0.x, A[2 * j + 1] = v0.y, C[2 * j] = v1.x, C[2 * j + 1] = v1.y;
+      S[2 * j] = v2.x, S[2 * j + 1] = v2.y, F[2 * j] = v3.x, F[2 * j + 1] = v3.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < BS_R; ++j) {
+      const bool in = j < len;
+      A[j] = in ? __ldcg(g[0] + r0 + j) : 0.0, C[j] = in ? __ldcg(g[1] + r0 + j) : 0.0;
+      S[j] = in ? __ldcg(g[2] + r0 + j) : 1.0, F[j] = in ? __ldcg(g[3] + r0 + j) : 0.0;
+    }
+  }
+}
+// the two reduced rows of a chunk -> rows q, q + 1 (q even) of the arrays g[0..3]
+__device__ __forceinline__ void rows_store2(double* const (&g)[4], long long q, const double (&o)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) *reinterpret_cast<double2*>(g[k] + q) = make_double2(o[k], o[4 + k]);
+}
+template <bool KEEP>
+__device__ __forceinline__ void chunk_sweep(double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R], int len,
+                                            double (&o)[8]) {
+  if (len == BS_R) chunk0_sweep<KEEP, true>(A, C, S, F, len, o);
+  else chunk0_sweep<KEEP, false>(A, C, S, F, len, o);
+}
+// One streaming level, forward: the CTA's m rows at src[0..3][base ..] -> 2 rows per chunk at dst[0..3][dbase ..]
+__device__ __forceinline__ void level_forward(double* const (&src)[4], long long base, int m, double* const (&dst)[4], long long dbase, int t) {
+  const int nc = (m + BS_R - 1) / BS_R;
+  for (int c = t; c < nc; c += BS_THREADS) {
+    const ChunkGeom gm = chunk_geom(m, c, 0);
+    double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
+    rows_load(src, base + gm.g0, gm.len, A, C, S, F);
+    chunk_sweep<false>(A, C, S, F, gm.len, o);
+    rows_store2(dst, dbase + 2 * c, o);
+  }
+}
+// ... and backward: usrc[ubase + 2 c], [.. + 1] hold u of the chunk's first / last row; u of all its rows -> udst[base ..]
+__device__ __forceinline__ void level_backward(double* const (&src)[4], long long base, int m, const double* usrc, long long ubase,
+                                               double* udst, int t) {
+  const int nc = (m + BS_R - 1) / BS_R;
+  for (int c = t; c < nc; c += BS_THREADS) {
+    const ChunkGeom gm = chunk_geom(m, c, 0);
+    const double2 ends = __ldcg(reinterpret_cast<const double2*>(usrc + ubase + 2 * c));
+    double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
+    rows_load(src, base + gm.g0, gm.len, A, C, S, F);
+    chunk_sweep<true>(A, C, S, F, gm.len, o);
+    chunk0_backward(A, C, S, F, gm.len, ends.x, ends.y, u);
+    double* dst = udst + base + gm.g0;
+    if (gm.len == BS_R && !((base + gm.g0) & 1)) {
+#pragma unroll
+      for (int j = 0; j < BS_R / 2; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(u[2 * j], u[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BS_R; ++j)
+        if (j < gm.len) dst[j] = u[j];
+    }
+  }
+}
+
+template <int P1C, int MINB>
+__global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid_constant__ CUtensorMap map_x,
+                                                                 const __grid_constant__ CUtensorMap map_r,
+                                                                 const __grid_constant__ CUtensorMap map_s, const OneLaunchArgs a,
                                                                  const int use_tma) {
-  using Smem = OneLaunchSmem<OlSrc<SRC>::NARR, P1C>;
-  constexpr int NARR = OlSrc<SRC>::NARR;
-  constexpr int P1T = BS_THREADS / 4;
+  using Smem = OneLaunchSmem<P1C>;
   extern __shared__ __align__(1024) unsigned char ol_smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(ol_smem_raw);
   if (smem_u32(ol_smem_raw) & 1023) __trap();
@@ -203,114 +280,115 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_onelaunch(const __grid_co
   const TileArgs& k = a.k;
   const int t = threadIdx.x;
   const long long ntiles = (k.m + BS_TILE - 1) / BS_TILE;
-  const long long tb0 = (long long)blockIdx.x * ntiles / gridDim.x, tb1 = ((long long)blockIdx.x + 1) * ntiles / gridDim.x;
-  const int T = (int)(tb1 - tb0);  // >= 1: the launcher never starts more CTAs than tiles
-  int rowsC;                       // rows of this CTA's level: 32 per tile (any short tile is the last one of the system)
+  // contiguous tile ranges; a ragged last tile takes the direct-load path, which costs about two staged tiles, and everybody
+  // would wait for its CTA at the grid barrier: it counts twice in the split
+  long long tb0, tb1;
   {
-    long long tl0;
-    const int rl = tile_rows(tb1 - 1, k.m, BS_TILE, &tl0);
-    rowsC = OL_ROUT * (T - 1) + bs_rows_left_of(2 * ((rl + BS_R - 1) / BS_R), P1T, OL_NLEV);
+    const long long units = ntiles + ((use_tma && (k.m % BS_TILE)) ? 1 : 0);
+    tb0 = min(ntiles, (long long)blockIdx.x * units / gridDim.x);
+    tb1 = blockIdx.x + 1 == gridDim.x ? ntiles : min(ntiles, ((long long)blockIdx.x + 1) * units / gridDim.x);
   }
+  const int T = (int)(tb1 - tb0);  // >= 1: the launcher never starts more CTAs than tiles
+  // the CTA's systems: level A rows [R0, R0 + mA) of the bar, then mB = 2 chunks(mA) rows at gb[..][oB ..], mC, mD (shared memory)
+  const long long R0 = tb0 * BS_TILE;
+  const int mA = (int)(min(k.m, tb1 * BS_TILE) - R0);
+  const int nA = (mA + BS_R - 1) / BS_R, mB = 2 * nA, nB = (mB + BS_R - 1) / BS_R, mC = 2 * nB, nC = (mC + BS_R - 1) / BS_R, mD = 2 * nC;
+  const long long oB = tb0 * OL_ROWS_B, oC = tb0 * OL_ROWS_C;
   constexpr int PC = lvl_stride(P1C);
-  const double* qx = a.rule.x;
-  if (SRC == BS_SRC_NODES && a.rule.m <= OL_QX_CAP) {
-    for (int j = t; j < a.rule.m; j += BS_THREADS) sm.qx[j] = a.rule.x[j];
-    qx = sm.qx;
-  }
+  const TiK K = make_tik(a.rule, a.P);
+  for (int j = t; j <= a.rule.m; j += BS_THREADS) sm.uv[j] = a.rule.uv[j];
+  for (int j = t; j < a.rule.m; j += BS_THREADS) sm.qx[j] = a.rule.x[j];
+  for (int j = t; j < GUESS_BINS + 2; j += BS_THREADS) sm.guessf[j] = a.rule.guessf[j];
+  const OlTables tb{sm.uv, sm.guessf, sm.qx, a.rule.m};
+  const bool classify = a.class_flags != nullptr;
   if (t == 0) mbar_init(&sm.mbar, 1);
   __syncthreads();
-  auto staged = [&](long long tile) {
-    long long t0;
-    return use_tma && tile_rows(tile, k.m, BS_TILE, &t0) == BS_TILE;
-  };
-  auto request = [&](long long tile) {  // thread 0
-    mbar_arrive_expect_tx(&sm.mbar, (unsigned)(NARR * BS_TILE * sizeof(double)));
-    const int row = (int)(tile * BS_TMA_BOX);
-    tma_load_box(sm.w.tile.rows[0], &map0, row, &sm.mbar);
-    if constexpr (NARR == 4) {
-      tma_load_box(sm.w.tile.rows[NARR - 3], &map1, row, &sm.mbar);
-      tma_load_box(sm.w.tile.rows[NARR - 2], &map2, row, &sm.mbar);
-      tma_load_box(sm.w.tile.rows[NARR - 1], &map3, row, &sm.mbar);
-    }
-  };
+  auto staged = [&](long long tile) { return use_tma && (tile + 1) * BS_TILE <= k.m; };  // (m % BS_TILE == 1 is refused by the launcher)
   unsigned phase = 0;
-  int cls = 0;
-  unsigned nbad = 0;
-  // One tile into registers as (lo, di, up, f) / (a, c, s, f); `next` is the tile to prefetch once the stage is free.
-  auto load_tile = [&](long long tile, long long next, bool classify, double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R],
-                       double (&F)[BS_R], ChunkGeom& gm, int& rows1, bool& vec) {
-    long long tile0;
-    const int rows0 = tile_rows(tile, k.m, BS_TILE, &tile0);
-    rows1 = 2 * ((rows0 + BS_R - 1) / BS_R);
-    gm = chunk_geom(rows0, t, tile0);
-    const bool st = staged(tile);
-    if (st) {
-      mbar_wait(&sm.mbar, phase);
-      phase ^= 1;
+  ol_stamp(a, 0);
+
+  // ---- level A forward: assemble, leave (1/h, s) per row, two reduced rows per chunk -> level B
+  // the two coordinates either side of a staged tile ride along as two 16-byte bulk copies when both pairs exist (every tile
+  // but the first and, at most, the last full one): nobody then waits for a global load on a tile's critical path
+  auto x_halo = [&](long long tile) { return tile > 0 && (tile + 1) * BS_TILE + 1 + a.halo_left < a.n_local; };
+  auto request_x = [&](long long tile) {  // thread 0
+    const bool hh = x_halo(tile);
+    // The stage was just READ with ordinary loads by every thread (ordered before this point by the CTA barrier) and is about
+    // to be WRITTEN by the async proxy: without a proxy fence from the issuing thread a tile now and then kept some 128-byte
+    // lines of its predecessor (measured on a B200: one CTA in ~300 per solve formed rows from coordinates 2048 nodes off; on
+    // a regular bar, where K 1 = 0, that is a wrong answer, on a jittered one a 1e-6 blemish).
+    asm volatile("fence.proxy.async;" ::: "memory");
+    mbar_arrive_expect_tx(&sm.mbar, (unsigned)(BS_TILE * sizeof(double)) + (hh ? 32u : 0u));
+    tma_load_box(sm.w.stage[0], &map_x, (int)(tile * BS_TMA_BOX), &sm.mbar);
+    if (hh) {
+      bulk_load(sm.halo, k.p0 + tile * BS_TILE - 2, 16, &sm.mbar);
+      bulk_load(sm.halo + 2, k.p0 + (tile + 1) * BS_TILE, 16, &sm.mbar);
     }
-    if (SRC == BS_SRC_NODES) {
-      double X[12];
-      if (st) nodes_from_stage(sm.w.tile.rows[0], a, gm.g0, t, X);
-      else nodes_direct(a, gm.g0, X);
-      __syncthreads();  // every chunk is in registers, and the previous tile is done with the pyramid
-      if (t == 0 && next >= 0 && staged(next)) request(next);
-      const long long i0 = gm.g0 + a.halo_left;
-      if (classify) ti_rows_from_nodes<true>(X, i0, gm.len, a, qx, A, C, S, F, cls, nbad);
-      else ti_rows_from_nodes<false>(X, i0, gm.len, a, qx, A, C, S, F, cls, nbad);
-      vec = gm.len == BS_R && !(reinterpret_cast<size_t>(k.out + gm.g0) & 15);
-    } else {
-      if (st) {
-        const int row = t >> 1;
-        const unsigned char* base = reinterpret_cast<const unsigned char*>(sm.w.tile.rows[0]) + row * 128;
-#pragma unroll
-        for (int j = 0; j < BS_R / 2; ++j) {
-          const int col = ((((t & 1) << 2) + j) ^ (row & 7)) << 4;
-          const double2 v0 = *reinterpret_cast<const double2*>(base + col);
-          const double2 v1 = *reinterpret_cast<const double2*>(base + col + BS_TILE * 8);
-          const double2 v2 = *reinterpret_cast<const double2*>(base + col + BS_TILE * 16);
-          const double2 v3 = *reinterpret_cast<const double2*>(base + col + BS_TILE * 24);
-          if (SRC == BS_SRC_BANDS) {
-            A[2 * j] = v0.x, A[2 * j + 1] = v0.y, S[2 * j] = v1.x, S[2 * j + 1] = v1.y;
-            C[2 * j] = v2.x, C[2 * j + 1] = v2.y;
-          } else {
-            A[2 * j] = v0.x, A[2 * j + 1] = v0.y, C[2 * j] = v1.x, C[2 * j + 1] = v1.y;
-            S[2 * j] = v2.x, S[2 * j + 1] = v2.y;
-          }
-          F[2 * j] = v3.x, F[2 * j + 1] = v3.y;
-        }
-        __syncthreads();
-        if (t == 0 && next >= 0 && staged(next)) request(next);
-        vec = !(reinterpret_cast<size_t>(k.out + gm.g0) & 15);
+  };
+  if (t == 0 && staged(tb0)) request_x(tb0);
+  int cls = 0;
+  bool bad = false;
+  for (int kk = 0; kk < T; ++kk) {
+    const long long tile = tb0 + kk;
+    const int c = kk * BS_THREADS + t;
+    const ChunkGeom gm = chunk_geom(mA, c, 0);  // len == 0: no such chunk
+    const long long G0 = R0 + gm.g0;            // first row of the chunk
+    double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
+    {
+      double X[12], Rv[BS_R];
+      if (staged(tile)) {
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1;
+        nodes_from_stage(sm.w.stage[0], sm.halo, x_halo(tile), a, G0, t, X);
       } else {
-        __syncthreads();
-        if (t == 0 && next >= 0 && staged(next)) request(next);
-        vec = chunk_load_direct<OlSrc<SRC>::FWD, true>(k, gm.g0, gm.len, A, C, S, F);
+        nodes_direct(a, G0, X);
+      }
+      __syncthreads();  // every chunk is in registers: the stage can take the next tile
+      if (t == 0 && kk + 1 < T && staged(tile + 1)) request_x(tile + 1);
+      if (classify) ti_rows_from_nodes<true>(X, G0 + a.halo_left, gm.len, a, K, tb, A, C, S, F, Rv, cls, bad);
+      else ti_rows_from_nodes<false>(X, G0 + a.halo_left, gm.len, a, K, tb, A, C, S, F, Rv, cls, bad);
+      if (gm.len == BS_R && !(G0 & 1)) {
+        double2* pr = reinterpret_cast<double2*>(a.r_el + G0);
+        double2* ps = reinterpret_cast<double2*>(a.s_ex + G0);
+#pragma unroll
+        for (int j = 0; j < BS_R / 2; ++j) pr[j] = make_double2(Rv[2 * j], Rv[2 * j + 1]), ps[j] = make_double2(S[2 * j], S[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BS_R; ++j)
+          if (j < gm.len) a.r_el[G0 + j] = Rv[j], a.s_ex[G0 + j] = S[j];
       }
     }
-  };
-
-  // ---- pass 1: every tile down to its 32 rows, which join the CTA's level
-  if (t == 0 && staged(tb0)) request(tb0);
-  LevelPtr c1 = sm.cta.level(0);
-  for (int kk = 0; kk < T; ++kk) {
-    double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
-    ChunkGeom gm;
-    int rows1;
-    bool vec;
-    load_tile(tb0 + kk, kk + 1 < T ? tb0 + kk + 1 : -1, a.class_flags != nullptr, A, C, S, F, gm, rows1, vec);
-    const typename Pyramid<P1T>::Left left =
-        tile_forward<OlSrc<SRC>::FWD, false, OL_NLEV>(sm.w.tile.pyr, k, A, C, S, F, gm.len, gm.g0, t, rows1);
-    if (t < left.rows) {
-      const int q = left.pos(t), p = row_slot(OL_ROUT * kk + t, rowsC, PC);
-      c1.a[p] = sm.w.tile.pyr.a[q], c1.c[p] = sm.w.tile.pyr.c[q], c1.s[p] = sm.w.tile.pyr.s[q], c1.d[p] = sm.w.tile.pyr.d[q];
+    if (gm.len >= 2) {
+      double o[8];
+      chunk_sweep<false>(A, C, S, F, gm.len, o);
+      rows_store2(a.gb, oB + 2 * c, o);
     }
   }
-  if (SRC == BS_SRC_NODES) {
-    if (cls && a.class_flags) atomicOr(a.class_flags, cls);
-    if (nbad) atomicAdd(a.bad_rows, nbad);
+  if (classify) {
+    const int c0 = __syncthreads_or(cls & 1), c1b = __syncthreads_or(cls & 2), cb = __syncthreads_or(bad);
+    if (t == 0) {
+      if (c0 | c1b) atomicOr(a.class_flags, (c0 ? 1 : 0) | (c1b ? 2 : 0));
+      if (cb) atomicOr(a.class_flags + 1, 1);
+    }
   }
-  // ---- the CTA's level down to its two interface rows
-  sm.cta.template reduce_to<0, true>(t, rowsC);
+  ol_stamp(a, 1);
+  // ---- levels B and C forward (no barrier inside a level), level D in shared memory down to the CTA's two interface rows
+  __threadfence();
+  __syncthreads();
+  level_forward(a.gb, oB, mB, a.gc, oC, t);
+  __threadfence();
+  __syncthreads();
+  LevelPtr c1 = sm.cta.level(0);
+  for (int c = t; c < nC; c += BS_THREADS) {
+    const ChunkGeom gm = chunk_geom(mC, c, 0);
+    double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
+    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F);
+    chunk_sweep<false>(A, C, S, F, gm.len, o);
+    const int p0 = row_slot(2 * c, mD, PC), p1 = row_slot(2 * c + 1, mD, PC);
+    c1.a[p0] = o[0], c1.c[p0] = o[1], c1.s[p0] = o[2], c1.d[p0] = o[3];
+    c1.a[p1] = o[4], c1.c[p1] = o[5], c1.s[p1] = o[6], c1.d[p1] = o[7];
+  }
+  sm.cta.reduce_cold(t, mD);
   {
     LevelPtr top = sm.cta.top();
     if (t < 2) {
@@ -318,8 +396,11 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_onelaunch(const __grid_co
       k.red_a[o] = top.a[t], k.red_c[o] = top.c[t], k.red_s[o] = top.s[t], k.red_f[o] = top.d[t];
     }
   }
+  asm volatile("fence.proxy.async.global;" ::: "memory");  // writers' side of the cross-proxy ordering (see request_rs): both are needed
   __threadfence();
+  ol_stamp(a, 2);
   grid.sync();
+  ol_stamp(a, 3);
   // ---- the 2-rows-per-CTA system, solved by every CTA for itself (the work area is free: no copy is in flight)
   {
     const int m2 = 2 * (int)gridDim.x;
@@ -329,7 +410,9 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_onelaunch(const __grid_co
       const int p = row_slot(rr, m2, PM);
       l1.a[p] = __ldcg(k.red_a + rr), l1.c[p] = __ldcg(k.red_c + rr), l1.s[p] = __ldcg(k.red_s + rr), l1.d[p] = __ldcg(k.red_f + rr);
     }
-    sm.w.mid.reduce(t, m2);
+    ol_stamp(a, 6);
+    sm.w.mid.reduce_cold(t, m2);
+    ol_stamp(a, 7);
     LevelPtr top = sm.w.mid.top();
     if (t == 0) {  // closed 2 x 2 system (a_0 = c_1 = 0), as in mid_body
       const double c0 = top.c[0], s0 = top.s[0], f0 = top.d[0], a1 = top.a[1], s1 = top.s[1], f1 = top.d[1];
@@ -337,89 +420,161 @@ __global__ void __launch_bounds__(BS_THREADS, 2) k_tri_onelaunch(const __grid_co
       top.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;
       top.d[1] = ((s0 - c0) * f1 - a1 * f0) / det;
     }
-    sm.w.mid.backsolve(t, m2);
+    sm.w.mid.backsolve_cold(t, m2);
     if (t < 2) sm.cta.top().d[t] = l1.d[row_slot(2 * (int)blockIdx.x + t, m2, PM)];
   }
-  sm.cta.backsolve(t, rowsC);  // starts and ends with a CTA barrier: the work area is free again afterwards
-  // ---- pass 2: the tiles again, last one first, swept with the multipliers kept and back-substituted
-  if (t == 0 && staged(tb1 - 1)) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the work area was written with ordinary stores
-    request(tb1 - 1);
+  sm.cta.backsolve_cold(t, mD);  // starts and ends with a CTA barrier: the work area is free again afterwards
+  ol_stamp(a, 4);
+  // ---- levels C and B backward
+  for (int c = t; c < nC; c += BS_THREADS) {
+    const ChunkGeom gm = chunk_geom(mC, c, 0);
+    const double us = c1.d[row_slot(2 * c, mD, PC)], ue = c1.d[row_slot(2 * c + 1, mD, PC)];
+    double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
+    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F);
+    chunk_sweep<true>(A, C, S, F, gm.len, o);
+    chunk0_backward(A, C, S, F, gm.len, us, ue, u);
+#pragma unroll
+    for (int j = 0; j < BS_R; ++j)
+      if (j < gm.len) a.uc[oC + gm.g0 + j] = u[j];
   }
+  __threadfence();
+  __syncthreads();
+  level_backward(a.gb, oB, mB, a.uc, oC, a.ub, t);
+  __threadfence();
+  __syncthreads();
+
+  // ---- level A backward: the tiles again, last one first
+  auto request_rs = [&](long long tile) {  // thread 0
+    // as in request_x; here the source, too, was written with ordinary stores (the forward pass, other threads, another CTA
+    // for the value left of the CTA's first tile): generic -> async ordering for both state spaces, from the issuing thread,
+    // after it has synchronised with the writers (the grid barrier and the CTA barriers since)
+    asm volatile("fence.proxy.async;" ::: "memory");
+    mbar_arrive_expect_tx(&sm.mbar, (unsigned)(2 * BS_TILE * sizeof(double)) + (tile > 0 ? 16u : 0u));
+    const int row = (int)(tile * BS_TMA_BOX);
+    tma_load_box(sm.w.stage[0], &map_r, row, &sm.mbar);
+    tma_load_box(sm.w.stage[1], &map_s, row, &sm.mbar);
+    if (tile > 0) bulk_load(sm.halo, a.r_el + tile * BS_TILE - 2, 16, &sm.mbar);  // [1] = 1/h left of the tile's first row
+  };
+  if (t == 0 && staged(tb1 - 1)) request_rs(tb1 - 1);  // (its proxy fence also covers the ordinary stores of the middle solve into the work area)
   for (int kk = T - 1; kk >= 0; --kk) {
+    const long long tile = tb0 + kk;
+    const int c = kk * BS_THREADS + t;
+    const ChunkGeom gm = chunk_geom(mA, c, 0);
+    const long long G0 = R0 + gm.g0;
+    double2 ends = make_double2(0.0, 0.0);
+    if (gm.len >= 2) ends = __ldcg(reinterpret_cast<const double2*>(a.ub + oB + 2 * c));
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
-    ChunkGeom gm;
-    int rows1;
-    bool vec;
-    load_tile(tb0 + kk, kk > 0 ? tb0 + kk - 1 : -1, false, A, C, S, F, gm, rows1, vec);
-    double u_left = 0.0;
-    if (t < bs_rows_left_of(rows1, P1T, OL_NLEV)) u_left = c1.d[row_slot(OL_ROUT * kk + t, rowsC, PC)];
-    const typename Pyramid<P1T>::Left left =
-        tile_forward<OlSrc<SRC>::FWD, true, OL_NLEV>(sm.w.tile.pyr, k, A, C, S, F, gm.len, gm.g0, t, rows1);
-    if (t < left.rows) sm.w.tile.pyr.d[left.pos(t)] = u_left;
-    tile_backward<OlSrc<SRC>::BWD, ACCUM, OL_NLEV>(sm.w.tile.pyr, k, A, C, S, F, gm.len, gm.g0, vec, t, rows1);
+    {
+      double Rv[BS_R], Sv[BS_R], rprev = 0.0;
+      const double* xl = k.p0 - a.halo_left;
+      if (staged(tile)) {
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1;
+        stage_chunk(sm.w.stage[0], t, Rv);
+        stage_chunk(sm.w.stage[1], t, Sv);
+        rprev = __shfl_up_sync(0xffffffffu, Rv[BS_R - 1], 1);
+        if ((t & 31) == 0) {
+          if (t > 0) rprev = stage_elem(sm.w.stage[0], 8 * t - 1);
+          else if (tile > 0) rprev = sm.halo[1];
+          else rprev = a.halo_left ? rcp_newton(xl[1] - xl[0]) : 0.0;  // ti_elem's expression
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < BS_R; ++j) {
+          const bool in = j < gm.len;
+          Rv[j] = in ? __ldcg(a.r_el + G0 + j) : 0.0, Sv[j] = in ? __ldcg(a.s_ex + G0 + j) : 1.0;
+        }
+        if (gm.len > 0) {
+          if (G0 > 0) rprev = __ldcg(a.r_el + G0 - 1);
+          else rprev = a.halo_left ? rcp_newton(xl[1] - xl[0]) : 0.0;
+        }
+      }
+      __syncthreads();  // every chunk is in registers: the stage can take the next tile
+      if (t == 0 && kk > 0 && staged(tile - 1)) request_rs(tile - 1);
+      ti_rows_from_scratch(Rv, Sv, rprev, G0 + a.halo_left, gm.len, a, K, A, C, S, F);
+    }
+    if (gm.len >= 2) {
+      double o[8], u[BS_R];
+      chunk_sweep<true>(A, C, S, F, gm.len, o);
+      chunk0_backward(A, C, S, F, gm.len, ends.x, ends.y, u);
+      // a Dirichlet row is returned exactly as Thomas returns it, f / 1 (matrix_solver/mod.rs:36-39 with zero couplings)
+      if (G0 == 0 && !(k.flags & BS_OPEN_LEFT)) u[0] = k.bc0 / 1.0;
+      if (G0 + gm.len == k.m && !(k.flags & BS_OPEN_RIGHT)) {
+#pragma unroll
+        for (int j = 0; j < BS_R; ++j)
+          if (j == gm.len - 1) u[j] = k.bc1 / 1.0;
+      }
+      double* dst = k.out + G0;
+      if (gm.len == BS_R && !(reinterpret_cast<size_t>(dst) & 15)) {
+#pragma unroll
+        for (int j = 0; j < BS_R / 2; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(u[2 * j], u[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BS_R; ++j)
+          if (j < gm.len) dst[j] = u[j];
+      }
+    }
   }
+  ol_stamp(a, 5);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
-struct OneLaunchPlan {
-  int grid = 0;       // CTAs (<= co-resident capacity, <= tiles)
-  int p1c = 0;        // capacity class of the CTA level
-};
-
-template <int SRC, bool ACCUM, int P1C>
+// Two builds: level D of 72 chunks (18 tiles per CTA) at two CTAs per SM (128 registers), of 256 chunks (64 tiles) at one.
+// (Three CTAs per SM with 80 registers spill and are slower: 0.275 against 0.209 ms at 10^7 rows.)
+template <int P1C, int MINB>
 inline int onelaunch_capacity() {
-  using Smem = OneLaunchSmem<OlSrc<SRC>::NARR, P1C>;
+  using Smem = OneLaunchSmem<P1C>;
   int dev = 0, coop = 0, per_sm = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (!coop) return 0;
-  if (cudaFuncSetAttribute(k_tri_onelaunch<SRC, ACCUM, P1C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_tri_onelaunch<P1C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tri_onelaunch<SRC, ACCUM, P1C>, BS_THREADS, sizeof(Smem)) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tri_onelaunch<P1C, MINB>, BS_THREADS, sizeof(Smem)) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   return std::min(per_sm * sms, 8 * OL_P1M / 2);  // the middle system holds 2 rows per CTA in 8 OL_P1M rows
 }
 
-// Launches the kernel on (args.k.p0 .. p3, args.k.m); returns 0 on success, -1 when the one-launch kernel does not apply
+// rows of scratch the levels B and C need for an m-row system (per array)
+inline size_t onelaunch_rows_b(size_t m) { return ((m + BS_TILE - 1) / BS_TILE) * (size_t)OL_ROWS_B; }
+inline size_t onelaunch_rows_c(size_t m) { return ((m + BS_TILE - 1) / BS_TILE) * (size_t)OL_ROWS_C; }
+
+template <int P1C, int MINB>
+inline int onelaunch_try(OneLaunchArgs& args, size_t tiles, int& cap, void** params, cudaStream_t st, unsigned long long* launches,
+                         int* grid_out) {
+  if (cap < 0) cap = onelaunch_capacity<P1C, MINB>();
+  const size_t grid = std::min<size_t>(tiles, (size_t)std::max(cap, 0));
+  *grid_out = (int)grid;
+  // level D holds 32 rows per tile (tiles + 1: a ragged last tile counts twice in the kernel's split of the tiles over the CTAs)
+  if (grid == 0 || (tiles + 1 + grid - 1) / grid > (size_t)(8 * P1C / OL_ROWS_D)) return -1;
+  ++*launches;
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tri_onelaunch<P1C, MINB>, dim3((unsigned)grid), dim3(BS_THREADS), params,
+                                              sizeof(OneLaunchSmem<P1C>), st);
+  return e == cudaSuccess ? 0 : bigsys_fail(e, "k_tri_onelaunch");
+}
+
+// Launches the kernel on (args.k.p0, args.k.m); returns 0 on success, -1 when the one-launch kernel does not apply
 // (no cooperative launch, system too long for the CTA level), 1 on a CUDA error (bigsys_error()).
-// caps: per-device capacities of the instantiations, asked once (index 0: P1C = 72, 1: P1C = 256).
-template <int SRC, bool ACCUM>
-inline int onelaunch_run(BigSys* s, OneLaunchArgs args, int (&caps)[2], cudaStream_t st, unsigned long long* launches) {
+// caps: per-device capacities of the instantiations, asked once.
+inline int onelaunch_run(BigSys* s, OneLaunchArgs args, int (&caps)[2], cudaStream_t st, unsigned long long* launches, int* grid_out) {
   const size_t m = (size_t)args.k.m;
   const size_t tiles = (m + BS_TILE - 1) / BS_TILE;
-  if (tiles < 2) return -1;
-  if (caps[0] < 0) caps[0] = onelaunch_capacity<SRC, ACCUM, 72>();
-  int which = 0;
-  size_t grid = std::min<size_t>(tiles, (size_t)std::max(caps[0], 0));
-  if (grid == 0 || (tiles + grid - 1) / grid > 72 / 4) {  // more than 18 tiles per CTA: the big CTA level
-    if (caps[1] < 0) caps[1] = onelaunch_capacity<SRC, ACCUM, 256>();
-    grid = std::min<size_t>(tiles, (size_t)std::max(caps[1], 0));
-    which = 1;
-    if (grid == 0 || (tiles + grid - 1) / grid > 256 / 4) return -1;
-  }
-  CUtensorMap c0, c1, c2, c3;
-  int use_tma = s->tma && !(reinterpret_cast<size_t>(args.k.p0) & 15) && bigsys_map(s, args.k.p0, m, &c0);
-  if (use_tma && SRC != BS_SRC_NODES)
-    use_tma = !((reinterpret_cast<size_t>(args.k.p1) | reinterpret_cast<size_t>(args.k.p2) | reinterpret_cast<size_t>(args.k.p3)) & 15) &&
-              bigsys_map(s, args.k.p1, m, &c1) && bigsys_map(s, args.k.p2, m, &c2) && bigsys_map(s, args.k.p3, m, &c3);
-  if (!use_tma) std::memset(&c0, 0, sizeof c0);
-  if (!use_tma || SRC == BS_SRC_NODES) c1 = c0, c2 = c0, c3 = c0;
-  void* params[] = {&c0, &c1, &c2, &c3, &args, &use_tma};
-  ++*launches;
-  cudaError_t e;
-  if (which == 0)
-    e = cudaLaunchCooperativeKernel((const void*)k_tri_onelaunch<SRC, ACCUM, 72>, dim3((unsigned)grid), dim3(BS_THREADS), params,
-                                    sizeof(OneLaunchSmem<OlSrc<SRC>::NARR, 72>), st);
-  else
-    e = cudaLaunchCooperativeKernel((const void*)k_tri_onelaunch<SRC, ACCUM, 256>, dim3((unsigned)grid), dim3(BS_THREADS), params,
-                                    sizeof(OneLaunchSmem<OlSrc<SRC>::NARR, 256>), st);
-  return e == cudaSuccess ? 0 : bigsys_fail(e, "k_tri_onelaunch");
+  // (the rule tables live in shared memory; a last tile of one row would leave its CTA a one-row system)
+  if (tiles < 2 || args.rule.m <= 0 || args.rule.m > OL_TAB_CAP || m % BS_TILE == 1) return -1;
+  CUtensorMap cx, cr, cs;
+  int use_tma = s->tma &&
+                !((reinterpret_cast<size_t>(args.k.p0) | reinterpret_cast<size_t>(args.r_el) | reinterpret_cast<size_t>(args.s_ex)) & 15) &&
+                bigsys_map(s, args.k.p0, m, &cx) && bigsys_map(s, args.r_el, m, &cr) && bigsys_map(s, args.s_ex, m, &cs);
+  if (!use_tma) std::memset(&cx, 0, sizeof cx), cr = cx, cs = cx;
+  void* params[] = {&cx, &cr, &cs, &args, &use_tma};
+  int rc = onelaunch_try<72, 2>(args, tiles, caps[0], params, st, launches, grid_out);
+  if (rc < 0) rc = onelaunch_try<256, 1>(args, tiles, caps[1], params, st, launches, grid_out);
+  return rc;
 }
 
 }  // namespace dzb

@@ -1,5 +1,4 @@
-set -x
-python tools/time_long_solve.py 10000000 > gpurun_out/r2c_time.json 2>gpurun_out/r2c_time.err
-ncu --set full --import-source on --clock-control none -k regex:k_tri_onelaunch -c 3 -o gpurun_out/r2c_onelaunch -f python tools/time_long_solve.py 10000000 > gpurun_out/r2c_ncu.log 2>&1
-tail -5 gpurun_out/r2c_ncu.log
-cat gpurun_out/r2c_time.json
+python -m pytest tests/test_gpu_onelaunch.py -q 2>&1 | tail -4
+python tools/_dbg.py 2>/dev/null | grep solve | cut -c1-50 | sort | uniq -c
+python tools/time_long_solve.py 1000000 10000000 2>&1 | tail -1 | cut -c1-500
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
