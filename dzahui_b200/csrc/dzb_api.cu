@@ -1126,13 +1126,13 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done) {
     if (const char* path = std::getenv("DZB_OL_TRACE_FILE")) {  // one line per CTA: the six stamps in microseconds
       if (FILE* f = std::fopen(path, "w")) {
         for (int c = 0; c < ctas; ++c) {
-          for (int k = 0; k < 6; ++k) std::fprintf(f, "%.3f ", (double)(h[8 * c + k] - t0) * 1e-3);
+          for (int k = 0; k < 8; ++k) std::fprintf(f, "%.3f ", (double)(h[8 * c + k] - t0) * 1e-3);
           std::fprintf(f, "\n");
         }
         std::fclose(f);
       }
     }
-    const char* names[] = {"start", "pass1 end", "cta level reduced", "after grid sync", "middle solved", "pass2 end", "middle rows loaded", "middle reduced"};
+    const char* names[] = {"start", "pass1 end", "cta level reduced", "after grid sync", "middle solved", "pass2 end", "level B reduced", "level C reduced"};
     for (int k = 0; k < 8; ++k) {
       double lo = 1e30, hi = 0, sum = 0;
       for (int c = 0; c < ctas; ++c) {

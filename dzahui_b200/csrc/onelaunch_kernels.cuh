@@ -139,10 +139,16 @@ __device__ __forceinline__ void ti_rows_from_nodes(const double (&X)[12], long l
       if (!(lo <= 0.0 && up <= 0.0 && ex >= -1e-6 * di)) cls |= 1;
       if (!(lo >= 0.0 && up >= 0.0 && di >= 1.25 * (lo + up))) cls |= 2;
     }
-    // padding and Dirichlet rows: (0, 1, 0, f), excess 1
-    A[j] = inter ? lo : 0.0, C[j] = inter ? up : 0.0, S[j] = inter ? ex : 1.0;
-    F[j] = (j == jd0 && j < len) ? a.P.bc0 : ((j == jd1 && j < len) ? a.P.bc1 : 0.0);
+    A[j] = lo, C[j] = up, S[j] = ex, F[j] = 0.0;
     Rv[j] = E[j + 1].r;
+  }
+  if (jlo != 0 || jhi != BS_R) {  // a chunk with padding or Dirichlet rows, (0, 1, 0, f) with excess 1: the first and the last of the bar
+#pragma unroll
+    for (int j = 0; j < BS_R; ++j) {
+      const bool inter = j >= jlo && j < jhi;
+      A[j] = inter ? A[j] : 0.0, C[j] = inter ? C[j] : 0.0, S[j] = inter ? S[j] : 1.0;
+      F[j] = (j == jd0 && j < len) ? a.P.bc0 : ((j == jd1 && j < len) ? a.P.bc1 : 0.0);
+    }
   }
 }
 
@@ -189,11 +195,17 @@ __device__ __forceinline__ void ti_rows_from_scratch(const double (&Rv)[BS_R], c
   const int jlo = max(0, jd0 + 1), jhi = min(len, jd1);
 #pragma unroll
   for (int j = 0; j < BS_R; ++j) {
-    const bool inter = j >= jlo && j < jhi;
     const double rl = j == 0 ? rprev : Rv[j - 1];
     const double lo = fma(K.mu, K.K0 * rl, K.bhp), up = fma(K.mu, K.K0 * Rv[j], K.bhn);  // ti_row's expressions
-    A[j] = inter ? lo : 0.0, C[j] = inter ? up : 0.0, S[j] = inter ? Sv[j] : 1.0;
-    F[j] = (j == jd0 && j < len) ? a.P.bc0 : ((j == jd1 && j < len) ? a.P.bc1 : 0.0);
+    A[j] = lo, C[j] = up, S[j] = Sv[j], F[j] = 0.0;
+  }
+  if (jlo != 0 || jhi != BS_R) {  // as in ti_rows_from_nodes
+#pragma unroll
+    for (int j = 0; j < BS_R; ++j) {
+      const bool inter = j >= jlo && j < jhi;
+      A[j] = inter ? A[j] : 0.0, C[j] = inter ? C[j] : 0.0, S[j] = inter ? S[j] : 1.0;
+      F[j] = (j == jd0 && j < len) ? a.P.bc0 : ((j == jd1 && j < len) ? a.P.bc1 : 0.0);
+    }
   }
 }
 
@@ -373,11 +385,10 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   }
   ol_stamp(a, 1);
   // ---- levels B and C forward (no barrier inside a level), level D in shared memory down to the CTA's two interface rows
-  __threadfence();
   __syncthreads();
   level_forward(a.gb, oB, mB, a.gc, oC, t);
-  __threadfence();
   __syncthreads();
+  ol_stamp(a, 6);
   LevelPtr c1 = sm.cta.level(0);
   for (int c = t; c < nC; c += BS_THREADS) {
     const ChunkGeom gm = chunk_geom(mC, c, 0);
@@ -388,6 +399,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     c1.a[p0] = o[0], c1.c[p0] = o[1], c1.s[p0] = o[2], c1.d[p0] = o[3];
     c1.a[p1] = o[4], c1.c[p1] = o[5], c1.s[p1] = o[6], c1.d[p1] = o[7];
   }
+  ol_stamp(a, 7);
   sm.cta.reduce_cold(t, mD);
   {
     LevelPtr top = sm.cta.top();
@@ -410,9 +422,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       const int p = row_slot(rr, m2, PM);
       l1.a[p] = __ldcg(k.red_a + rr), l1.c[p] = __ldcg(k.red_c + rr), l1.s[p] = __ldcg(k.red_s + rr), l1.d[p] = __ldcg(k.red_f + rr);
     }
-    ol_stamp(a, 6);
     sm.w.mid.reduce_cold(t, m2);
-    ol_stamp(a, 7);
     LevelPtr top = sm.w.mid.top();
     if (t == 0) {  // closed 2 x 2 system (a_0 = c_1 = 0), as in mid_body
       const double c0 = top.c[0], s0 = top.s[0], f0 = top.d[0], a1 = top.a[1], s1 = top.s[1], f1 = top.d[1];
@@ -437,10 +447,8 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     for (int j = 0; j < BS_R; ++j)
       if (j < gm.len) a.uc[oC + gm.g0 + j] = u[j];
   }
-  __threadfence();
   __syncthreads();
   level_backward(a.gb, oB, mB, a.uc, oC, a.ub, t);
-  __threadfence();
   __syncthreads();
 
   // ---- level A backward: the tiles again, last one first
