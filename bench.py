@@ -358,10 +358,19 @@ def measure_c4(cx, n, assembly, steps, warmup, parity_ref=None, e2e_steps=0):
     asm_ms = cx.time_steps(solver.rebuild, steps, 3)[0] / steps
     sol_ms = cx.time_steps(lambda: solver.solve_device(0.0), steps, 3)[0] / steps
     out["assemble_ms"], out["solve_ms"] = asm_ms, sol_ms
+    out["path"] = solver.path()
+    one_launch = "onelaunch" in out["path"]
     ach = SURVEY_BYTES_STATIC * n / (ms * 1e-3) / 1e9
-    out["roofline"] = {"bound": "hbm", "kernel": "assemble + tridiagonal solve kernels (whole step)", "achieved": ach, "peak": cx.peak,
+    out["roofline"] = {"bound": "hbm",
+                       "kernel": "k_tri_onelaunch (rows formed on chip, one cooperative launch per assemble + solve)" if one_launch
+                       else "assemble + tridiagonal solve kernels (whole step)",
+                       "achieved": ach, "peak": cx.peak,
                        "unit": "GB/s", "frac": ach / cx.peak, "algorithmic_bytes_per_launch": SURVEY_BYTES_STATIC * n,
                        "bytes_accounting": "SURVEY 8(d): assembly 40 B/DOF (x 8 in, 4 bands 32 out) + solve 40 B/DOF (4 bands in, u out)",
+                       "design_bytes_per_row": ("x in 8 + (1/h, row excess) out and in 32 + u out 8 = 48, plus the level-B/C rows and solutions "
+                                                "(~22 B/row, partly L2 hits); the bands are never materialised (rebuild is a no-op: "
+                                                "assemble_ms ~ 0, everything is in solve_ms)") if one_launch
+                       else "x 8 + bands out 32 + bands in twice 64 + u 8 = 112",
                        "traffic": None, "peak_source": cx.peak_src}
     if assembly != "fast":
         # the reference-arithmetic assembly is fp64-pipe bound, not HBM bound: G-1 quadrature nodes x 27 separately rounded
