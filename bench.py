@@ -431,6 +431,63 @@ def measure_c4(cx, n, assembly, steps, warmup, parity_ref=None, e2e_steps=0):
     return out
 
 
+def measure_c4_split(cx, n, assembly, steps, warmup, comm, parity_ref=None):
+    """BASELINE config 4 at N > 1: ONE n-node bar split into row blocks, one per rank (strong scaling).  Per step every rank
+    calls `dzb_solver_block_rebuild` (assembly of its block) + `dzb_solver_block_solve_device` (block elimination, exchange of
+    the 2 interface rows per block, interface solve, back-substitution): the communicator is the library's own (dzb_comm_*)."""
+    import numpy as np
+    dz, dist = cx.dz, cx.dist
+    from dzahui_b200 import synthetic
+    from dzahui_b200.distributed import SplitBarTimeIndependent
+    mesh = synthetic.regular_bar(n)
+    params = dz.DiffussionParams.time_independent().mu(MU).b(BADV).boundary_conditions(*BC).build()
+    amode = {"auto": dz.ASSEMBLY_AUTO, "faithful": dz.ASSEMBLY_FAITHFUL, "fast": dz.ASSEMBLY_FAST}[assembly]
+    t0 = time.perf_counter()
+    bar = SplitBarTimeIndependent(params, mesh, G, comm, dz.make_options(amode, dz.SOLVE_PARALLEL))
+    dz.synchronize()
+    out = {"assembly": assembly, "nodes": n, "n_gpus": cx.world, "rows_per_gpu": bar.rows[1] - bar.rows[0],
+           "create_s": time.perf_counter() - t0, "transport": "peer mailboxes (NVLink stores + flag, no collective launch)"
+           if comm.peer_mailboxes else "ncclAllGather of 8 doubles per rank"}
+
+    def step():
+        bar.rebuild()
+        bar.solve_device()
+
+    ramp_clocks(step, cx.local_rank)
+    total_ms, per_step, launches = cx.time_steps(step, steps, warmup)
+    bar.status()
+    ms = total_ms / steps
+    out.update({"ms_per_step": ms, "value": n * steps / (total_ms * 1e-3), "unit": UNIT, "scaling": "strong",
+                "gpu_launches_per_step": launches / steps, "steps": steps, "path": bar.path()})
+    out["assemble_ms"] = cx.time_steps(bar.rebuild, steps, 3)[0] / steps
+    out["solve_ms"] = cx.time_steps(bar.solve_device, steps, 3)[0] / steps
+    bar.status()
+    ach = SURVEY_BYTES_STATIC * n / (ms * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "kernel": out["path"], "achieved": ach, "peak": cx.peak * cx.world, "unit": "GB/s",
+                       "frac": ach / (cx.peak * cx.world), "algorithmic_bytes_per_launch": SURVEY_BYTES_STATIC * n,
+                       "bytes_accounting": "SURVEY 8(d): assembly 40 B/DOF + solve 40 B/DOF, against N x the measured copy peak",
+                       "traffic": None, "peak_source": cx.peak_src}
+    if parity_ref is not None:
+        u_block = bar.solve(0.0)
+        parts = [None] * cx.world if cx.rank == 0 else None
+        dist.gather_object(u_block, parts, dst=0)
+        if cx.rank == 0:
+            import oracle_lib as o
+            u = np.concatenate(parts)
+            if not parity_ref:   # the reference-arithmetic bands of the whole bar, from the CPU port (all host threads)
+                lo, di, up, rhs = o.ti_assemble(mesh, MU, BADV, BC, G, mode=0, threads=host_threads())
+                parity_ref["ref_f64"] = o.thomas(lo, di, up, rhs)
+                parity_ref["f128"] = o.thomas(lo, di, up, rhs, kind="f128")
+            ref, truth = parity_ref["ref_f64"], parity_ref["f128"]
+            nrm = float(np.linalg.norm(truth))
+            out["parity"] = {"rel_l2_gpu_vs_reference_f64": float(np.linalg.norm(u - ref)) / float(np.linalg.norm(ref)),
+                             "rel_l2_reference_f64_vs_f128": float(np.linalg.norm(ref - truth)) / nrm,
+                             "rel_l2_gpu_vs_f128": float(np.linalg.norm(u - truth)) / nrm,
+                             "reference": "oracle quadrature-loop assembly + solve_by_thomas (f64) and __float128 Thomas of the same bands"}
+    bar.close()
+    return out
+
+
 def measure_c5_strong(cx, total_bars, steps, warmup, weak_ms):
     """BASELINE's wording of config 5: ONE ensemble of `total_bars` bars sharded across the ranks (strong scaling)."""
     import numpy as np
@@ -554,8 +611,10 @@ def main():
         if world == 1:
             sec = measure_c4(cx, n, args.assembly, args.steps, args.warmup, parity_ref=None, e2e_steps=e2e_steps)
         else:
-            from dzahui_b200 import split_bar
-            sec = split_bar.measure(cx, n, args.assembly, args.steps, args.warmup, G, MU, BADV, BC)
+            from dzahui_b200.distributed import NativeComm
+            comm = NativeComm.from_torch()
+            sec = measure_c4_split(cx, n, args.assembly, args.steps, args.warmup, comm, parity_ref={})
+            comm.close()
         clocks = sampler.result()
         ms_per_step, value, launches = sec["ms_per_step"], sec["value"], int(sec["gpu_launches_per_step"] * args.steps)
         roofline = sec.pop("roofline")
@@ -594,8 +653,14 @@ def main():
             extra["c4"] = c4
         else:
             try:
-                from dzahui_b200 import split_bar
-                extra["c4_split"] = split_bar.measure(cx, args.nodes, "auto", min(args.steps, 50), 3, G, MU, BADV, BC)
+                from dzahui_b200.distributed import NativeComm
+                comm = NativeComm.from_torch()
+                cache = {}
+                c4 = {"workload": c4_workload(args.nodes, world)}
+                for mode in ("auto", "fast"):
+                    c4[mode] = measure_c4_split(cx, args.nodes, mode, min(args.steps, 50), 3, comm, parity_ref=cache)
+                comm.close()
+                extra["c4_split"] = c4
             except Exception as ex:  # the headline must not depend on the extra section
                 extra["c4_split"] = {"error": repr(ex)}
         if world == 1 and args.bars == C5_BARS:

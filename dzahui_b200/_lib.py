@@ -80,6 +80,14 @@ SIGNATURES = {
     "dzb_solver_block_edges_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dzb_solver_block_residual_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dzb_solver_block_device_solution": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dzb_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "dzb_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "dzb_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dzb_comm_all_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dzb_comm_destroy": (None, [C.c_void_p]),
+    "dzb_solver_block_rebuild": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dzb_solver_block_solve_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dzb_solver_block_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dzb_format_f64": (C.c_int, [C.c_double, C.c_char_p, C.c_size_t]),
     "dzb_csv_prepare_dir": (C.c_int, [C.c_char_p, C.c_int]),
     "dzb_csv_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_char_p), C.c_size_t, c_double_p, C.c_size_t]),

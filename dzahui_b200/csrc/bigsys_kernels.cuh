@@ -45,6 +45,7 @@
 #include <string>
 #include <vector>
 
+#include "comm_kernels.cuh"
 #include "tridiag_kernels.cuh"
 
 namespace dzb {
@@ -887,30 +888,7 @@ __global__ void __launch_bounds__(256) k_residual_dd(const double* __restrict__ 
   }
 }
 
-// ---- SPIKE interface system on the device: rows[8 r ..] = block r's (a, c, s, f) x 2, 2 n_blocks unknowns ----------
-// Serial Thomas in row-excess form (sigma'_i = s_i + m sigma'_{i-1}, beta_i = sigma'_i - c_i: same-signed sums for an
-// M-matrix); every rank runs it redundantly on the gathered rows, so nothing but the all-gather crosses NVLink.
-__global__ void k_interface_solve(const double* __restrict__ rows, int m, double* __restrict__ ends, double* __restrict__ work) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double sig = rows[2] - rows[0];  // row 0: the (zero) outer coupling of the closed end leaves the excess
-  double beta = sig - rows[1], fp = rows[3];
-  work[0] = beta, work[m] = fp;
-  for (int i = 1; i < m; ++i) {
-    const double a = rows[4 * i], c = i == m - 1 ? 0.0 : rows[4 * i + 1], s = rows[4 * i + 2], f = rows[4 * i + 3];
-    const double mm = -a / beta;
-    const double s_eff = i == m - 1 ? s - rows[4 * i + 1] : s;  // drop the stored (zero) outer coupling from the excess
-    sig = fma(mm, sig, s_eff);
-    fp = fma(mm, fp, f);
-    beta = sig - c;
-    work[i] = beta, work[m + i] = fp;
-  }
-  double x = work[2 * m - 1] / work[m - 1];
-  ends[m - 1] = x;
-  for (int i = m - 2; i >= 0; --i) {
-    x = (work[m + i] - rows[4 * i + 1] * x) / work[i];
-    ends[i] = x;
-  }
-}
+// (the SPIKE interface system of a bar split across GPUs: comm_kernels.cuh)
 
 // ---- is the system one the partitioned elimination is reliable on? -------------------------------------------------
 // The chunk sweeps eliminate every chunk on its own (local Dirichlet problems).  That is as stable as serial Thomas
@@ -981,6 +959,27 @@ inline int bigsys_fail(cudaError_t e, const char* what) {
   return 1;
 }
 
+// One-off per-DEVICE set-up at a call site (function attributes and occupancy are per device; the ABI has dzb_set_device):
+//   static PerDevice<int> cap;  int& v = cap.slot(&fresh);  if (fresh) v = ...;
+constexpr int BS_MAX_DEVICES = 64;
+inline int bigsys_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < BS_MAX_DEVICES ? d : 0;
+}
+template <class T>
+struct PerDevice {
+  T v[BS_MAX_DEVICES] = {};
+  bool init[BS_MAX_DEVICES] = {};
+  T& slot(bool* fresh) {
+    const int d = bigsys_device();
+    *fresh = !init[d];
+    init[d] = true;
+    return v[d];
+  }
+  void forget() { init[bigsys_device()] = false; }  // the set-up failed: try again next time
+};
+
 inline void bigsys_free(BigSys* s) {
   for (BigLevel& l : s->levels)
     for (double** p : {&l.a, &l.c, &l.s, &l.f, &l.u})
@@ -1029,12 +1028,16 @@ inline int bigsys_mid_launch(const double* p0, const double* p1, const double* p
                              bool accum, int flags, double* top8, double us, double ue, cudaStream_t st) {
   constexpr size_t smem = sizeof(Pyramid<P1>);
   if (smem > 48 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<char> attr;
+    bool fresh;
+    attr.slot(&fresh);
+    if (fresh) {
       cudaError_t e1 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaError_t e2 = cudaFuncSetAttribute(k_tri_mid<P1, SRC, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e1 != cudaSuccess || e2 != cudaSuccess) return bigsys_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute");
-      attr_set = true;
+      if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        attr.forget();
+        return bigsys_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute");
+      }
     }
   }
   if (accum)
@@ -1092,13 +1095,16 @@ inline bool bigsys_map(BigSys* s, const double* p, size_t m, CUtensorMap* out) {
   return true;
 }
 inline int bigsys_sm_count() {
-  static int n = [] {
-    int dev = 0, v = 0;
+  static PerDevice<int> n;
+  bool fresh;
+  int& v = n.slot(&fresh);
+  if (fresh) {
+    int dev = 0, q = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
+    cudaDeviceGetAttribute(&q, cudaDevAttrMultiProcessorCount, dev);
+    v = q > 0 ? q : 148;
+  }
+  return v;
 }
 
 // One application of the tile kernel.  Big systems whose arrays are 16-byte aligned go through the TMA-staged persistent
@@ -1113,12 +1119,16 @@ inline cudaError_t bigsys_launch_tile_n(BigSys* s, size_t m, const double* p0, c
       !((reinterpret_cast<size_t>(p0) | reinterpret_cast<size_t>(p1) | reinterpret_cast<size_t>(p2) | reinterpret_cast<size_t>(p3)) & 15)) {
     CUtensorMap c0, c1, c2, c3;  // by value: a lookup may grow the cache
     if (bigsys_map(s, p0, m, &c0) && bigsys_map(s, p1, m, &c1) && bigsys_map(s, p2, m, &c2) && bigsys_map(s, p3, m, &c3)) {
-      static bool attr_set = false;  // per instantiation
-      if (!attr_set) {
+      static PerDevice<char> attr;  // per instantiation and device
+      bool fresh;
+      attr.slot(&fresh);
+      if (fresh) {
         cudaError_t e = cudaFuncSetAttribute(k_tri_tile_tma<SRC, SOLVE, ACCUM, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)BS_STAGE_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (e != cudaSuccess) {
+          attr.forget();
+          return e;
+        }
       }
       const size_t grid = std::min(tiles, (size_t)2 * bigsys_sm_count());
       k_tri_tile_tma<SRC, SOLVE, ACCUM, NLEV><<<(unsigned)grid, BS_THREADS, BS_STAGE_SMEM, st>>>(c0, c1, c2, c3, k);
@@ -1181,15 +1191,18 @@ inline int bigsys_backward(BigSys* s, const double* lo, const double* di, const 
 template <int SRC, bool ACCUM, int MAXT>
 inline int bigsys_fused_try_n(const TileArgs& k, size_t tiles, cudaStream_t st, unsigned long long* launches) {
   constexpr size_t smem = sizeof(FusedSmem<MAXT>);
-  static int capacity = [] {
+  static PerDevice<int> cap;  // per instantiation and device
+  bool fresh;
+  int& capacity = cap.slot(&fresh);
+  if (fresh) {
     int dev = 0, coop = 0, per_sm = 0;
+    capacity = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (!coop) return 0;
-    if (cudaFuncSetAttribute(k_tri_fused<SRC, ACCUM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tri_fused<SRC, ACCUM, MAXT>, BS_THREADS, smem) != cudaSuccess) return 0;
-    return per_sm * bigsys_sm_count();
-  }();
+    if (coop && cudaFuncSetAttribute(k_tri_fused<SRC, ACCUM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tri_fused<SRC, ACCUM, MAXT>, BS_THREADS, smem) == cudaSuccess)
+      capacity = per_sm * bigsys_sm_count();
+  }
   if (tiles > (size_t)MAXT || tiles > (size_t)capacity) return -1;
   TileArgs args = k;
   void* params[] = {&args};

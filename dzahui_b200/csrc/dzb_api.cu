@@ -3,6 +3,8 @@
 // (explicit fma() only where the FAST kernels ask for it; FAITHFUL kernels keep separate mul/add like the reference).
 // No CPU fallback: every compute entry point needs a CUDA device and reports DZB_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is bound with dlopen (dzb_comm.inl), nothing links against it
 
 #include <algorithm>
 #include <cmath>
@@ -65,6 +67,23 @@ int sync_stream() {
   return DZB_OK;
 }
 inline unsigned blocks_for(long long work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+// ---- per-device resources (the ABI has dzb_set_device: nothing device-side may be a process-wide static) -------------
+constexpr size_t SLABS = 8;  // dzb_ensemble_solve: slabs of the pipelined read-back
+struct DeviceCtx {
+  unsigned* d_bad = nullptr;   // rows the closed-form assembly did not cover in the last launch
+  int* d_flags = nullptr;      // k_tri_classify's verdict
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t stepped[SLABS] = {}, copied = nullptr;
+  bool copy_ready = false;     // set only after every create call above has succeeded
+  unsigned long long* d_trace = nullptr;
+};
+DeviceCtx g_ctx[dzb::BS_MAX_DEVICES];
+DeviceCtx& device_ctx() { return g_ctx[dzb::bigsys_device()]; }
+
+bool env_set(const char* name) { return std::getenv(name) != nullptr; }
+// environment knobs of the per-call paths, read once (knobs looked at when a handle is created are read there)
+const bool g_no_multi_step = env_set("DZB_NO_MULTI_STEP"), g_no_slab_copy = env_set("DZB_NO_SLAB_COPY"), g_ol_trace = env_set("DZB_OL_TRACE");
 
 // ---- quadrature rule cache (device copies keyed by (device, G)) -------------------------------------------------
 struct DeviceRule {
@@ -187,7 +206,7 @@ int launch_assembly(const double* d_mesh, size_t n, size_t n_bars, size_t G, int
     long long blocks = (total + 255) / 256;
     const long long cap = 148LL * 8 * 4;  // grid-stride: a few waves of 8 resident CTAs on each of the 148 SMs
     if (blocks > cap) blocks = cap;
-    static unsigned* d_bad = nullptr;  // rows the closed form did not cover in the last launch (device side only)
+    unsigned*& d_bad = device_ctx().d_bad;  // rows the closed form did not cover in the last launch (device side only)
     if (!d_bad) CK(cudaMalloc((void**)&d_bad, sizeof(unsigned)));
     CK(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), g_stream));
     dzb::k_assemble_fast<KIND><<<(unsigned)blocks, 256, smem, g_stream>>>(d_mesh, (long long)n, (long long)n_bars, rule, P, o,
@@ -372,7 +391,14 @@ struct dzb_solver {
   int* d_cls = nullptr;          // [0] matrix-class bits of the last classifying launch, [1] != 0: a row outside the closed form
   int ol_caps[2] = {-1, -1};
   int last_path = 0;             // 0 materialised + partitioned / serial, 1 one launch from the node coordinates
+  // block of a split bar on the one-launch path: x_own holds halo + own nodes behind x_pad spare entries, so that the
+  // block's first OWN row is 16-byte aligned (TMA); the matrix class / closed-form coverage of new coordinates is
+  // accumulated by the kernel and looked at when somebody reads the result (no host round trip inside a collective solve)
+  size_t x_pad = 0;
+  bool cls_pending = false;
 };
+
+struct dzb_comm;
 
 namespace {
 
@@ -444,10 +470,14 @@ template <int L>
 int launch_step_fast(dzb_ensemble* e) {
   constexpr int WARPS = 4;
   constexpr size_t smem = WARPS * (32 * L + 34) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    CK(cudaFuncSetAttribute(dzb::k_td_step_fast<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  if (smem > 48 * 1024) {
+    static dzb::PerDevice<char> attr;
+    bool fresh;
+    attr.slot(&fresh);
+    if (fresh && cudaFuncSetAttribute(dzb::k_td_step_fast<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      attr.forget();
+      return fail(DZB_CUDA, "cudaFuncSetAttribute(k_td_step_fast)");
+    }
   }
   const unsigned blocks = (unsigned)((e->B + WARPS - 1) / WARPS);
   dzb::k_td_step_fast<L, WARPS><<<blocks, 32 * WARPS, smem, g_stream>>>(e->u[e->cur], e->u[e->cur ^ 1], e->a_lo, e->a_di, e->a_up,
@@ -568,7 +598,7 @@ int ensemble_step_once(dzb_ensemble* e, double dt) {
 
 // true when the partitioned solver is reliable on (lo, di, up): an M-matrix or a strictly dominant positive one
 int tri_parallel_ok(const double* lo, const double* di, const double* up, size_t n, bool* ok) {
-  static int* d_flags = nullptr;
+  int*& d_flags = device_ctx().d_flags;
   if (!d_flags) CK(cudaMalloc((void**)&d_flags, sizeof(int)));
   CK(cudaMemsetAsync(d_flags, 0, sizeof(int), g_stream));
   dzb::k_tri_classify<<<dzb::bigsys_grid(n), 256, 0, g_stream>>>(lo, di, up, (long long)n, d_flags);
@@ -1012,6 +1042,7 @@ int dzb_boundary_vertices_device(const uint32_t* d_triangles, size_t n_triangles
 }
 
 // ------------------------------------------------------------------------------------------------- static solvers
+static int block_assemble(dzb_solver* s, const double* x_with_halo);
 static int static_alloc(dzb_solver* s, size_t n) {
   int rc;
   for (double** p : {&s->lo, &s->di, &s->up, &s->rhs, &s->out})
@@ -1070,21 +1101,25 @@ static int static_materialise(dzb_solver* s) {
 }
 // Assemble + solve in one launch straight from the node coordinates.  *done = false: the path does not apply to this
 // system (matrix class, size, no cooperative launch) and the caller goes on with materialised bands.
-static int static_solve_onelaunch(dzb_solver* s, bool* done) {
+static int static_solve_onelaunch(dzb_solver* s, bool* done, const dzb::PeerBox* px = nullptr) {
   *done = false;
   const bool known = s->classified_valid && s->classified_version == s->x_version;
-  if (known && !s->classified_ok) return DZB_OK;
-  if (s->fused_bad_valid && s->fused_bad_version == s->x_version) return DZB_OK;
+  if (!s->is_block) {
+    if (known && !s->classified_ok) return DZB_OK;
+    if (s->fused_bad_valid && s->fused_bad_version == s->x_version) return DZB_OK;
+  }
   dzb::OneLaunchArgs a{};
   int rc = get_rule(s->G, &a.rule);
   if (rc) return rc;
   if (a.rule.m <= 0) return DZB_OK;
   double* r = s->ol_red;
   constexpr size_t RS = 8 * dzb::OL_P1M;
-  a.k = dzb::TileArgs{s->x_view, nullptr, nullptr, nullptr, (long long)s->n, r, r + RS, r + 2 * RS, r + 3 * RS, nullptr, s->out, 0};
+  a.k = dzb::TileArgs{s->x_view, nullptr, nullptr, nullptr, (long long)s->n, r, r + RS, r + 2 * RS, r + 3 * RS, nullptr, s->out,
+                      s->is_block ? s->block_flags : 0};
   a.k.bc0 = s->bc0, a.k.bc1 = s->bc1;
   a.P = dzb::AsmParams{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
-  a.n_local = (long long)s->n, a.halo_left = 0;
+  a.n_local = (long long)(s->is_block ? s->n_alloc : s->n), a.halo_left = (s->is_block && (s->block_flags & dzb::BS_OPEN_LEFT)) ? 1 : 0;
+  if (px) a.px = *px;
   a.r_el = s->ol_r, a.s_ex = s->ol_s;
   {
     const size_t rb = dzb::onelaunch_rows_b(s->n), rc = dzb::onelaunch_rows_c(s->n);
@@ -1094,8 +1129,8 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done) {
     for (int i = 0; i < 4; ++i) a.gc[i] = q, q += rc;
     a.uc = q;
   }
-  static const bool trace_on = std::getenv("DZB_OL_TRACE") != nullptr;  // tuning aid: phase timeline of every CTA to stderr
-  static unsigned long long* d_trace = nullptr;
+  const bool trace_on = g_ol_trace;  // tuning aid: phase timeline of every CTA to stderr
+  unsigned long long*& d_trace = device_ctx().d_trace;
   if (trace_on && !d_trace) CK(cudaMalloc((void**)&d_trace, 8 * 1024 * sizeof(unsigned long long)));
   a.trace = trace_on ? d_trace : nullptr;
   a.class_flags = known ? nullptr : s->d_cls;
@@ -1105,6 +1140,11 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done) {
   if (lr > 0) return fail(DZB_CUDA, dzb::bigsys_error());
   if (lr < 0) {
     s->fused = false;
+    return DZB_OK;
+  }
+  if (s->is_block) {  // a collective: never waits for the host; the flags are looked at by dzb_solver_block_read / _status
+    if (!known) s->cls_pending = true, s->classified_valid = true, s->classified_version = s->x_version, s->classified_ok = true;
+    *done = true;
     return DZB_OK;
   }
   if (trace_on) {
@@ -1176,7 +1216,7 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
   if (!rc) rc = static_finish(s, opt, m);
   // closed-form assembly + partitioned solver on a bar of at least two tiles: from now on one launch per assemble + solve
   if (!rc && opt.assembly_mode == DZB_ASSEMBLY_FAST && s->want_parallel && s->refine_steps == 0 && s->n >= 2 * (size_t)dzb::BS_TILE &&
-      !std::getenv("DZB_NO_ONELAUNCH")) {
+      !env_set("DZB_NO_ONELAUNCH")) {
     rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
     if (!rc) rc = dalloc(&s->ol_r, s->n);
     if (!rc) rc = dalloc(&s->ol_s, s->n);
@@ -1354,7 +1394,8 @@ int dzb_solver_bands(const dzb_solver* s, int which, double* lo, double* di, dou
   } else {
     if (which != 0) return fail(DZB_INVALID, "static solvers only have a stiffness matrix");
     if (s->bands_stale) {  // one-launch path: the bands only exist when somebody asks for them
-      int rc = static_materialise(const_cast<dzb_solver*>(s));
+      dzb_solver* ms = const_cast<dzb_solver*>(s);
+      int rc = s->is_block ? block_assemble(ms, s->x_own + s->x_pad) : static_materialise(ms);
       if (rc) return rc;
     }
     dl = s->lo, dd = s->di, du = s->up, dr = s->rhs;
@@ -1424,6 +1465,21 @@ int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right
       rc = fail(DZB_INVALID, "the block's matrix is neither an M-matrix nor strictly dominant: the partitioned (SPIKE) solver "
                              "is not reliable on it; solve the bar on one GPU (serial recurrence)");
   }
+  if (!rc) s->classified_valid = true, s->classified_version = m->version, s->classified_ok = true, s->x_version = m->version;
+  // closed-form assembly on a block of at least two tiles: the rows can be formed inside the solve (k_tri_onelaunch), the
+  // interface rows crossing GPUs through the peer mailboxes of a dzb_comm (dzb_solver_block_solve_device)
+  if (!rc && opt.assembly_mode == DZB_ASSEMBLY_FAST && s->refine_steps == 0 && s->n >= 2 * (size_t)dzb::BS_TILE && !env_set("DZB_NO_ONELAUNCH")) {
+    s->x_pad = lead;  // halo at [x_pad], first own row at [x_pad + lead]: index 0 or 2, 16-byte aligned
+    rc = dalloc(&s->x_own, s->n_alloc + s->x_pad + 2);
+    if (!rc) rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
+    if (!rc) rc = dalloc(&s->ol_r, s->n);
+    if (!rc) rc = dalloc(&s->ol_s, s->n);
+    if (!rc) rc = dalloc(&s->ol_pool, 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n)));
+    if (!rc) rc = dalloc(&s->d_cls, 2);
+    if (!rc && cudaMemcpyAsync(s->x_own + s->x_pad, m->d_nodes, s->n_alloc * sizeof(double), cudaMemcpyDeviceToDevice, g_stream) != cudaSuccess)
+      rc = fail(DZB_CUDA, "D2D node coordinates");
+    if (!rc) s->x_view = s->x_own + s->x_pad + lead, s->fused = true;
+  }
   if (!rc) rc = sync_stream();
   if (rc) {
     dzb_solver_destroy(s);
@@ -1432,9 +1488,46 @@ int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right
   *out = s;
   return DZB_OK;
 }
+// bands of a block for its current coordinates (the halo rows come out as discarded boundary rows)
+static int block_assemble(dzb_solver* s, const double* x_with_halo) {
+  const size_t lead = (s->block_flags & dzb::BS_OPEN_LEFT) ? 1 : 0;
+  dzb::AsmParams P{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
+  dzb::AsmOut o{s->lo - lead, s->di - lead, s->up - lead, s->rhs - lead, nullptr, nullptr, nullptr};
+  int rc = launch_assembly<dzb::KIND_TI>(x_with_halo, s->n_alloc, 1, s->G, s->assembly_mode, P, o, nullptr);
+  if (!rc) s->bands_stale = false;
+  return rc;
+}
+/* XSolver::new again for a block, into the buffers it owns: `m` holds the block's nodes + halo nodes as at creation. */
+int dzb_solver_block_rebuild(dzb_solver* s, const dzb_mesh* m) {
+  if (!s || !m) return fail(DZB_INVALID, "null pointer");
+  if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  if (m->n != s->n_alloc) return fail(DZB_WRONG_DIMS, "rebuild needs a mesh with the block's node count (own + halo nodes)");
+  if (s->fused) {  // the rows are formed inside the solve: only the (aligned, private) coordinates change
+    if (m->version != s->x_version)
+      CK(cudaMemcpyAsync(s->x_own + s->x_pad, m->d_nodes, s->n_alloc * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    s->x_version = m->version;
+    s->bands_stale = true;
+    return DZB_OK;
+  }
+  int rc = block_assemble(s, m->d_nodes);
+  if (rc) return rc;
+  s->x_version = m->version;
+  if (!(s->classified_valid && s->classified_version == m->version)) {  // new coordinates: is the block still one the
+    bool ok = false;                                                     // partitioned elimination is reliable on?
+    if ((rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok))) return rc;
+    s->classified_valid = true, s->classified_version = m->version, s->classified_ok = ok;
+    if (!ok) return fail(DZB_INVALID, "the block's matrix is neither an M-matrix nor strictly dominant");
+  }
+  return DZB_OK;
+}
+static int block_fresh_bands(dzb_solver* s) {  // one-launch blocks materialise their bands only when a caller needs them
+  if (!s->bands_stale) return DZB_OK;
+  return block_assemble(s, s->x_own + s->x_pad);
+}
 int dzb_solver_block_reduce(dzb_solver* s, int which_rhs, double top8[8]) {
   if (!s || !top8) return fail(DZB_INVALID, "null pointer");
   if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  if (int frc = block_fresh_bands(s)) return frc;
   const double* f = which_rhs ? s->big.resid : s->rhs;
   if (dzb::bigsys_block_reduce(&s->big, s->lo, s->di, s->up, f, s->block_flags, s->d_top8, g_stream, &g_launches))
     return fail(DZB_CUDA, dzb::bigsys_error());
@@ -1470,6 +1563,7 @@ int dzb_solver_block_residual(dzb_solver* s, double u_left, double u_right) {
 int dzb_solver_block_reduce_device(dzb_solver* s, int which_rhs, double* d_top8) {
   if (!s || !d_top8) return fail(DZB_INVALID, "null pointer");
   if (!s->is_block) return fail(DZB_INVALID, "not a block solver");
+  if (int frc = block_fresh_bands(s)) return frc;
   const double* f = which_rhs ? s->big.resid : s->rhs;
   if (dzb::bigsys_block_reduce(&s->big, s->lo, s->di, s->up, f, s->block_flags, d_top8, g_stream, &g_launches))
     return fail(DZB_CUDA, dzb::bigsys_error());
@@ -1545,6 +1639,10 @@ int dzb_interface_solve(const double* rows, size_t n_blocks, double* ends) {
   return DZB_OK;
 }
 
+}  // extern "C"
+#include "dzb_comm.inl"
+extern "C" {
+
 // ------------------------------------------------------------------------------------------------- ensembles
 int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double mu, double b, double bc_left, double bc_right,
                            const double* ic, size_t n_ic, size_t G, const dzb_options* opt, dzb_ensemble** out) {
@@ -1558,7 +1656,7 @@ int dzb_ensemble_step(dzb_ensemble* e, double dt, size_t steps) {
     if (rc) return rc;
     s = 1;
     // nobody can observe the intermediate states: keep operator and state on chip for blocks of steps (8 rows per lane only)
-    if (e->fast && e->lean_ok && !e->use_big && e->lean_L <= 8 && !std::getenv("DZB_NO_MULTI_STEP")) {
+    if (e->fast && e->lean_ok && !e->use_big && e->lean_L <= 8 && !g_no_multi_step) {
       while (s < steps) {
         const int blk = (int)std::min<size_t>(steps - s, 1024);
         DISPATCH_LEAN(e, launch_step_lean_multi, e, blk);
@@ -1581,15 +1679,18 @@ int dzb_ensemble_solve(dzb_ensemble* e, double dt, double* out_host, size_t len)
   // Steady state of a large ensemble on the lean path: the bars are stepped in slabs and every slab's 1/8 of the state
   // starts its way to the host (copy stream) while the next slab is still being stepped, so the step hides behind the
   // PCIe transfer instead of preceding it.  Same kernel, same arithmetic; anything else takes the plain path.
-  constexpr size_t SLABS = 8;
-  if (e->fast && e->lean_ok && !e->use_big && e->prepared && e->prepared_dt == dt && e->B >= 256 * SLABS && !std::getenv("DZB_NO_SLAB_COPY")) {
-    static cudaStream_t copy_stream = nullptr;
-    static cudaEvent_t stepped[SLABS] = {}, copied = nullptr;
-    if (!copy_stream) {
-      CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-      for (cudaEvent_t& ev : stepped) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+  if (e->fast && e->lean_ok && !e->use_big && e->prepared && e->prepared_dt == dt && e->B >= 256 * SLABS && !g_no_slab_copy) {
+    DeviceCtx& cx = device_ctx();
+    if (!cx.copy_ready) {  // a failed attempt leaves copy_ready false and is retried from where it stopped
+      if (!cx.copy_stream) CK(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
+      for (cudaEvent_t& ev : cx.stepped)
+        if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      if (!cx.copied) CK(cudaEventCreateWithFlags(&cx.copied, cudaEventDisableTiming));
+      cx.copy_ready = true;
     }
+    cudaStream_t copy_stream = cx.copy_stream;
+    cudaEvent_t* stepped = cx.stepped;
+    cudaEvent_t copied = cx.copied;
     const size_t per = (e->B + SLABS - 1) / SLABS;
     for (size_t k = 0, bar0 = 0; k < SLABS && bar0 < e->B; ++k, bar0 += per) {
       const size_t nb = std::min(per, e->B - bar0);

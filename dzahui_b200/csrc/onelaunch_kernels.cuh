@@ -53,6 +53,8 @@ struct OneLaunchArgs {
   unsigned long long* trace;  // tuning aid (DZB_OL_TRACE=1): [8 gridDim.x] %globaltimer at the phase boundaries of every CTA; nullptr normally
   int* class_flags;  // [0]: k_tri_classify's bits or'ed over every interior row (bit 0: not M-like, bit 1: not mass-like);
                      // [1]: != 0 when some row is outside the closed form.  nullptr: already known for these coordinates
+  PeerBox px;        // world > 1: the system is one block of a bar split across GPUs; its two interface rows go through the
+                     // peer mailboxes (comm_kernels.cuh) between the passes and every rank solves the 2-rows-per-block system
 };
 
 template <int P1C>
@@ -66,6 +68,7 @@ struct OneLaunchSmem {
   double qx[OL_TAB_CAP];
   unsigned short guessf[GUESS_BINS + 2];
   alignas(16) double halo[4];                     // the two values either side of a staged tile (forward: x; backward: [0..1] = 1/h)
+  double xrows[MB_MAX * 8], xends[2 * MB_MAX], xwork[4 * MB_MAX];  // split bar: everybody's interface rows, their solution
   alignas(8) unsigned long long mbar;
 };
 // 16 or 32 bytes next to a staged tile, through the same mbarrier (plain bulk copy: 16-byte aligned, size a multiple of 16)
@@ -424,7 +427,23 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     }
     sm.w.mid.reduce_cold(t, m2);
     LevelPtr top = sm.w.mid.top();
-    if (t == 0) {  // closed 2 x 2 system (a_0 = c_1 = 0), as in mid_body
+    if (a.px.world > 1) {
+      // One block of a split bar: its two rows keep their couplings to the neighbouring blocks.  CTA 0 posts them to every
+      // rank (every CTA holds the same bits), every CTA collects all of them from the local mailbox and solves the
+      // 2-rows-per-block interface system for itself: no launch, no host, one NVLink store + flag per peer.
+      if (t < a.px.world) {
+        if (blockIdx.x == 0) {
+          const double v[8] = {top.a[0], top.c[0], top.s[0], top.d[0], top.a[1], top.c[1], top.s[1], top.d[1]};
+          mb_post(a.px, t, v);
+        }
+        mb_wait(a.px, t, sm.xrows + 8 * t);
+      }
+      __syncthreads();
+      if (t == 0) {
+        interface_solve_serial(sm.xrows, 2 * a.px.world, sm.xends, sm.xwork);
+        top.d[0] = sm.xends[2 * a.px.rank], top.d[1] = sm.xends[2 * a.px.rank + 1];
+      }
+    } else if (t == 0) {  // closed 2 x 2 system (a_0 = c_1 = 0), as in mid_body
       const double c0 = top.c[0], s0 = top.s[0], f0 = top.d[0], a1 = top.a[1], s1 = top.s[1], f1 = top.d[1];
       const double det = (s0 * s1 - s0 * a1) - c0 * s1;
       top.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;

@@ -7,8 +7,11 @@
   solves the 2P-row interface system redundantly on the host, and back-substitutes locally.  Optional refinement sweeps
   add one all-gather of the block edge values (the residual's halo) and one more of interface rows per sweep.
 
-Collectives go through `torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests).  `LocalComm` runs
-all blocks in one process — what a single-GPU test uses to exercise the block kernels."""
+Two drivers.  `SplitBarTimeIndependent` + `NativeComm` is the production one: the communicator lives inside the C library
+(dzb_comm_*: NCCL bound at run time plus NVLink peer mailboxes), a solve is ONE collective C call per rank
+(dzb_solver_block_solve_device) and, with closed-form assembly, one kernel launch per rank.  The older step-by-step driver
+(`spike_solve`, `DeviceSpike`) moves the interface rows through `torch.distributed` (NCCL on the GPU box, gloo in the CPU
+tests); `LocalComm` runs all blocks in one process — what a single-GPU test uses to exercise the block kernels."""
 import ctypes as C
 
 import numpy as np
@@ -274,3 +277,106 @@ class DistributedBarTimeIndependent:
         for b in self.blocks:
             b.close()
         self.blocks = []
+
+
+# ---------------------------------------------------------------------------------------------- native communicator
+COMM_ID_BYTES = 128
+
+
+class NativeComm:
+    """dzb_comm: the library's own communicator (include/dzahui_b200.h).  `NativeComm.from_torch()` takes rank / world from
+    the default torch.distributed group and ships rank 0's 128-byte id through it — the one thing the host has to do;
+    `NativeComm(id_bytes, rank, world)` is the same for a host that moved the id some other way (a Rust host: MPI, a
+    file).  world == 1 needs no id and no NCCL."""
+
+    def __init__(self, unique_id, rank, world):
+        self._lib = _lib.load()
+        self._h = None
+        h = C.c_void_p()
+        check(self._lib.dzb_comm_init(unique_id, int(rank), int(world), C.byref(h)), self._lib)
+        self._h = h
+        self.rank, self.world = int(rank), int(world)
+        pm = C.c_int()
+        check(self._lib.dzb_comm_info(h, None, None, C.byref(pm)), self._lib)
+        self.peer_mailboxes = bool(pm.value)
+
+    @staticmethod
+    def unique_id():
+        lib = _lib.load()
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        check(lib.dzb_comm_unique_id(buf), lib)
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, group=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            return cls(None, 0, 1)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(box[0], rank, world)
+
+    def all_gather(self, d_send, d_recv, count):
+        """ncclAllGather of `count` doubles per rank between device pointers, on the library's stream"""
+        check(self._lib.dzb_comm_all_gather(self._h, C.c_void_p(int(d_send)), C.c_void_p(int(d_recv)), int(count)), self._lib)
+
+    def close(self):
+        if self._h:
+            self._lib.dzb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SplitBarTimeIndependent:
+    """`DiffussionSolverTimeIndependent` (time_independent.rs:46-53) for ONE bar split into row blocks, one per rank of a
+    `NativeComm`.  `mesh` is the whole bar's node array (every rank slices its block + halo nodes from it).
+    `rebuild()` + `solve_device()` is one assemble + solve step; nothing in them waits for the host."""
+
+    def __init__(self, params, mesh, gauss_step, comm, options=None):
+        self.comm = comm
+        mesh = np.asarray(mesh, dtype=np.float64)
+        self.n_total = len(mesh)
+        self.partition = partition_rows(self.n_total, comm.world)
+        self.rows = self.partition[comm.rank]
+        nodes, hl, hr = block_nodes(mesh, *self.rows)
+        self.block = BarBlock(params, nodes, hl, hr, gauss_step, options)
+        self._lib = self.block._lib
+
+    def rebuild(self, nodes_with_halo=None):
+        """XSolver::new again into the block's buffers; `nodes_with_halo`: new coordinates of the block (own + halo nodes)"""
+        b = self.block
+        if nodes_with_halo is not None:
+            b._mesh.set_nodes(nodes_with_halo)
+        check(self._lib.dzb_solver_block_rebuild(b._h, b._mesh._h), self._lib)
+
+    def solve_device(self):
+        """collective: every rank calls it; returns the device pointer of this block's nodal values"""
+        p = C.c_void_p()
+        check(self._lib.dzb_solver_block_solve_device(self.block._h, self.comm._h, C.byref(p)), self._lib)
+        return p.value
+
+    def status(self):
+        """synchronises; raises if a collective solve since the last call went wrong on this rank"""
+        check(self._lib.dzb_solver_block_status(self.block._h, self.comm._h), self._lib)
+
+    def solve(self, _time_step=0.0):
+        """nodal values of this rank's rows [self.rows[0], self.rows[1])"""
+        self.solve_device()
+        self.status()
+        return self.block.block_read()
+
+    def path(self):
+        buf = C.create_string_buffer(160)
+        check(self._lib.dzb_solver_path(self.block._h, buf, 160), self._lib)
+        return buf.value.decode()
+
+    def close(self):
+        if self.block is not None:
+            self.block.close()
+            self.block = None

@@ -177,6 +177,36 @@ int dzb_solver_block_edges_device(const dzb_solver* s, double* d_edges2);
 int dzb_solver_block_residual_device(dzb_solver* s, const double* d_left, const double* d_right);
 int dzb_solver_block_device_solution(const dzb_solver* s, const double** device_ptr);
 
+/* ---- the split bar as ONE collective call per rank: the communicator lives in the library ---------------------- */
+/* One process per GPU (at most 8 ranks: one NVSwitch box).  Rank 0 makes the id and ships its 128 bytes to the other
+ * ranks by whatever the host has (MPI, a file, a socket); every rank then calls dzb_comm_init after dzb_set_device.
+ * The library binds NCCL at run time (libnccl.so.2), so a Rust host needs no NCCL binding of its own.  Besides the NCCL
+ * communicator, init maps a small mailbox of every rank into every other rank (cudaIpc*, NVLink peer access): where that
+ * works (dzb_comm_info: peer_mailboxes = 1) the 8 doubles per rank of a solve travel as peer stores + a flag from INSIDE
+ * the kernels and no collective is launched at all; otherwise they go through ncclAllGather on the library's stream. */
+#define DZB_COMM_ID_BYTES 128
+typedef struct dzb_comm dzb_comm;
+int dzb_comm_unique_id(unsigned char id[DZB_COMM_ID_BYTES]);
+int dzb_comm_init(const unsigned char id[DZB_COMM_ID_BYTES], int rank, int world, dzb_comm** out); /* collective; id may be NULL when world == 1 */
+int dzb_comm_info(const dzb_comm* c, int* rank, int* world, int* peer_mailboxes);
+int dzb_comm_all_gather(dzb_comm* c, const double* d_send, double* d_recv, size_t count_per_rank); /* device pointers, the library's stream */
+void dzb_comm_destroy(dzb_comm* c);
+/* XSolver::new again for a block (time_independent.rs:57-71), into the buffers it owns: `m` = the block's nodes + halo
+ * nodes as at creation, current coordinates.  The "assemble" half of a step; a no-op but for a coordinate copy when the
+ * block forms its rows inside the solve (DZB_ASSEMBLY_FAST). */
+int dzb_solver_block_rebuild(dzb_solver* s, const dzb_mesh* m);
+/* DiffEquationSolver::solve for the split bar (solver_trait.rs:23; ONE solve_by_thomas over the whole system in the
+ * reference, matrix_solver/mod.rs:17-48).  Collective: every rank of `c` calls it with its block (rank r owns the r-th
+ * block).  Block elimination, exchange of the interface rows, interface solve (redundantly on every rank) and
+ * back-substitution are queued on the library's stream without any host synchronisation; with DZB_ASSEMBLY_FAST and peer
+ * mailboxes the whole assemble + solve of a rank is ONE kernel launch.  refine_steps of the block's options add one
+ * exchange of edge values + one more solve each.  *device_ptr (may be NULL) = the block's nodal values on the device. */
+int dzb_solver_block_solve_device(dzb_solver* s, dzb_comm* c, const double** device_ptr);
+/* Synchronises and reports what the collective solves since the last call left behind: DZB_CUDA when some rank's rows never
+ * arrived (time-out instead of a hang), DZB_INVALID when new coordinates made the block's matrix unfit for the partitioned
+ * elimination or left a row outside the closed form. */
+int dzb_solver_block_status(dzb_solver* s, dzb_comm* c);
+
 /* ---- CSV snapshots: Writer (writer.rs:47-146), host code ------------------------------------------------------- */
 /* `f64::to_string()` of Rust: shortest round-trip digits, never an exponent, "1" for 1.0, "-0", "NaN", "inf". */
 int dzb_format_f64(double v, char* buf, size_t cap);
