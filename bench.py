@@ -636,6 +636,34 @@ def main():
                "ms_per_step": e2e_s / e2e_steps * 1e3}
         extra["e2e_including_create"] = {"value": dof * world * e2e_steps / (e2e_s + extra["create_s"]), "unit": UNIT,
                                          "steps": e2e_steps, "create_s": extra["create_s"]}
+        # the same call with the states cast to f32 on the device first (what the reference's renderer uploads): half the bytes
+        host32 = torch.empty(dof, dtype=torch.float32, pin_memory=True)
+        step_f32 = lambda: solver.solve_f32(C5_DT, host32.data_ptr())
+        for _ in range(3):
+            step_f32()
+        barrier()
+        k32 = max(5, e2e_steps // 2)
+        t0 = time.perf_counter()
+        for _ in range(k32):
+            step_f32()
+        torch.cuda.synchronize()
+        s32 = max_over_ranks(time.perf_counter() - t0)
+        extra["e2e_f32"] = {"call": "dzb_ensemble_solve_f32(dt, host_out_f32)", "value": dof * world * k32 / s32, "unit": UNIT,
+                            "ms_per_step": s32 / k32 * 1e3, "d2h_bytes_per_step": dof * 4, "steps": k32}
+        # what bounds both: a bare pinned D2H copy of the same bytes, no kernels, every rank at once (tools/d2h_probe.py)
+        dev_probe = torch.empty(dof * 8, dtype=torch.uint8, device="cuda")
+        host_view = host_out.view(torch.uint8)
+        host_view.copy_(dev_probe, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            host_view.copy_(dev_probe, non_blocking=True)
+        torch.cuda.synchronize()
+        sp = max_over_ranks(time.perf_counter() - t0) / 5
+        extra["e2e_limiter"] = {"what": "bare cudaMemcpyAsync of one step's result (device -> pinned host), all ranks at once, no kernels",
+                                "ms_per_copy": sp * 1e3, "GBps_per_rank": dof * 8 / sp / 1e9, "GBps_aggregate": world * dof * 8 / sp / 1e9,
+                                "e2e_step_over_bare_copy": e2e["ms_per_step"] / (sp * 1e3)}
+        del dev_probe, host32
         solver.close()
         del host_out
     else:

@@ -96,6 +96,7 @@ SIGNATURES = {
                                          C.POINTER(C.c_void_p)]),
     "dzb_ensemble_step": (C.c_int, [C.c_void_p, C.c_double, C.c_size_t]),
     "dzb_ensemble_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_size_t]),
+    "dzb_ensemble_solve_f32": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_size_t]),
     "dzb_ensemble_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "dzb_ensemble_read_bars": (C.c_int, [C.c_void_p, c_size_p, C.c_size_t, c_double_p]),
     "dzb_ensemble_state_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

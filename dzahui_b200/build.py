@@ -24,12 +24,29 @@ def _nvcc():
     return "nvcc"
 
 
+STAMP = OUT + ".srchash"
+
+
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS) + [os.path.abspath(__file__)]:
+        path = f if os.path.isabs(f) else os.path.join(CSRC, f)
+        if os.path.exists(path):
+            h.update(f.encode())
+            with open(path, "rb") as fh:
+                h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(OUT):
+    """True when the library is missing or was built from other sources than the ones in the tree (by content, not by
+    mtime: a copy of the tree — the GPU box's snapshot — keeps contents but not time stamps)."""
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -48,6 +65,8 @@ def build(force=False, verbose=False):
         print(r.stdout)
     if r.returncode:
         raise RuntimeError(f"nvcc failed (see {log})")
+    with open(STAMP, "w") as f:
+        f.write(_source_hash() + "\n")
     return OUT
 
 

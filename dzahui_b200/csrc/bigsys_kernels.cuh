@@ -896,11 +896,14 @@ __global__ void __launch_bounds__(256) k_residual_dd(const double* __restrict__ 
 // for a strictly dominant matrix with positive couplings (the mass matrix); on an indefinite system (e.g. the reference's
 // kink-straddling quadrature on a strongly irregular mesh, or a cell Peclet number above 1) the local problems can be
 // nearly singular while the serial recurrence, which always carries the left boundary along, is not.
-// flags: bit 0 set = not M-like, bit 1 set = not mass-like.  Interior rows only.
+// flags: bit 0 set = not M-like, bit 1 set = not mass-like.  Interior rows only: rows 1 .. n-2 of a closed system; at an open
+// end (a block of a longer bar, BS_OPEN_LEFT / BS_OPEN_RIGHT) the block's first / last row is an interior row of the bar too.
 __global__ void __launch_bounds__(256) k_tri_classify(const double* __restrict__ lo, const double* __restrict__ di,
-                                                      const double* __restrict__ up, long long n, int* __restrict__ flags) {
+                                                      const double* __restrict__ up, long long n, int* __restrict__ flags,
+                                                      int open_ends) {
   int f = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n - 1; i += (long long)gridDim.x * blockDim.x) {
+  const long long first = (open_ends & BS_OPEN_LEFT) ? 0 : 1, last = (open_ends & BS_OPEN_RIGHT) ? n : n - 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + first; i < last; i += (long long)gridDim.x * blockDim.x) {
     const double a = lo[i], b = di[i], c = up[i];
     if (!(a <= 0.0 && c <= 0.0 && excess3(a, b, c) >= -1e-6 * b)) f |= 1;
     if (!(a >= 0.0 && c >= 0.0 && b >= 1.25 * (a + c))) f |= 2;

@@ -25,9 +25,9 @@ struct PeerBox {
   double* box[MB_MAX];          // every rank's mailbox as mapped into this process (box[rank] is the local one)
   int rank, world;              // world <= 1: no exchange
   unsigned long long epoch;     // of this exchange
-  int* err;                     // set to 1 when a record did not arrive within MB_TIMEOUT_NS (a rank that never launched)
+  int* err;                     // set to 1 when a record did not arrive within timeout_ns (a rank that never launched)
+  unsigned long long timeout_ns;
 };
-constexpr unsigned long long MB_TIMEOUT_NS = 4000000000ULL;
 
 __device__ __forceinline__ unsigned long long mb_now() {
   unsigned long long ns;
@@ -61,7 +61,7 @@ __device__ __forceinline__ void mb_wait(const PeerBox& px, int src, double* dst)
   const unsigned long long t0 = mb_now();
   unsigned spin = 0;
   while (mb_load_flag(rec) != px.epoch) {
-    if ((++spin & 1023u) == 0 && mb_now() - t0 > MB_TIMEOUT_NS) {  // an error after a few seconds, not a hang
+    if ((++spin & 1023u) == 0 && mb_now() - t0 > px.timeout_ns) {  // an error after the time-out, not a hang
       if (px.err) atomicExch(px.err, 1);
       break;
     }

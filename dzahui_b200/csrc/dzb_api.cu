@@ -227,6 +227,20 @@ __global__ void k_td_init_state(const double* __restrict__ ic, double* __restric
   const long long bar = g / n, i = g - bar * n;
   u[g] = i == 0 ? bc0 : (i == n - 1 ? bc1 : ic[bar * (n - 2) + i - 1]);
 }
+// f64 -> f32 of a slab of states (Drawable::get_vertices' cast, mesh/mod.rs:108-113), two values per thread.  u and out are
+// the same element offset into 256-byte aligned allocations: an odd offset leaves one scalar element in front of the pairs.
+__global__ void __launch_bounds__(256) k_cast_f32(const double* __restrict__ u, float* __restrict__ out, long long n) {
+  const long long head = (reinterpret_cast<size_t>(u) >> 3) & 1;
+  if (head && blockIdx.x == 0 && threadIdx.x == 0 && n > 0) out[0] = (float)u[0];
+  for (long long i = head + 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 2LL * gridDim.x * blockDim.x) {
+    if (i + 1 < n) {
+      const double2 v = *reinterpret_cast<const double2*>(u + i);
+      *reinterpret_cast<float2*>(out + i) = make_float2((float)v.x, (float)v.y);
+    } else {
+      out[i] = (float)u[i];
+    }
+  }
+}
 // GL vertex / index / element tables from the sorted nodes (mesh_builder.rs:249-253, :278-307)
 __global__ void k_mesh_tables(const double* __restrict__ nodes, long long n, double prom_width, double* __restrict__ vertices,
                               uint32_t* __restrict__ indices, uint32_t* __restrict__ elements) {
@@ -344,6 +358,7 @@ struct dzb_ensemble {
   bool lean_ok = false;   // the lean step applies (no row needed the quadrature-loop fallback); decided at prepare time
   dzb::LeanConsts lean_k{};
   double* u[2] = {nullptr, nullptr};
+  float* u32 = nullptr;  // dzb_ensemble_solve_f32: the state as f32, what a renderer uploads (mesh/mod.rs:108-113)
   int cur = 0;
   bool prepared = false;
   double prepared_dt = 0.0;
@@ -420,6 +435,7 @@ void ensemble_free(dzb_ensemble* e) {
                      &e->a_up, &e->alpha, &e->cc, &e->u[0], &e->u[1], &e->bdi, &e->idn, &e->hh})
     dfree(*p);
   if (e->d_bad) cudaFree(e->d_bad), e->d_bad = nullptr;
+  if (e->u32) cudaFree(e->u32), e->u32 = nullptr;
   dzb::bigsys_free(&e->big);
   delete e;
 }
@@ -597,11 +613,11 @@ int ensemble_step_once(dzb_ensemble* e, double dt) {
 }
 
 // true when the partitioned solver is reliable on (lo, di, up): an M-matrix or a strictly dominant positive one
-int tri_parallel_ok(const double* lo, const double* di, const double* up, size_t n, bool* ok) {
+int tri_parallel_ok(const double* lo, const double* di, const double* up, size_t n, bool* ok, int open_ends = 0) {
   int*& d_flags = device_ctx().d_flags;
   if (!d_flags) CK(cudaMalloc((void**)&d_flags, sizeof(int)));
   CK(cudaMemsetAsync(d_flags, 0, sizeof(int), g_stream));
-  dzb::k_tri_classify<<<dzb::bigsys_grid(n), 256, 0, g_stream>>>(lo, di, up, (long long)n, d_flags);
+  dzb::k_tri_classify<<<dzb::bigsys_grid(n), 256, 0, g_stream>>>(lo, di, up, (long long)n, d_flags, open_ends);
   LAUNCHED();
   int f = 0;
   CK(cudaMemcpyAsync(&f, d_flags, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
@@ -624,9 +640,17 @@ int ensemble_assemble(dzb_ensemble* e) {
     if ((long long)e->B <= tw_max_bars() && !e->rden && (rc = dalloc(&e->rden, e->B * e->n))) return rc;
     if ((long long)e->B <= tw_max_bars())
       dzb::k_thomas_factor_warp<<<(unsigned)e->B, 32, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, e->rden, (long long)e->n);
-    else
-      dzb::k_thomas_factor<<<blocks_for((long long)e->B, 64), 64, 0, g_stream>>>(e->mlo, e->mdi, e->mup, e->c, e->den, (long long)e->n,
-                                                                                (long long)e->B);
+    else {  // many bars: a warp per 32 bars over padded shared-memory tiles (coalesced; same arithmetic as k_thomas_factor)
+      static dzb::PerDevice<char> attr;
+      bool fresh;
+      attr.slot(&fresh);
+      if (fresh && cudaFuncSetAttribute(dzb::k_thomas_factor_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dzb::TF_SMEM) != cudaSuccess) {
+        attr.forget();
+        return fail(DZB_CUDA, "cudaFuncSetAttribute(k_thomas_factor_tile)");
+      }
+      dzb::k_thomas_factor_tile<<<blocks_for((long long)e->B, 32 * dzb::TF_WARPS), 32 * dzb::TF_WARPS, dzb::TF_SMEM, g_stream>>>(
+          e->mlo, e->mdi, e->mup, e->c, e->den, (long long)e->n, (long long)e->B);
+    }
     LAUNCHED();
   }
   e->prepared = false;
@@ -908,6 +932,7 @@ struct dzb_mesh2d {
 static int boundary_vertices_device(const uint32_t* d_tri, size_t n_tri, size_t n_vert, uint32_t* d_out, size_t* n_out) {
   *n_out = 0;
   if (n_tri == 0 || n_vert == 0) return DZB_OK;
+  if (n_vert > 0xfffffffeull) return fail(DZB_WRONG_DIMS, "more vertices than a u32 index can address");  // (0xffffffff, 0xffffffff) is the empty-slot key
   unsigned long long slots = 1024;
   while (slots < 8ull * n_tri) slots <<= 1;  // 3 T edges at most -> load factor <= 0.375
   unsigned long long* keys = nullptr;
@@ -932,12 +957,13 @@ static int boundary_vertices_device(const uint32_t* d_tri, size_t n_tri, size_t 
   CK2(cudaMalloc((void**)&cnt, slots * sizeof(unsigned)));
   CK2(cudaMalloc((void**)&flag, n_vert));
   CK2(cudaMalloc((void**)&blk, nblk * sizeof(unsigned)));
-  CK2(cudaMalloc((void**)&d_total, sizeof(unsigned long long)));
+  CK2(cudaMalloc((void**)&d_total, 2 * sizeof(unsigned long long)));  // [0] boundary vertices, [1] edges with an index out of range
+  CK2(cudaMemsetAsync(d_total, 0, 2 * sizeof(unsigned long long), g_stream));
   CK2(cudaMemsetAsync(keys, 0xff, slots * sizeof(unsigned long long), g_stream));
   CK2(cudaMemsetAsync(cnt, 0, slots * sizeof(unsigned), g_stream));
   CK2(cudaMemsetAsync(flag, 0, n_vert, g_stream));
   const unsigned grid_e = (unsigned)std::min<unsigned long long>((3ull * n_tri + 255) / 256, 148ull * 32);
-  dzb::k_edge_count<<<grid_e, 256, 0, g_stream>>>(d_tri, (long long)n_tri, keys, cnt, slots - 1);
+  dzb::k_edge_count<<<grid_e, 256, 0, g_stream>>>(d_tri, (long long)n_tri, (uint32_t)n_vert, keys, cnt, slots - 1, d_total + 1);
   ++g_launches;
   const unsigned grid_s = (unsigned)std::min<unsigned long long>((slots + 255) / 256, 148ull * 32);
   dzb::k_edge_flag<<<grid_s, 256, 0, g_stream>>>(keys, cnt, slots, flag);
@@ -948,13 +974,14 @@ static int boundary_vertices_device(const uint32_t* d_tri, size_t n_tri, size_t 
   ++g_launches;
   dzb::k_flag_scatter<<<(unsigned)nblk, 256, 0, g_stream>>>(flag, (long long)n_vert, blk, d_out);
   ++g_launches;
-  unsigned long long total = 0;
-  CK2(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, g_stream));
+  unsigned long long total[2] = {0, 0};
+  CK2(cudaMemcpyAsync(total, d_total, sizeof total, cudaMemcpyDeviceToHost, g_stream));
   CK2(cudaStreamSynchronize(g_stream));
   CK2(cudaGetLastError());
 #undef CK2
   cleanup();
-  *n_out = (size_t)total;
+  if (total[1]) return fail(DZB_MESH_PARSE, "a triangle refers to a vertex that does not exist");
+  *n_out = (size_t)total[0];
   return rc;
 }
 
@@ -1460,7 +1487,7 @@ int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right
   }
   if (!rc) {
     bool ok = false;
-    rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok);
+    rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok, s->block_flags);
     if (!rc && !ok)
       rc = fail(DZB_INVALID, "the block's matrix is neither an M-matrix nor strictly dominant: the partitioned (SPIKE) solver "
                              "is not reliable on it; solve the bar on one GPU (serial recurrence)");
@@ -1514,7 +1541,7 @@ int dzb_solver_block_rebuild(dzb_solver* s, const dzb_mesh* m) {
   s->x_version = m->version;
   if (!(s->classified_valid && s->classified_version == m->version)) {  // new coordinates: is the block still one the
     bool ok = false;                                                     // partitioned elimination is reliable on?
-    if ((rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok))) return rc;
+    if ((rc = tri_parallel_ok(s->lo, s->di, s->up, s->n, &ok, s->block_flags))) return rc;
     s->classified_valid = true, s->classified_version = m->version, s->classified_ok = ok;
     if (!ok) return fail(DZB_INVALID, "the block's matrix is neither an M-matrix nor strictly dominant");
   }
@@ -1672,10 +1699,17 @@ int dzb_ensemble_step(dzb_ensemble* e, double dt, size_t steps) {
   }
   return DZB_OK;
 }
-int dzb_ensemble_solve(dzb_ensemble* e, double dt, double* out_host, size_t len) {
-  if (!e || !out_host) return fail(DZB_INVALID, "null pointer");
+// one solve(dt) on every bar, all states to the host: as f64 (out64) or cast to f32 on the device first (out32)
+static int ensemble_solve_impl(dzb_ensemble* e, double dt, double* out64, float* out32, size_t len) {
+  if (!e || (!out64 && !out32)) return fail(DZB_INVALID, "null pointer");
   if (len != e->B * e->n) return fail(DZB_WRONG_DIMS, "output length != n_bars * n");
   int rc = DZB_OK;
+  if (out32 && !e->u32) CK(cudaMalloc((void**)&e->u32, len * sizeof(float)));
+  auto cast_slab = [&](const double* state, size_t first, size_t count) {  // state[first, first + count) -> e->u32
+    const unsigned grid = (unsigned)std::min<size_t>((count / 2 + 255) / 256 + 1, 148 * 8);
+    k_cast_f32<<<grid, 256, 0, g_stream>>>(state + first, e->u32 + first, (long long)count);
+    ++g_launches;
+  };
   // Steady state of a large ensemble on the lean path: the bars are stepped in slabs and every slab's 1/8 of the state
   // starts its way to the host (copy stream) while the next slab is still being stepped, so the step hides behind the
   // PCIe transfer instead of preceding it.  Same kernel, same arithmetic; anything else takes the plain path.
@@ -1696,10 +1730,14 @@ int dzb_ensemble_solve(dzb_ensemble* e, double dt, double* out_host, size_t len)
       const size_t nb = std::min(per, e->B - bar0);
       DISPATCH_LEAN(e, launch_step_lean_slab, e, bar0, nb);
       if (rc) return rc;
+      if (out32) cast_slab(e->u[e->cur ^ 1], bar0 * e->n, nb * e->n);
       CK(cudaEventRecord(stepped[k], g_stream));
       CK(cudaStreamWaitEvent(copy_stream, stepped[k], 0));
-      CK(cudaMemcpyAsync(out_host + bar0 * e->n, e->u[e->cur ^ 1] + bar0 * e->n, nb * e->n * sizeof(double), cudaMemcpyDeviceToHost,
-                         copy_stream));
+      if (out32)
+        CK(cudaMemcpyAsync(out32 + bar0 * e->n, e->u32 + bar0 * e->n, nb * e->n * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+      else
+        CK(cudaMemcpyAsync(out64 + bar0 * e->n, e->u[e->cur ^ 1] + bar0 * e->n, nb * e->n * sizeof(double), cudaMemcpyDeviceToHost,
+                           copy_stream));
     }
     e->cur ^= 1;
     CK(cudaEventRecord(copied, copy_stream));
@@ -1709,8 +1747,22 @@ int dzb_ensemble_solve(dzb_ensemble* e, double dt, double* out_host, size_t len)
   }
   rc = ensemble_step_once(e, dt);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(out_host, e->u[e->cur], len * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  if (out32) {
+    cast_slab(e->u[e->cur], 0, len);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out32, e->u32, len * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+  } else {
+    CK(cudaMemcpyAsync(out64, e->u[e->cur], len * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  }
   return sync_stream();
+}
+int dzb_ensemble_solve(dzb_ensemble* e, double dt, double* out_host, size_t len) {
+  if (!out_host) return fail(DZB_INVALID, "null pointer");
+  return ensemble_solve_impl(e, dt, out_host, nullptr, len);
+}
+int dzb_ensemble_solve_f32(dzb_ensemble* e, double dt, float* out_host, size_t len) {
+  if (!out_host) return fail(DZB_INVALID, "null pointer");
+  return ensemble_solve_impl(e, dt, nullptr, out_host, len);
 }
 int dzb_ensemble_state(const dzb_ensemble* e, double* out_host, size_t len) {
   if (!e || !out_host) return fail(DZB_INVALID, "null pointer");

@@ -50,6 +50,7 @@ struct dzb_comm {
   bool peer_ok = false;                    // every rank mapped every other rank's mailbox
   unsigned long long epoch = 0;            // exchanges made so far (the same on every rank)
   int* d_err = nullptr;                    // set by a mailbox wait that timed out
+  unsigned long long timeout_ns = 30000000000ULL;  // DZB_COMM_TIMEOUT_S: how far apart the ranks may make the same call
   // scratch of the materialised path
   double *d_top8 = nullptr, *d_rows = nullptr, *d_ends = nullptr, *d_work = nullptr, *d_ends2 = nullptr, *d_edge8 = nullptr,
          *d_edges = nullptr;
@@ -60,7 +61,7 @@ namespace {
 dzb::PeerBox comm_peerbox(dzb_comm* c) {  // the next exchange
   dzb::PeerBox px{};
   for (int r = 0; r < c->world; ++r) px.box[r] = c->peer[r];
-  px.rank = c->rank, px.world = c->world, px.epoch = ++c->epoch, px.err = c->d_err;
+  px.rank = c->rank, px.world = c->world, px.epoch = ++c->epoch, px.err = c->d_err, px.timeout_ns = c->timeout_ns;
   return px;
 }
 __global__ void k_block_edges(const double* __restrict__ u, long long n, double* __restrict__ edge8) {
@@ -116,6 +117,7 @@ int dzb_comm_init(const unsigned char id[DZB_COMM_ID_BYTES], int rank, int world
   if (world > 1 && !id) return fail(DZB_INVALID, "null unique id");
   dzb_comm* c = new dzb_comm;
   c->rank = rank, c->world = world;
+  if (const char* t = std::getenv("DZB_COMM_TIMEOUT_S")) c->timeout_ns = (unsigned long long)(std::max(0.001, std::atof(t)) * 1e9);
   auto bail = [&](int code) {
     const std::string msg = g_err;
     dzb_comm_destroy(c);

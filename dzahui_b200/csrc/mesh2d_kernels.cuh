@@ -23,13 +23,19 @@ __device__ __forceinline__ unsigned long long m2_hash(unsigned long long k) {  /
 }
 
 // edges of triangle t: (t0,t1), (t0,t2), (t2,t1) as in mesh_builder.rs:417-446
-__global__ void __launch_bounds__(256) k_edge_count(const uint32_t* __restrict__ tri, long long n_tri,
+// An index >= n_vert (a caller-supplied triangle list is not trusted) never reaches the table — k_edge_flag would write
+// flag[] out of bounds with it — and is reported through *bad instead.
+__global__ void __launch_bounds__(256) k_edge_count(const uint32_t* __restrict__ tri, long long n_tri, uint32_t n_vert,
                                                     unsigned long long* __restrict__ keys, unsigned* __restrict__ cnt,
-                                                    unsigned long long mask) {
+                                                    unsigned long long mask, unsigned long long* __restrict__ bad) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < 3 * n_tri; e += (long long)gridDim.x * blockDim.x) {
     const long long t = e / 3;
     const int k = (int)(e - 3 * t);
     const uint32_t p = tri[3 * t + (k == 2 ? 2 : 0)], q = tri[3 * t + (k == 0 ? 1 : (k == 1 ? 2 : 1))];
+    if (p >= n_vert || q >= n_vert) {
+      atomicAdd(bad, 1ull);
+      continue;
+    }
     const unsigned long long key = ((unsigned long long)min(p, q) << 32) | (unsigned long long)max(p, q);
     unsigned long long h = m2_hash(key) & mask;
     for (;;) {

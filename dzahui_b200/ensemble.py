@@ -46,6 +46,15 @@ class EnsembleTimeDependent:
     def solve_into(self, time_step, host_ptr):
         check(self._lib.dzb_ensemble_solve(self._h, float(time_step), C.c_void_p(int(host_ptr)), self.n_bars * self.n), self._lib)
 
+    def solve_f32(self, time_step, out=None):
+        """One solve(time_step) on every bar; the states come back cast to f32 on the device (half the PCIe bytes): what the
+        reference's renderer uploads (mesh/mod.rs:108-113).  `out`: float32 array [n_bars][n] or a raw (pinned) host pointer."""
+        if out is None:
+            out = np.empty((self.n_bars, self.n), dtype=np.float32)
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else int(out)
+        check(self._lib.dzb_ensemble_solve_f32(self._h, float(time_step), C.c_void_p(ptr), self.n_bars * self.n), self._lib)
+        return out
+
     def state(self, out=None):
         if out is None:
             out = np.empty((self.n_bars, self.n), dtype=np.float64)

@@ -225,6 +225,10 @@ int dzb_ensemble_td_create(const double* meshes, size_t n_bars, size_t n, double
 int dzb_ensemble_step(dzb_ensemble* e, double time_step, size_t steps);
 /* one solve(time_step) on every bar; out_host[n_bars][n] holds all states on return (use dzb_host_alloc memory for PCIe speed) */
 int dzb_ensemble_solve(dzb_ensemble* e, double time_step, double* out_host, size_t len);
+/* the same step with the states cast to f32 on the device before they cross PCIe (half the bytes): what a renderer
+ * uploads anyway — Drawable::get_vertices casts every f64 to f32 for the GL buffer (mesh/mod.rs:108-113).  The device state
+ * stays f64; out_host[n_bars][n] receives (float)u. */
+int dzb_ensemble_solve_f32(dzb_ensemble* e, double time_step, float* out_host, size_t len);
 int dzb_ensemble_state(const dzb_ensemble* e, double* out_host, size_t len);
 int dzb_ensemble_read_bars(const dzb_ensemble* e, const size_t* bar_ids, size_t count, double* out_host);
 int dzb_ensemble_state_device(const dzb_ensemble* e, const double** device_ptr); /* bar-major [n_bars][n] */

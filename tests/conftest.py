@@ -39,7 +39,7 @@ def dz():
     sys.path.insert(0, ROOT)
     import dzahui_b200
     from dzahui_b200 import _lib, build
-    if not os.path.exists(_lib.SO_PATH):
-        build.build()
+    if not os.environ.get("DZB_LIB"):
+        build.build()   # no-op unless the library is missing or its sources changed since it was built (content hash)
     _lib.load()
     return dzahui_b200

@@ -1,3 +1,4 @@
-python -m pytest tests/test_gpu_split_bar.py -x -q 2>&1 | tail -15 > gpurun_out/r2n_tests.txt
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5 >> gpurun_out/r2n_tests.txt
-python tools/split_bar_check.py --nodes 1000003 10000000 > gpurun_out/r2n_split1.txt 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2p_tests.txt
+python bench.py > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err
+python tools/d2h_probe.py > gpurun_out/r2p_d2h.json 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file gpurun_out/r2p_launches_create.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-extra > /dev/null 2>&1
