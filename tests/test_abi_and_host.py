@@ -200,3 +200,43 @@ def test_header_is_plain_c(tmp_path):
     src.write_text('#include "dzahui_b200.h"\nint main(void) { dzb_options o; dzb_mesh* m = 0; (void)o; (void)m; return DZB_OK; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                            str(src)])
+
+
+def test_rust_shim_matches_header():
+    """INTEGRATION.md's `extern "C"` block is uncompiled (no rustc in the image): keep it honest mechanically.  Every
+    `pub fn dzb_*` it declares must exist in include/dzahui_b200.h with the same number of parameters, and the Rust
+    `DzbOptions` must list the header's `dzb_options` fields in the header's order."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "dzahui_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    rust = doc[doc.index('extern "C" {'):]
+    rust = rust[:rust.index("\n}\n")]
+    rust = re.sub(r"//[^\n]*", "", rust)
+
+    def split_args(text):           # top-level commas only (a Rust fn-pointer parameter has commas of its own)
+        out, depth, cur = [], 0, ""
+        for ch in text:
+            depth += ch == "("
+            depth -= ch == ")"
+            if ch == "," and depth == 0:
+                out.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        return [a for a in out + [cur] if a.strip() and a.strip() != "void"]
+
+    c_fns = {m.group(1): split_args(m.group(2)) for m in re.finditer(r"\b(dzb_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)}
+    r_fns = {m.group(1): split_args(m.group(2)) for m in re.finditer(r"pub fn (dzb_\w+)\s*\((.*?)\)\s*(?:->\s*[\w:* ]+)?;", rust, flags=re.S)}
+    assert len(r_fns) >= 30
+    for name, args in r_fns.items():
+        assert name in c_fns, f"{name} is not in the header"
+        assert len(args) == len(c_fns[name]), f"{name}: {len(args)} parameters in the Rust block, {len(c_fns[name])} in the header"
+    c_opt = re.search(r"typedef struct dzb_options \{(.*?)\} dzb_options;", hdr, flags=re.S).group(1)
+    c_fields = re.findall(r"int\s+(\w+)\s*;", c_opt)
+    r_opt = re.search(r"pub struct DzbOptions \{(.*?)\}", doc, flags=re.S).group(1)
+    r_fields = re.findall(r"pub (\w+): c_int", r_opt)
+    assert c_fields == r_fields and len(c_fields) == 4, (c_fields, r_fields)
+    # the status codes
+    for name, val in re.findall(r"pub const (DZB_\w+): c_int = (\d+);", doc):
+        assert re.search(rf"\b{name} = {val}\b", hdr), name
