@@ -13,6 +13,7 @@
 #ifndef DZAHUI_B200_HPP
 #define DZAHUI_B200_HPP
 
+#include <algorithm>
 #include <array>
 #include <functional>
 #include <memory>
@@ -293,6 +294,87 @@ class DiffussionSolverTimeIndependent : public detail::HandleSolver {
     return "DiffussionSolverTimeIndependent { boundary_conditions: [" + std::to_string(boundary_conditions[0]) + ", " +
            std::to_string(boundary_conditions[1]) + "], gauss_step: " + std::to_string(gauss_step) + ", mu: " + std::to_string(mu) +
            ", b: " + std::to_string(b) + " }";
+  }
+};
+
+// ---- one bar split across the GPUs of a box: the library's communicator + the collective block solve ---------------------
+// (reference: ONE solve_by_thomas over the whole system, matrix_solver/mod.rs:17-48)
+class Comm {
+  struct Deleter {
+    void operator()(dzb_comm* c) const { dzb_comm_destroy(c); }
+  };
+  std::shared_ptr<dzb_comm> h_;
+  int rank_ = 0, world_ = 1;
+  explicit Comm(dzb_comm* c, int rank, int world) : h_(c, Deleter{}), rank_(rank), world_(world) {}
+
+ public:
+  // rank 0 makes the id and ships its 128 bytes to the other ranks (MPI, a file, a socket)
+  static Result<std::array<unsigned char, DZB_COMM_ID_BYTES>> unique_id() {
+    std::array<unsigned char, DZB_COMM_ID_BYTES> id{};
+    const int rc = dzb_comm_unique_id(id.data());
+    if (rc) return Error::from_status(rc);
+    return id;
+  }
+  // collective; `id` may be null for a one-rank communicator
+  static Result<Comm> init(const unsigned char* id, int rank, int world) {
+    dzb_comm* c = nullptr;
+    const int rc = dzb_comm_init(id, rank, world, &c);
+    if (rc) return Error::from_status(rc);
+    return Comm(c, rank, world);
+  }
+  dzb_comm* handle() const { return h_.get(); }
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  bool peer_mailboxes() const {
+    int pm = 0;
+    dzb_comm_info(h_.get(), nullptr, nullptr, &pm);
+    return pm != 0;
+  }
+};
+
+// DiffussionSolverTimeIndependent for the rows [first, last) of a bar this rank owns; `whole_mesh` is the whole bar
+class SplitBarTimeIndependent {
+  struct Deleter {
+    void operator()(dzb_solver* s) const { dzb_solver_destroy(s); }
+  };
+  std::shared_ptr<dzb_solver> h_;
+  Mesh mesh_;
+  Comm comm_;
+  size_t first_ = 0, last_ = 0;
+  SplitBarTimeIndependent(dzb_solver* s, Mesh m, Comm c, size_t first, size_t last)
+      : h_(s, Deleter{}), mesh_(std::move(m)), comm_(std::move(c)), first_(first), last_(last) {}
+
+ public:
+  static Result<SplitBarTimeIndependent> create(const DiffussionParamsTimeIndependent& p, const std::vector<double>& whole_mesh,
+                                                size_t gauss_step, const Comm& comm, const dzb_options* opt = nullptr) {
+    const size_t n = whole_mesh.size(), w = (size_t)comm.world(), r = (size_t)comm.rank();
+    const size_t base = n / w, rem = n % w, first = r * base + std::min(r, rem), last = first + base + (r < rem ? 1 : 0);
+    const bool hl = r > 0, hr = r + 1 < w;
+    std::vector<double> nodes(whole_mesh.begin() + (first - (hl ? 1 : 0)), whole_mesh.begin() + (last + (hr ? 1 : 0)));
+    auto m = Mesh::from_nodes(nodes);
+    if (m.is_err()) return m.error();
+    dzb_solver* s = nullptr;
+    const int rc = dzb_diffusion_ti_create_block(m.value().handle(), hl, hr, p.mu, p.b, p.boundary_conditions[0], p.boundary_conditions[1],
+                                                 gauss_step, opt, &s);
+    if (rc) return Error::from_status(rc);
+    return SplitBarTimeIndependent(s, m.value(), comm, first, last);
+  }
+  std::pair<size_t, size_t> rows() const { return {first_, last_}; }
+  // XSolver::new again into the block's buffers (current coordinates of the block's mesh)
+  Result<bool> rebuild() {
+    const int rc = dzb_solver_block_rebuild(h_.get(), mesh_.handle());
+    if (rc) return Error::from_status(rc);
+    return true;
+  }
+  // collective: every rank calls it; this rank's nodal values
+  Result<std::vector<double>> solve(double /*time_step*/) {
+    int rc = dzb_solver_block_solve_device(h_.get(), comm_.handle(), nullptr);
+    if (!rc) rc = dzb_solver_block_status(h_.get(), comm_.handle());
+    if (rc) return Error::from_status(rc);
+    std::vector<double> out(last_ - first_);
+    rc = dzb_solver_block_read(h_.get(), out.data(), out.size());
+    if (rc) return Error::from_status(rc);
+    return out;
   }
 };
 

@@ -141,6 +141,27 @@ static void gpu_tests(const std::string& assets) {
     Solver none = None{};
     CHECK(instantiate(none, mesh, 150).unwrap()->solve(0.0).unwrap().empty());
   }
+  {  // the split bar through the library's communicator (one rank here): the block solve is the single-GPU solve
+    auto p = DiffussionParams::time_independent().mu(1.0).b(1.0).boundary_conditions(0.0, 1.0).build();
+    const size_t n = 100001;
+    std::vector<double> mesh(n);
+    for (size_t i = 0; i < n; ++i) mesh[i] = (double)i / (double)(n - 1);
+    auto comm = Comm::init(nullptr, 0, 1).unwrap();
+    CHECK(comm.world() == 1 && comm.rank() == 0);
+    for (int assembly : {(int)DZB_ASSEMBLY_FAST, (int)DZB_ASSEMBLY_AUTO}) {
+      dzb_options opt{assembly, DZB_SOLVE_PARALLEL, 0, 0};
+      auto bar = SplitBarTimeIndependent::create(p, mesh, 150, comm, &opt).unwrap();
+      CHECK(bar.rows().first == 0 && bar.rows().second == n);
+      CHECK(bar.rebuild().is_ok());
+      auto u = bar.solve(0.0).unwrap();
+      auto whole = DiffussionSolverTimeIndependent::create(p, mesh, 150, &opt).unwrap().solve(0.0).unwrap();
+      double worst = 0.0;
+      for (size_t i = 0; i < n; ++i) worst = std::max(worst, std::fabs(u[i] - whole[i]));
+      CHECK(u.size() == n && u[0] == 0.0 && u[n - 1] == 1.0 && worst <= 1e-10);
+    }
+    CHECK(Comm::init(nullptr, 0, 2).is_err());   // more than one rank needs rank 0's id
+    CHECK(Comm::init(nullptr, 1, 1).is_err());
+  }
   {  // EulerSolver: the reference's integration tests (tests/euler.rs), closures given by their affine coefficients
     auto first = EulerSolver<2>::constant(1.0);  // EulerSolver::new(|_: &[f64; 2]| 1.0)
     std::array<double, 2> s2{0.0, 0.0};          // [pos, time]
