@@ -1192,9 +1192,9 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done, const dzb::PeerBox*
     }
     if (const char* path = std::getenv("DZB_OL_TRACE_FILE")) {  // one line per CTA: the six stamps in microseconds
       if (FILE* f = std::fopen(path, "w")) {
-        for (int c = 0; c < ctas; ++c) {
-          for (int k = 0; k < 8; ++k) std::fprintf(f, "%.3f ", (double)(h[8 * c + k] - t0) * 1e-3);
-          std::fprintf(f, "\n");
+        for (int c = 0; c < ctas; ++c) {  // the stamps in microseconds, then the SM the CTA ran on
+          for (int k = 0; k < 8; ++k) std::fprintf(f, "%.3f ", (double)((k ? h[8 * c + k] : (h[8 * c] & ~0xfffULL)) - (t0 & ~0xfffULL)) * 1e-3);
+          std::fprintf(f, "%u\n", (unsigned)(h[8 * c] & 0xfffULL));
         }
         std::fclose(f);
       }

@@ -100,6 +100,11 @@ __device__ __forceinline__ void ol_stamp(const OneLaunchArgs& a, int slot) {
   if (a.trace && threadIdx.x == 0) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    if (slot == 0) {  // the low 12 bits of the start stamp carry the SM the CTA runs on
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      ns = (ns & ~0xfffULL) | (smid & 0xfffu);
+    }
     a.trace[8 * blockIdx.x + slot] = ns;
   }
 }
@@ -295,8 +300,11 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   const TileArgs& k = a.k;
   const int t = threadIdx.x;
   const long long ntiles = (k.m + BS_TILE - 1) / BS_TILE;
-  // contiguous tile ranges; a ragged last tile takes the direct-load path, which costs about two staged tiles, and everybody
-  // would wait for its CTA at the grid barrier: it counts twice in the split
+  // Contiguous tile ranges, an even share each.  (The two CTAs of an SM do not finish pass 1 together: the one placed first wins
+  // the issue slots and is done after ~75 us at 10^7 rows, its neighbour after ~95 us.  Giving the first arrival — found with a
+  // per-%smid arrival counter, blockIdx does not tell — a larger share evened the two out and changed nothing: the SM takes as
+  // long for its 33 tiles either way, so the split stays even.)  A ragged last tile takes the direct-load path, which costs about two staged
+  // tiles, and everybody would wait for its CTA at the grid barrier: it counts twice in the split
   long long tb0, tb1;
   {
     const long long units = ntiles + ((use_tma && (k.m % BS_TILE)) ? 1 : 0);

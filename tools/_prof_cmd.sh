@@ -1,1 +1,11 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/r2q_tests.txt
+for s in 0 50 80 110 140 170; do
+echo "skew $s" >> gpurun_out/r2t_skew.txt
+for r in 1 2; do
+DZB_OL_SKEW=$s python tools/time_long_solve.py 10000000 4000000 2000000 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({k:round(v['ms'],4) for k,v in d.items()})" >> gpurun_out/r2t_skew.txt
+done
+done
+DZB_OL_SKEW=110 DZB_OL_TRACE=1 DZB_OL_TRACE_FILE=gpurun_out/r2t_ctas.txt python tools/time_long_solve.py 10000000 > /dev/null 2>&1
+DZB_OL_SKEW=110 python -m pytest tests/test_gpu_onelaunch.py tests/test_gpu_split_bar.py -x -q 2>&1 | tail -3 >> gpurun_out/r2t_skew.txt
