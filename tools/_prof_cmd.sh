@@ -1,11 +1,6 @@
-for s in 0 50 80 110 140 170; do
-echo "skew $s" >> gpurun_out/r2t_skew.txt
-for r in 1 2; do
-DZB_OL_SKEW=$s python tools/time_long_solve.py 10000000 4000000 2000000 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print({k:round(v['ms'],4) for k,v in d.items()})" >> gpurun_out/r2t_skew.txt
-done
-done
-DZB_OL_SKEW=110 DZB_OL_TRACE=1 DZB_OL_TRACE_FILE=gpurun_out/r2t_ctas.txt python tools/time_long_solve.py 10000000 > /dev/null 2>&1
-DZB_OL_SKEW=110 python -m pytest tests/test_gpu_onelaunch.py tests/test_gpu_split_bar.py -x -q 2>&1 | tail -3 >> gpurun_out/r2t_skew.txt
+N=$1
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29577"
+timeout 400 $T tools/split_bar_check.py --nodes 10000000 > gpurun_out/r2u_split${N}.txt 2>&1
+NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT DZB_COMM_NO_PEER=1 timeout 400 $T tools/split_bar_check.py --nodes 10000000 --no-check > gpurun_out/r2u_split${N}_nccl.txt 2>&1
+timeout 300 $T tools/d2h_probe.py > gpurun_out/r2u_d2h${N}.txt 2>&1
+timeout 600 $T bench.py --gpus $N --steps 100 > gpurun_out/r2u_bench${N}.json 2> gpurun_out/r2u_bench${N}.err
