@@ -15,6 +15,10 @@ c_size_p = C.POINTER(C.c_size_t)
 FORCE_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
 
+class EulerOp(C.Structure):
+    _fields_ = [("opcode", C.c_int32), ("arg", C.c_int32), ("value", C.c_double)]
+
+
 class Options(C.Structure):
     _fields_ = [("assembly_mode", C.c_int), ("solve_mode", C.c_int), ("refine_steps", C.c_int), ("stored_operators", C.c_int)]
 
@@ -105,6 +109,8 @@ SIGNATURES = {
     "dzb_ensemble_step_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "dzb_ensemble_destroy": (None, [C.c_void_p]),
     "dzb_euler_create": (C.c_int, [C.c_size_t, C.c_size_t, c_double_p, c_double_p, C.POINTER(C.c_void_p)]),
+    "dzb_euler_create_program": (C.c_int, [C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, c_double_p, C.c_size_t, c_double_p,
+                                           C.POINTER(C.c_void_p)]),
     "dzb_euler_set_values": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
     "dzb_euler_step": (C.c_int, [C.c_void_p, C.c_double, C.c_size_t]),
     "dzb_euler_values": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),

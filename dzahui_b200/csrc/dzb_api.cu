@@ -339,6 +339,10 @@ static long long tw_max_bars() {
 struct dzb_euler {
   size_t T = 0, W = 0;                // trajectories, entries per state (incl. t)
   double *v = nullptr, *c = nullptr;  // SoA [W][T] state, [W + 1][T] coefficients
+  // derivative function given as a postfix program (dzb_euler_create_program) instead of affine coefficients
+  dzb::EulerOp* d_ops = nullptr;
+  double* d_params = nullptr;         // SoA [n_params][T]
+  int n_ops = 0, n_params = 0;
 };
 
 struct dzb_ensemble {
@@ -1839,6 +1843,52 @@ int dzb_euler_create(size_t n_traj, size_t width, const double* coeffs, const do
   *out = e;
   return DZB_OK;
 }
+int dzb_euler_create_program(size_t n_traj, size_t width, const dzb_euler_op* program, size_t n_ops, const double* params,
+                             size_t n_params, const double* values, dzb_euler** out) {
+  if (!out || !program || !values || (n_params && !params)) return fail(DZB_INVALID, "null pointer");
+  *out = nullptr;
+  if (width < 2 || width > 5) return fail(DZB_INVALID, "EulerSolver takes [f64; 2] .. [f64; 5] (solvers/euler/mod.rs:19-22)");
+  if (n_traj == 0) return fail(DZB_INVALID, "no trajectories");
+  if (n_ops == 0 || n_ops > (size_t)dzb::EULER_MAX_OPS) return fail(DZB_INVALID, "a derivative program has 1 .. 96 operations");
+  // run the program's stack discipline once on the host: the device interpreter does not check anything
+  int depth = 0;
+  std::vector<dzb::EulerOp> ops(n_ops);
+  for (size_t q = 0; q < n_ops; ++q) {
+    const int oc = program[q].opcode, arg = program[q].arg;
+    if (oc < 0 || oc >= dzb::EOP_COUNT) return fail(DZB_INVALID, "unknown opcode in the derivative program");
+    if (oc == dzb::EOP_VALUE && (arg < 0 || (size_t)arg >= width)) return fail(DZB_INVALID, "the program reads a value outside [f64; width]");
+    if (oc == dzb::EOP_PARAM && (arg < 0 || (size_t)arg >= n_params)) return fail(DZB_INVALID, "the program reads a parameter that was not given");
+    if (oc <= dzb::EOP_PARAM) ++depth;
+    else if (oc <= dzb::EOP_DIV) {
+      if (depth < 2) return fail(DZB_INVALID, "the derivative program pops an empty stack");
+      --depth;
+    } else if (depth < 1) return fail(DZB_INVALID, "the derivative program pops an empty stack");
+    if (depth > dzb::EULER_MAX_STACK) return fail(DZB_INVALID, "the derivative program needs more than 16 stack entries");
+    ops[q] = dzb::EulerOp{oc, arg, program[q].value};
+  }
+  if (depth != 1) return fail(DZB_INVALID, "the derivative program must leave exactly one value");
+  dzb_euler* e = new dzb_euler;
+  e->T = n_traj, e->W = width, e->n_ops = (int)n_ops, e->n_params = (int)n_params;
+  int rc;
+  if ((rc = dalloc(&e->v, n_traj * width)) || (rc = dalloc(&e->d_ops, n_ops)) || (rc = dalloc(&e->d_params, n_traj * n_params))) {
+    dzb_euler_destroy(e);
+    return rc;
+  }
+  std::vector<double> hv(n_traj * width), hp(n_traj * n_params);
+  for (size_t i = 0; i < n_traj; ++i) {
+    for (size_t j = 0; j < width; ++j) hv[j * n_traj + i] = values[i * width + j];
+    for (size_t j = 0; j < n_params; ++j) hp[j * n_traj + i] = params[i * n_params + j];
+  }
+  if (cudaMemcpyAsync(e->v, hv.data(), hv.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess ||
+      cudaMemcpyAsync(e->d_ops, ops.data(), ops.size() * sizeof(dzb::EulerOp), cudaMemcpyHostToDevice, g_stream) != cudaSuccess ||
+      (!hp.empty() && cudaMemcpyAsync(e->d_params, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream) != cudaSuccess) ||
+      (rc = sync_stream())) {
+    dzb_euler_destroy(e);
+    return rc ? rc : fail(DZB_CUDA, "H2D euler program");
+  }
+  *out = e;
+  return DZB_OK;
+}
 int dzb_euler_set_values(dzb_euler* e, const double* values, size_t len) {
   if (!e || !values) return fail(DZB_INVALID, "null pointer");
   if (len != e->T * e->W) return fail(DZB_WRONG_DIMS, "length != n_traj * width");
@@ -1851,8 +1901,20 @@ int dzb_euler_set_values(dzb_euler* e, const double* values, size_t len) {
 int dzb_euler_step(dzb_euler* e, double step, size_t steps) {
   if (!e) return fail(DZB_INVALID, "null pointer");
   if (steps == 0) return DZB_OK;
-  const unsigned blocks = (unsigned)((e->T + 255) / 256);
   const long long T = (long long)e->T, k = (long long)steps;
+  if (e->d_ops) {
+    const dzb::EulerProgram prog{e->d_ops, e->n_ops, e->n_params, e->d_params};
+    const unsigned pb = (unsigned)((e->T + 127) / 128);
+    switch (e->W) {
+      case 2: dzb::k_euler_program<2><<<pb, 128, 0, g_stream>>>(e->v, prog, T, step, k); break;
+      case 3: dzb::k_euler_program<3><<<pb, 128, 0, g_stream>>>(e->v, prog, T, step, k); break;
+      case 4: dzb::k_euler_program<4><<<pb, 128, 0, g_stream>>>(e->v, prog, T, step, k); break;
+      default: dzb::k_euler_program<5><<<pb, 128, 0, g_stream>>>(e->v, prog, T, step, k); break;
+    }
+    LAUNCHED();
+    return DZB_OK;
+  }
+  const unsigned blocks = (unsigned)((e->T + 255) / 256);
   switch (e->W) {
     case 2: dzb::k_euler_steps<2><<<blocks, 256, 0, g_stream>>>(e->v, e->c, T, step, k); break;
     case 3: dzb::k_euler_steps<3><<<blocks, 256, 0, g_stream>>>(e->v, e->c, T, step, k); break;
@@ -1882,6 +1944,8 @@ void dzb_euler_destroy(dzb_euler* e) {
   if (!e) return;
   dfree(e->v);
   dfree(e->c);
+  dfree(e->d_ops);
+  dfree(e->d_params);
   delete e;
 }
 

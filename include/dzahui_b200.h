@@ -247,6 +247,23 @@ void dzb_ensemble_destroy(dzb_ensemble* e);
  * [n_traj][width].  DZB_INVALID unless 2 <= width <= 5. */
 typedef struct dzb_euler dzb_euler;
 int dzb_euler_create(size_t n_traj, size_t width, const double* coeffs, const double* values, dzb_euler** out);
+/* Derivative functions that are not affine: the expression itself, as a postfix program shared by all trajectories — the
+ * device analogue of the reference's `Fn(&[f64; N]) -> f64` (mod.rs:24-31) for closed-form expressions of the OLD values,
+ * per-trajectory parameters and constants.  CONST pushes `value`, VALUE pushes values[arg], PARAM pushes this trajectory's
+ * params[arg]; binary operations pop b then a and push (a op b).  IEEE double, one rounding per operation in program order,
+ * no contraction: + - * / neg abs sqrt give the bits the Rust closure gives; sin cos exp log use the device's libm.  At most
+ * 96 operations and 16 stack entries; DZB_INVALID for a malformed program.  params: host [n_traj][n_params]. */
+typedef enum dzb_euler_opcode {
+  DZB_EOP_CONST = 0, DZB_EOP_VALUE = 1, DZB_EOP_PARAM = 2, DZB_EOP_ADD = 3, DZB_EOP_SUB = 4, DZB_EOP_MUL = 5, DZB_EOP_DIV = 6,
+  DZB_EOP_NEG = 7, DZB_EOP_SQRT = 8, DZB_EOP_ABS = 9, DZB_EOP_SIN = 10, DZB_EOP_COS = 11, DZB_EOP_EXP = 12, DZB_EOP_LOG = 13
+} dzb_euler_opcode;
+typedef struct dzb_euler_op {
+  int32_t opcode; /* dzb_euler_opcode */
+  int32_t arg;
+  double value;
+} dzb_euler_op;
+int dzb_euler_create_program(size_t n_traj, size_t width, const dzb_euler_op* program, size_t n_ops, const double* params,
+                             size_t n_params, const double* values, dzb_euler** out);
 /* `steps` successive do_step(values, step) on every trajectory; the states stay on the device */
 int dzb_euler_step(dzb_euler* e, double step, size_t steps);
 int dzb_euler_set_values(dzb_euler* e, const double* values, size_t len);     /* [n_traj][width]: restart from these states */

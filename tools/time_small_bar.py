@@ -1,8 +1,12 @@
 """Latency of the reference-arithmetic (FAITHFUL, bit-identical) path on ONE bar, the shape the reference itself runs:
 static solve(), time-dependent solve(dt) and XSolver::new (assembly + factorisation) at a few sizes.  Device-resident,
-CUDA events.  Usage: python tools/time_small_bar.py [n ...]   (tuning aid; not part of the test suite)"""
+CUDA events.  Next to every GPU figure the CPU port (oracle/, the reference's algorithm on ONE host thread, as the reference
+runs it) on the same box: banded Thomas / banded step, and assembly with the quadrature loop.
+Usage: python tools/time_small_bar.py [n ...]   (tuning aid; not part of the test suite)"""
 import os, sys, json, time, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import oracle_lib as o
 import dzahui_b200 as dz
 from dzahui_b200 import solvers, params
 
@@ -20,6 +24,14 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps * 1e3  # microseconds
 
 
+def cpu_timed(fn, reps):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps * 1e6  # microseconds
+
+
 def main():
     sizes = [int(float(a)) for a in sys.argv[1:]] or [100, 1000, 10000, 65536]
     out = {}
@@ -34,6 +46,17 @@ def main():
         td = solvers.DiffussionSolverTimeDependent(q, mesh, 150, options=opt)
         out[n] = {"static_solve_us": timed(lambda: s.solve_device(0.0), reps), "td_step_us": timed(lambda: td.solve_device(1e-9), reps),
                   "static_rebuild_us": timed(lambda: s.rebuild(), max(3, reps // 4)), "td_rebuild_us": timed(lambda: td.rebuild(), max(3, reps // 4))}
+        # the CPU port on one thread (banded storage: the reference's dense Array2 would be far slower beyond a few thousand nodes)
+        creps = max(3, min(200, 400_000 // n))
+        bands = o.ti_assemble(x, 1.0, 0.5, (1.0, 15.0), 150)
+        tdb = o.td_assemble(x, 1.0, 0.5, 150)
+        sess = o.EnsembleSession([b[None, :] for b in tdb], o.td_initial_state(np.sin(x[1:-1]), n, (0.0, 1.0))[None, :], (0.0, 1.0))
+        k = 20
+        out[n].update({"cpu_static_solve_us": cpu_timed(lambda: o.thomas(*bands), creps),
+                       "cpu_td_step_us": cpu_timed(lambda: sess.advance(1e-9, k, 1), max(3, creps // 4)) / k,
+                       "cpu_static_rebuild_us": cpu_timed(lambda: o.ti_assemble(x, 1.0, 0.5, (1.0, 15.0), 150), max(3, creps // 8)),
+                       "cpu_td_rebuild_us": cpu_timed(lambda: o.td_assemble(x, 1.0, 0.5, 150), max(3, creps // 8))})
+        sess.close()
     print(json.dumps(out))
 
 
