@@ -453,6 +453,7 @@ def measure_c4_split(cx, n, assembly, steps, warmup, comm, parity_ref=None):
         bar.rebuild()
         bar.solve_device()
 
+    cx.barrier()   # rank 0 may come out of the previous mode's CPU parity check: nobody spins on its mailbox meanwhile
     ramp_clocks(step, cx.local_rank)
     total_ms, per_step, launches = cx.time_steps(step, steps, warmup)
     bar.status()

@@ -115,3 +115,37 @@ def test_two_ranks_against_the_oracle(gpu, no_peer):
         assert l["world"] == 2 and l["relL2_gpu_vs_f128_of_its_bands"] <= 1e-10
         if no_peer:
             assert not l["peer_mailboxes"]
+
+
+def test_second_device_in_one_process(gpu, oracle):
+    """dzb_set_device switches devices inside one process: every device-side one-off (shared-memory attributes, occupancy,
+    scratch flags, the copy stream of the pipelined read-back) is kept per device, so the same work on device 1 after
+    device 0 gives the same bits.  Needs two GPUs."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dzahui_b200 import synthetic
+    p = gpu.DiffussionParams.time_independent().mu(1.0).b(0.5).boundary_conditions(-2.0, 7.0).build()
+    mesh = jittered(300_007, 3)
+    ids = np.arange(2100)
+    meshes = synthetic.ensemble_meshes(ids, 300)
+    ic = synthetic.ensemble_initial_conditions(meshes, ids)
+    results = []
+    try:
+        for dev in (0, 1, 0):
+            gpu.set_device(dev)
+            out = []
+            for amode in (gpu.ASSEMBLY_FAST, gpu.ASSEMBLY_AUTO):
+                s = gpu.DiffussionSolverTimeIndependent(p, mesh, 150, gpu.make_options(amode, gpu.SOLVE_PARALLEL, 0))
+                out.append(s.solve(0.0))
+                s.close()
+            e = gpu.EnsembleTimeDependent(meshes, 1.0, 1.0, (1.0, 15.0), ic, 150)
+            for _ in range(3):
+                st = e.solve(1e-8)          # the third call takes the pipelined (copy-stream) read-back
+            out.append(st.copy())
+            e.close()
+            results.append(out)
+    finally:
+        gpu.set_device(0)
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert a.tobytes() == b.tobytes()
