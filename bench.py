@@ -91,9 +91,12 @@ def config_for(args, world):
     return {"workload": c4_workload(args.nodes, world), "dof_per_gpu": args.nodes // world,
             "value_covers": "assembly (XSolver::new into resident buffers) + tridiagonal solve, every step",
             "l2": "inputs larger than L2 (bands 320 MB)" if args.nodes * 32 > 2.6e8 else "working set may fit L2",
-            "e2e_steps": e2e_steps, "e2e_call": "dzb_mesh_set_nodes(host_x) + dzb_solver_rebuild + dzb_solver_solve(host_out)",
+            "e2e_steps": e2e_steps, "e2e_call": ("dzb_mesh_set_nodes(host_x) + dzb_solver_rebuild + dzb_solver_solve(host_out)" if world == 1 else
+                         "every rank: dzb_mesh_set_nodes(host block) + dzb_solver_block_rebuild + dzb_solver_block_solve_device + "
+                         "dzb_solver_block_read(host_out)"),
             "e2e_inputs": "node coordinates H2D (pinned) + assembly + solve + nodal values D2H (pinned) every step",
-            "parallelism": "1 GPU" if world == 1 else f"one bar split into {world} row blocks, one ncclAllGather of 8 doubles per rank per solve"}
+            "parallelism": "1 GPU" if world == 1 else (f"one bar split into {world} row blocks; 8 doubles per rank cross GPUs per solve "
+                                                        "(NVLink peer mailboxes, else ncclAllGather: extra.transport)")}
 
 
 def peaks():
@@ -431,7 +434,7 @@ def measure_c4(cx, n, assembly, steps, warmup, parity_ref=None, e2e_steps=0):
     return out
 
 
-def measure_c4_split(cx, n, assembly, steps, warmup, comm, parity_ref=None):
+def measure_c4_split(cx, n, assembly, steps, warmup, comm, parity_ref=None, e2e_steps=0):
     """BASELINE config 4 at N > 1: ONE n-node bar split into row blocks, one per rank (strong scaling).  Per step every rank
     calls `dzb_solver_block_rebuild` (assembly of its block) + `dzb_solver_block_solve_device` (block elimination, exchange of
     the 2 interface rows per block, interface solve, back-substitution): the communicator is the library's own (dzb_comm_*)."""
@@ -468,6 +471,28 @@ def measure_c4_split(cx, n, assembly, steps, warmup, comm, parity_ref=None):
                        "frac": ach / (cx.peak * cx.world), "algorithmic_bytes_per_launch": SURVEY_BYTES_STATIC * n,
                        "bytes_accounting": "SURVEY 8(d): assembly 40 B/DOF + solve 40 B/DOF, against N x the measured copy peak",
                        "traffic": None, "peak_source": cx.peak_src}
+    if e2e_steps:   # every rank: its block's coordinates (own + halo nodes) from pinned host memory, its nodal values back
+        torch = cx.torch
+        first, last = bar.rows
+        nodes = mesh[first - (1 if first > 0 else 0): last + (1 if last < n else 0)]
+        host_x = torch.from_numpy(np.ascontiguousarray(nodes)).pin_memory()
+        host_u = torch.empty(last - first, dtype=torch.float64, pin_memory=True)
+
+        def step_e2e():
+            bar.rebuild(host_x.numpy())
+            bar.solve_device()
+            bar.block.block_read_into(host_u.data_ptr())
+        for _ in range(2):
+            step_e2e()
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        cx.torch.cuda.synchronize()
+        sec = cx.max_over_ranks(time.perf_counter() - t0)
+        bar.status()
+        out["e2e"] = {"value": n * e2e_steps / sec, "unit": UNIT, "h2d_bytes_per_step": len(nodes) * 8, "d2h_bytes_per_step": (last - first) * 8,
+                      "ms_per_step": sec / e2e_steps * 1e3, "steps": e2e_steps, "bytes": "per rank"}
     if parity_ref is not None:
         u_block = bar.solve(0.0)
         parts = [None] * cx.world if cx.rank == 0 else None
@@ -614,14 +639,14 @@ def main():
         else:
             from dzahui_b200.distributed import NativeComm
             comm = NativeComm.from_torch()
-            sec = measure_c4_split(cx, n, args.assembly, args.steps, args.warmup, comm, parity_ref={})
+            sec = measure_c4_split(cx, n, args.assembly, args.steps, args.warmup, comm, parity_ref={}, e2e_steps=e2e_steps)
             comm.close()
         clocks = sampler.result()
         ms_per_step, value, launches = sec["ms_per_step"], sec["value"], int(sec["gpu_launches_per_step"] * args.steps)
         roofline = sec.pop("roofline")
         e2e_sec = sec.pop("e2e", None)
         extra.update(sec)
-        d2h, h2d = n * 8, n * 8
+        d2h, h2d = n * 8 // world, n * 8 // world
 
     # ---- end to end through the host-facing call
     if args.workload == "c5":
@@ -669,7 +694,7 @@ def main():
         del host_out
     else:
         e2e = e2e_sec or {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                          "note": "the split bar's blocks stay on their GPUs; see extra"}
+                          "note": "not measured"}
 
     # ---- the other BASELINE configuration on which the metric is quoted, in the same run
     if not args.no_extra and args.workload == "c5":
@@ -687,7 +712,7 @@ def main():
                 cache = {}
                 c4 = {"workload": c4_workload(args.nodes, world)}
                 for mode in ("auto", "fast"):
-                    c4[mode] = measure_c4_split(cx, args.nodes, mode, min(args.steps, 50), 3, comm, parity_ref=cache)
+                    c4[mode] = measure_c4_split(cx, args.nodes, mode, min(args.steps, 50), 3, comm, parity_ref=cache, e2e_steps=10)
                 comm.close()
                 extra["c4_split"] = c4
             except Exception as ex:  # the headline must not depend on the extra section

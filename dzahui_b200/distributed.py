@@ -130,6 +130,10 @@ class BarBlock:
         check(self._lib.dzb_solver_block_read(self._h, out.ctypes.data_as(_lib.c_double_p), self.n), self._lib)
         return out
 
+    def block_read_into(self, host_ptr):
+        """the block's nodal values into a caller's host buffer of self.n doubles (pinned memory: PCIe speed)"""
+        check(self._lib.dzb_solver_block_read(self._h, C.cast(C.c_void_p(int(host_ptr)), _lib.c_double_p), self.n), self._lib)
+
     def bands(self):
         lo, di, up, rhs = (np.empty(self.n) for _ in range(4))
         check(self._lib.dzb_solver_bands(self._h, 0, lo.ctypes.data_as(_lib.c_double_p), di.ctypes.data_as(_lib.c_double_p),

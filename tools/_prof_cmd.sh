@@ -1,6 +1,4 @@
-python -m pytest tests/test_gpu_onelaunch.py tests/test_gpu_split_bar.py -x -q 2>&1 | tail -5 > gpurun_out/r2w_tests.txt
-for r in 1 2 3; do python tools/time_long_solve.py 10000000 4000000 2000000 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print({k:round(v['ms'],4) for k,v in d.items()})" >> gpurun_out/r2w_time.txt; done
-DZB_OL_TRACE=1 DZB_OL_TRACE_FILE=gpurun_out/r2w_ctas.txt python tools/time_long_solve.py 10000000 > /dev/null 2>&1
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29577"
+timeout 600 python -m pytest tests/test_gpu_split_bar.py -x -q 2>&1 | tail -8 > gpurun_out/r2x_tests.txt
+timeout 600 $T bench.py --gpus 2 --workload c4 --assembly fast --steps 50 > gpurun_out/r2x_bench_c4_n2.json 2> gpurun_out/r2x_bench_c4_n2.err
+timeout 600 python bench.py --workload c4 --assembly fast --steps 50 > gpurun_out/r2x_bench_c4_n1.json 2> gpurun_out/r2x_bench_c4_n1.err
