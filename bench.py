@@ -232,6 +232,14 @@ def cpu_static_sample(n, threads):
     return n / dt, dt
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return next(l.split(":", 1)[1].strip() for l in f if l.startswith("model name"))
+    except Exception:
+        return "unknown"
+
+
 def host_threads():
     """cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the reference arm wants)"""
     try:
@@ -270,7 +278,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": statistics.mean(secs) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_for(args, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "cpu_model": cpu_model()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
@@ -374,7 +382,7 @@ def measure_c4(cx, n, assembly, steps, warmup, parity_ref=None, e2e_steps=0):
                                                 "(~22 B/row, partly L2 hits); the bands are never materialised (rebuild is a no-op: "
                                                 "assemble_ms ~ 0, everything is in solve_ms)") if one_launch
                        else "x 8 + bands out 32 + bands in twice 64 + u 8 = 112",
-                       "traffic": None, "peak_source": cx.peak_src}
+                       "traffic": None, "peak_source": cx.peak_src, "frac_of_8TBs_spec": ach / 8000.0}
     if assembly != "fast":
         # the reference-arithmetic assembly is fp64-pipe bound, not HBM bound: G-1 quadrature nodes x 27 separately rounded
         # operations per row (no FMA: the reference never contracts) against 64 fp64 lanes per SM per clock
@@ -470,7 +478,7 @@ def measure_c4_split(cx, n, assembly, steps, warmup, comm, parity_ref=None, e2e_
     out["roofline"] = {"bound": "hbm", "kernel": out["path"], "achieved": ach, "peak": cx.peak * cx.world, "unit": "GB/s",
                        "frac": ach / (cx.peak * cx.world), "algorithmic_bytes_per_launch": SURVEY_BYTES_STATIC * n,
                        "bytes_accounting": "SURVEY 8(d): assembly 40 B/DOF + solve 40 B/DOF, against N x the measured copy peak",
-                       "traffic": None, "peak_source": cx.peak_src}
+                       "traffic": None, "peak_source": cx.peak_src, "frac_of_8TBs_spec": ach / (8000.0 * cx.world)}
     if e2e_steps:   # every rank: its block's coordinates (own + halo nodes) from pinned host memory, its nodal values back
         torch = cx.torch
         first, last = bar.rows
@@ -611,7 +619,8 @@ def main():
                                             "u in/out 16 + element length 8 + 1/den 8 + unscaled diagonal 8 = 40 (off-diagonals rebuilt on chip)")),
                     "algorithmic_bytes_per_launch": design_bytes,
                     "frac_survey_bytes": survey_bytes / (kern_ms * 1e-3) / 1e9 / peak, "survey_bytes_per_launch": survey_bytes,
-                    "traffic": traffic, **traffic_lbl, "kernel_ms": kern_ms, "peak_source": peak_src}
+                    "traffic": traffic, **traffic_lbl, "kernel_ms": kern_ms, "peak_source": peak_src,
+                    "frac_of_8TBs_spec": achieved / 8000.0}
 
         # ---- temporal blocking, reported separately: one launch advances every bar by 64 steps with operator and state on chip
         if not args.stored_operators:
@@ -743,13 +752,14 @@ def main():
                 c_all, ct = cpu_static_sample(nn, threads)
                 c_one, _ = cpu_static_sample(nn, 1)
                 extra["c4"]["cpu_baseline"] = {"value": c_all, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": c_one,
+                                               "cpu_model": cpu_model(),
                                                "sample": f"{nn}-node regular bar: quadrature-loop assembly + Thomas ({ct:.1f} s)"}
         else:
             v_all, t_all = cpu_static_sample(nn, threads)
             v_one, _ = cpu_static_sample(nn, 1)
             sample = f"{nn}-node regular bar: quadrature-loop assembly + Thomas ({t_all:.1f} s)"
         line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                                "single_thread_value": v_one}
+                                "single_thread_value": v_one, "cpu_model": cpu_model()}
     if rank == 0:
         emit(line)
     if world > 1:

@@ -57,6 +57,16 @@ def main():
                        "cpu_static_rebuild_us": cpu_timed(lambda: o.ti_assemble(x, 1.0, 0.5, (1.0, 15.0), 150), max(3, creps // 8)),
                        "cpu_td_rebuild_us": cpu_timed(lambda: o.td_assemble(x, 1.0, 0.5, 150), max(3, creps // 8))})
         sess.close()
+        if n <= 4096:  # the reference's own shape: dense n x n Array2 (zero-filled every time) and quad_pair + cos per (row, node)
+            lo, di, up, rhs = bands
+            dense = np.diag(di) + np.diag(lo[1:], -1) + np.diag(up[:-1], 1)
+            out[n].update({"cpu_dense_static_solve_us": cpu_timed(lambda: o.thomas_dense(dense, rhs), max(3, creps // 4)),
+                           "cpu_dense_static_rebuild_us": cpu_timed(lambda: o.ti_assemble(x, 1.0, 0.5, (1.0, 15.0), 150, mode=2), 3)})
+    try:
+        with open("/proc/cpuinfo") as f:
+            out["cpu_model"] = next(l.split(":", 1)[1].strip() for l in f if l.startswith("model name"))
+    except Exception:
+        pass
     print(json.dumps(out))
 
 
