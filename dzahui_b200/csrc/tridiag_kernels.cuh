@@ -26,9 +26,12 @@ namespace dzb {
 // Coalesced: with a thread per bar on the natural [bar][node] layout the lanes
 // of a warp are a whole bar (8 KB at 1024 nodes) apart: every load touches 32 different lines and the kernel ran at ~1.3 TB/s
 // (2.0 ms for the 65536 x 1024 ensemble).  Here a warp owns 32 bars and walks them 32 rows at a time: the lanes load each
-// bar's 32-row piece of lo / di / up as one 256-byte row into a padded shared-memory tile, lane b then runs bar b's
+// bar's 32-row piece of lo / di / up as one 256-byte row into a padded shared-memory tile (cp.async), lane b then runs bar b's
 // recurrence over the tile (the same expressions in the same order: bit-identical), leaves c over up and den over di, and
 // the tile goes back with coalesced stores.
+__device__ __forceinline__ void tf_copy8(double* smem_dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
+}
 constexpr int TF_ROWS = 32, TF_WARPS = 4;
 constexpr size_t TF_SMEM = (size_t)TF_WARPS * 3 * 32 * (TF_ROWS + 1) * sizeof(double);
 __global__ void __launch_bounds__(32 * TF_WARPS) k_thomas_factor_tile(const double* __restrict__ lo, const double* __restrict__ di,
@@ -45,13 +48,14 @@ __global__ void __launch_bounds__(32 * TF_WARPS) k_thomas_factor_tile(const doub
   double cp = 0.0;
   for (long long i0 = 0; i0 < n; i0 += TF_ROWS) {
     const long long row = i0 + lane;
-    if (row < n) {
-#pragma unroll 8
+    if (row < n) {  // global -> shared without a register round trip: all 3 nb copies of the lane are in flight at once
+#pragma unroll 4
       for (int b = 0; b < nb; ++b) {
         const long long g = (bar0 + b) * n + row;
-        L[b][lane] = lo[g], D[b][lane] = di[g], U[b][lane] = up[g];
+        tf_copy8(&L[b][lane], lo + g), tf_copy8(&D[b][lane], di + g), tf_copy8(&U[b][lane], up + g);
       }
     }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (lane < nb) {
       const int rows = (int)min((long long)TF_ROWS, n - i0);
