@@ -149,3 +149,32 @@ def test_second_device_in_one_process(gpu, oracle):
     for other in results[1:]:
         for a, b in zip(results[0], other):
             assert a.tobytes() == b.tobytes()
+
+
+def test_collective_call_checks_its_arguments(gpu):
+    """a block whose open ends do not match its rank in the communicator, a solver that is not a block, the library's own
+    all-gather on a one-rank communicator"""
+    import ctypes as C
+    import torch
+    from dzahui_b200 import _lib
+    from dzahui_b200.distributed import BarBlock, NativeComm
+    lib = _lib.load()
+    p = gpu.DiffussionParams.time_independent().mu(1.0).b(0.5).boundary_conditions(-2.0, 7.0).build()
+    comm = NativeComm(None, 0, 1)
+    x = np.linspace(0.0, 1.0, 5001)
+    open_left = BarBlock(p, x, True, False, 150, gpu.make_options(gpu.ASSEMBLY_AUTO, gpu.SOLVE_PARALLEL, 0))   # a middle/last block
+    ptr = C.c_void_p()
+    assert lib.dzb_solver_block_solve_device(open_left._h, comm._h, C.byref(ptr)) == 7      # DZB_INVALID: rank 0 of 1 has no neighbour
+    assert b"open ends" in lib.dzb_last_error()
+    open_left.close()
+    s = gpu.DiffussionSolverTimeIndependent(p, x, 150)
+    assert lib.dzb_solver_block_solve_device(s._h, comm._h, C.byref(ptr)) == 7               # not a block solver
+    assert lib.dzb_solver_block_rebuild(s._h, None) == 7
+    s.close()
+    src = torch.arange(6, dtype=torch.float64, device="cuda")
+    dst = torch.zeros(6, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    comm.all_gather(src.data_ptr(), dst.data_ptr(), 6)
+    gpu.synchronize()
+    assert torch.equal(src, dst)
+    comm.close()
