@@ -378,7 +378,7 @@ def measure_c4(cx, n, assembly, steps, warmup, parity_ref=None, e2e_steps=0):
                        "achieved": ach, "peak": cx.peak,
                        "unit": "GB/s", "frac": ach / cx.peak, "algorithmic_bytes_per_launch": SURVEY_BYTES_STATIC * n,
                        "bytes_accounting": "SURVEY 8(d): assembly 40 B/DOF (x 8 in, 4 bands 32 out) + solve 40 B/DOF (4 bands in, u out)",
-                       "design_bytes_per_row": ("x in 8 + (1/h, row excess) out and in 32 + u out 8 = 48, plus the level-B/C rows and solutions "
+                       "design_bytes_per_row": ("x in twice 16 + row excess out and in 16 + u out 8 = 40, plus the level-B/C rows and solutions "
                                                 "(~22 B/row, partly L2 hits); the bands are never materialised (rebuild is a no-op: "
                                                 "assemble_ms ~ 0, everything is in solve_ms)") if one_launch
                        else "x 8 + bands out 32 + bands in twice 64 + u 8 = 112",

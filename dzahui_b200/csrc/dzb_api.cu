@@ -403,7 +403,7 @@ struct dzb_solver {
   double* x_own = nullptr;
   unsigned long long x_version = 0;  // coordinate stamp of x_view, for the matrix-class cache
   double* ol_red = nullptr;      // 4 x [8 OL_P1M]: the two interface rows of every CTA
-  double *ol_r = nullptr, *ol_s = nullptr;  // [n] each: what pass 1 leaves per row for pass 2 (1/h, row-sum excess)
+  double* ol_s = nullptr;        // [n]: what pass 1 leaves per row for pass 2 (the row-sum excess)
   double* ol_pool = nullptr;               // levels B and C of the one-launch kernel: 4 + 1 arrays each (rows and their solutions)
   bool fused_bad_valid = false;            // the coordinates stamped fused_bad_version hold a row outside the closed form:
   unsigned long long fused_bad_version = 0;  // materialised bands (with the quadrature loop on such rows) for them
@@ -1151,7 +1151,7 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done, const dzb::PeerBox*
   a.P = dzb::AsmParams{s->mu, s->b, s->bc0, s->bc1, 0.0, 0.0};
   a.n_local = (long long)(s->is_block ? s->n_alloc : s->n), a.halo_left = (s->is_block && (s->block_flags & dzb::BS_OPEN_LEFT)) ? 1 : 0;
   if (px) a.px = *px;
-  a.r_el = s->ol_r, a.s_ex = s->ol_s;
+  a.s_ex = s->ol_s;
   {
     const size_t rb = dzb::onelaunch_rows_b(s->n), rc = dzb::onelaunch_rows_c(s->n);
     double* q = s->ol_pool;
@@ -1249,7 +1249,6 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
   if (!rc && opt.assembly_mode == DZB_ASSEMBLY_FAST && s->want_parallel && s->refine_steps == 0 && s->n >= 2 * (size_t)dzb::BS_TILE &&
       !env_set("DZB_NO_ONELAUNCH")) {
     rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
-    if (!rc) rc = dalloc(&s->ol_r, s->n);
     if (!rc) rc = dalloc(&s->ol_s, s->n);
     if (!rc) rc = dalloc(&s->ol_pool, 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n)));
     if (!rc) rc = dalloc(&s->d_cls, 2);
@@ -1451,7 +1450,7 @@ void dzb_solver_destroy(dzb_solver* s) {
     if (*p) *p -= s->off;
     dfree(*p);
   }
-  for (double** p : {&s->c, &s->den, &s->rden, &s->out, &s->d_top8, &s->x_own, &s->ol_red, &s->ol_r, &s->ol_s, &s->ol_pool}) dfree(*p);
+  for (double** p : {&s->c, &s->den, &s->rden, &s->out, &s->d_top8, &s->x_own, &s->ol_red, &s->ol_s, &s->ol_pool}) dfree(*p);
   solver_detach(s);
   if (s->d_cls) cudaFree(s->d_cls), s->d_cls = nullptr;
   dzb::bigsys_free(&s->big);
@@ -1503,7 +1502,6 @@ int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right
     s->x_pad = lead;  // halo at [x_pad], first own row at [x_pad + lead]: index 0 or 2, 16-byte aligned
     rc = dalloc(&s->x_own, s->n_alloc + s->x_pad + 2);
     if (!rc) rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
-    if (!rc) rc = dalloc(&s->ol_r, s->n);
     if (!rc) rc = dalloc(&s->ol_s, s->n);
     if (!rc) rc = dalloc(&s->ol_pool, 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n)));
     if (!rc) rc = dalloc(&s->d_cls, 2);

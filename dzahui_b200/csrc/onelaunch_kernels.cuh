@@ -11,9 +11,8 @@
 //   level A (the bar itself, ~34 000 rows per CTA at n = 10^7), per tile: the node coordinates arrive through the TMA (one
 //            16 KB box, SWIZZLE_128B, prefetched one tile ahead; the two coordinates either side as bulk copies), every
 //            thread forms the 8 rows of its chunk in registers with the lean closed form of assembly_kernels.cuh (ti_elem /
-//            ti_row: bit-identical to k_assemble_fast's bands), leaves TWO numbers per row in memory — 1/h of the element to
-//            the row's right and the row-sum excess s = lo + di + up — sweeps the chunk and writes its two reduced rows to
-//            level B.  No shared-memory pyramid per tile: a pyramid level is ~1 us of single-warp latency during which
+//            ti_row: bit-identical to k_assemble_fast's bands), leaves ONE number per row in memory — the row-sum excess
+//            s = lo + di + up, the expensive part of a row — sweeps the chunk and writes its two reduced rows to level B.  No shared-memory pyramid per tile: a pyramid level is ~1 us of single-warp latency during which
 //            the rest of the CTA waits (measured: 2 us of every 7 us tile in pass 1, 3.4 of 4.9 us in pass 2);
 //   level B (rows / 4) and level C (rows / 16): the same chunk sweep by all 256 threads over the CTA's slice of the
 //            previous level's rows (global scratch, L2 resident), no barrier inside a level;
@@ -21,11 +20,14 @@
 //            every CTA solves the 2-rows-per-CTA system redundantly in shared memory (592 rows on a B200) — no second
 //            barrier, no CTA waits for another one again;
 //   and back: D in shared memory, then C, B, A: each chunk is swept again with its multipliers kept in registers and
-//            back-substituted from the two values the level above left for it.  Level A reads its two numbers per row through
-//            the TMA, tiles in reverse order (what was written last is the likeliest to still be in L2): the off-diagonals
-//            are one multiply-add away from 1/h (lo = mu K0/h_left + b hp, up = mu K0/h_right + b hn).
+//            back-substituted from the two values the level above left for it.  Level A reads the coordinates and the
+//            excesses through the TMA, tiles in reverse order (what was written last is the likeliest to still be in L2): the
+//            off-diagonals are a reciprocal and a multiply-add away from the coordinates (lo = mu K0/h_left + b hp,
+//            up = mu K0/h_right + b hn, 1/h by ti_elem's own expression: the same bits as in pass 1).  Pass 1 used to leave 1/h
+//            as well; it is write-bandwidth bound once the assembly is taken out (measured: 60 of its 90 us), and the 8 B per
+//            row were worth more than the nine reciprocals per chunk they saved pass 2.
 //
-// HBM traffic: x in (8) + (1/h, s) out and in again (32) + u out (8) = 48 B/row, plus the level-B rows and solutions
+// HBM traffic: x in twice (16) + s out and in again (16) + u out (8) = 40 B/row, plus the level-B rows and solutions
 // (~20 B/row, mostly L2 hits), instead of 112; one launch instead of seven; the rows are formed once.  A mesh with a row the
 // closed form does not cover (degenerate spacing: ti_elem's sufficient test fails) is reported through class_flags[1] and
 // the caller goes back to materialised bands.
@@ -45,7 +47,6 @@ struct OneLaunchArgs {
   AsmParams P;
   long long n_local; // nodes of the local coordinate array (rows + halo nodes of an open block)
   int halo_left;     // 1 when x[-1] exists (open left end): local node index of row r = r + halo_left
-  double* r_el;      // [m] scratch: 1/h of the element to the right of row r
   double* s_ex;      // [m] scratch: row-sum excess of row r
   double* gb[4];     // [OL_ROWS_B tiles] x (a, c, s, f): level B rows
   double* gc[4];     // [OL_ROWS_C tiles] x (a, c, s, f): level C rows
@@ -117,13 +118,13 @@ struct OlTables {  // rule tables, in shared memory (the launcher refuses rules 
 };
 
 // Rows i0 .. i0+7 (local node indices) of the static diffusion system in row-excess form (a, c, s, f), from the
-// coordinates X[k] = x_local[i0 - 2 + k] (entries outside [0, n_local) are zero and never reach a result).  Rv[j] = 1/h of
-// the element to the right of row j.  Straight-line code: rows that do not exist, Dirichlet rows and rows outside the closed
+// coordinates X[k] = x_local[i0 - 2 + k] (entries outside [0, n_local) are zero and never reach a result).
+// Straight-line code: rows that do not exist, Dirichlet rows and rows outside the closed
 // form are sorted out with selects, so the eight rows of a chunk interleave freely.
 template <bool CLASSIFY>
 __device__ __forceinline__ void ti_rows_from_nodes(const double (&X)[12], long long i0, int len, const OneLaunchArgs& a, const TiK& K,
                                                    const OlTables& tb, double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R],
-                                                   double (&F)[BS_R], double (&Rv)[BS_R], int& cls, bool& bad) {
+                                                   double (&F)[BS_R], int& cls, bool& bad) {
   TiElem E[BS_R + 1];  // element el between X[el + 1] and X[el + 2]
 #pragma unroll
   for (int el = 0; el <= BS_R; ++el) E[el] = ti_elem(X[el + 1], X[el + 2], K);
@@ -148,7 +149,6 @@ __device__ __forceinline__ void ti_rows_from_nodes(const double (&X)[12], long l
       if (!(lo >= 0.0 && up >= 0.0 && di >= 1.25 * (lo + up))) cls |= 2;
     }
     A[j] = lo, C[j] = up, S[j] = ex, F[j] = 0.0;
-    Rv[j] = E[j + 1].r;
   }
   if (jlo != 0 || jhi != BS_R) {  // a chunk with padding or Dirichlet rows, (0, 1, 0, f) with excess 1: the first and the last of the bar
 #pragma unroll
@@ -193,18 +193,19 @@ __device__ __forceinline__ void nodes_direct(const OneLaunchArgs& a, long long g
   }
 }
 
-// Pass 2: rows g0 .. g0+len again, from the two numbers per row pass 1 left behind.  rprev = 1/h of the element to the
-// left of the chunk's first row.
-__device__ __forceinline__ void ti_rows_from_scratch(const double (&Rv)[BS_R], const double (&Sv)[BS_R], double rprev, long long i0, int len,
+// Pass 2: rows g0 .. g0+len again, from the coordinates X[k] = x_local[i0 - 2 + k] and the excesses pass 1 left behind.
+__device__ __forceinline__ void ti_rows_from_scratch(const double (&X)[12], const double (&Sv)[BS_R], long long i0, int len,
                                                      const OneLaunchArgs& a, const TiK& K, double (&A)[BS_R], double (&C)[BS_R],
                                                      double (&S)[BS_R], double (&F)[BS_R]) {
+  double R[BS_R + 1];  // 1/h of the element between X[el + 1] and X[el + 2]: ti_elem's expression, the bits of pass 1
+#pragma unroll
+  for (int el = 0; el <= BS_R; ++el) R[el] = rcp_newton(X[el + 2] - X[el + 1]);
   const long long nl = a.n_local;
   const int jd0 = (int)max(-1LL, min(8LL, -i0)), jd1 = (int)max(-1LL, min(8LL, nl - 1 - i0));
   const int jlo = max(0, jd0 + 1), jhi = min(len, jd1);
 #pragma unroll
   for (int j = 0; j < BS_R; ++j) {
-    const double rl = j == 0 ? rprev : Rv[j - 1];
-    const double lo = fma(K.mu, K.K0 * rl, K.bhp), up = fma(K.mu, K.K0 * Rv[j], K.bhn);  // ti_row's expressions
+    const double lo = fma(K.mu, K.K0 * R[j], K.bhp), up = fma(K.mu, K.K0 * R[j + 1], K.bhn);  // ti_row's expressions
     A[j] = lo, C[j] = up, S[j] = Sv[j], F[j] = 0.0;
   }
   if (jlo != 0 || jhi != BS_R) {  // as in ti_rows_from_nodes
@@ -289,7 +290,6 @@ __device__ __forceinline__ void level_backward(double* const (&src)[4], long lon
 
 template <int P1C, int MINB>
 __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid_constant__ CUtensorMap map_x,
-                                                                 const __grid_constant__ CUtensorMap map_r,
                                                                  const __grid_constant__ CUtensorMap map_s, const OneLaunchArgs a,
                                                                  const int use_tma) {
   using Smem = OneLaunchSmem<P1C>;
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     const long long G0 = R0 + gm.g0;            // first row of the chunk
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
     {
-      double X[12], Rv[BS_R];
+      double X[12];
       if (staged(tile)) {
         mbar_wait(&sm.mbar, phase);
         phase ^= 1;
@@ -368,17 +368,16 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       }
       __syncthreads();  // every chunk is in registers: the stage can take the next tile
       if (t == 0 && kk + 1 < T && staged(tile + 1)) request_x(tile + 1);
-      if (classify) ti_rows_from_nodes<true>(X, G0 + a.halo_left, gm.len, a, K, tb, A, C, S, F, Rv, cls, bad);
-      else ti_rows_from_nodes<false>(X, G0 + a.halo_left, gm.len, a, K, tb, A, C, S, F, Rv, cls, bad);
+      if (classify) ti_rows_from_nodes<true>(X, G0 + a.halo_left, gm.len, a, K, tb, A, C, S, F, cls, bad);
+      else ti_rows_from_nodes<false>(X, G0 + a.halo_left, gm.len, a, K, tb, A, C, S, F, cls, bad);
       if (gm.len == BS_R && !(G0 & 1)) {
-        double2* pr = reinterpret_cast<double2*>(a.r_el + G0);
         double2* ps = reinterpret_cast<double2*>(a.s_ex + G0);
 #pragma unroll
-        for (int j = 0; j < BS_R / 2; ++j) pr[j] = make_double2(Rv[2 * j], Rv[2 * j + 1]), ps[j] = make_double2(S[2 * j], S[2 * j + 1]);
+        for (int j = 0; j < BS_R / 2; ++j) ps[j] = make_double2(S[2 * j], S[2 * j + 1]);
       } else {
 #pragma unroll
         for (int j = 0; j < BS_R; ++j)
-          if (j < gm.len) a.r_el[G0 + j] = Rv[j], a.s_ex[G0 + j] = S[j];
+          if (j < gm.len) a.s_ex[G0 + j] = S[j];
       }
     }
     if (gm.len >= 2) {
@@ -484,11 +483,15 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     // for the value left of the CTA's first tile): generic -> async ordering for both state spaces, from the issuing thread,
     // after it has synchronised with the writers (the grid barrier and the CTA barriers since)
     asm volatile("fence.proxy.async;" ::: "memory");
-    mbar_arrive_expect_tx(&sm.mbar, (unsigned)(2 * BS_TILE * sizeof(double)) + (tile > 0 ? 16u : 0u));
+    const bool hh = x_halo(tile);
+    mbar_arrive_expect_tx(&sm.mbar, (unsigned)(2 * BS_TILE * sizeof(double)) + (hh ? 32u : 0u));
     const int row = (int)(tile * BS_TMA_BOX);
-    tma_load_box(sm.w.stage[0], &map_r, row, &sm.mbar);
+    tma_load_box(sm.w.stage[0], &map_x, row, &sm.mbar);
     tma_load_box(sm.w.stage[1], &map_s, row, &sm.mbar);
-    if (tile > 0) bulk_load(sm.halo, a.r_el + tile * BS_TILE - 2, 16, &sm.mbar);  // [1] = 1/h left of the tile's first row
+    if (hh) {
+      bulk_load(sm.halo, k.p0 + tile * BS_TILE - 2, 16, &sm.mbar);
+      bulk_load(sm.halo + 2, k.p0 + (tile + 1) * BS_TILE, 16, &sm.mbar);
+    }
   };
   if (t == 0 && staged(tb1 - 1)) request_rs(tb1 - 1);  // (its proxy fence also covers the ordinary stores of the middle solve into the work area)
   for (int kk = T - 1; kk >= 0; --kk) {
@@ -500,33 +503,20 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     if (gm.len >= 2) ends = __ldcg(reinterpret_cast<const double2*>(a.ub + oB + 2 * c));
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
     {
-      double Rv[BS_R], Sv[BS_R], rprev = 0.0;
-      const double* xl = k.p0 - a.halo_left;
+      double X[12], Sv[BS_R];
       if (staged(tile)) {
         mbar_wait(&sm.mbar, phase);
         phase ^= 1;
-        stage_chunk(sm.w.stage[0], t, Rv);
+        nodes_from_stage(sm.w.stage[0], sm.halo, x_halo(tile), a, G0, t, X);
         stage_chunk(sm.w.stage[1], t, Sv);
-        rprev = __shfl_up_sync(0xffffffffu, Rv[BS_R - 1], 1);
-        if ((t & 31) == 0) {
-          if (t > 0) rprev = stage_elem(sm.w.stage[0], 8 * t - 1);
-          else if (tile > 0) rprev = sm.halo[1];
-          else rprev = a.halo_left ? rcp_newton(xl[1] - xl[0]) : 0.0;  // ti_elem's expression
-        }
       } else {
+        nodes_direct(a, G0, X);
 #pragma unroll
-        for (int j = 0; j < BS_R; ++j) {
-          const bool in = j < gm.len;
-          Rv[j] = in ? __ldcg(a.r_el + G0 + j) : 0.0, Sv[j] = in ? __ldcg(a.s_ex + G0 + j) : 1.0;
-        }
-        if (gm.len > 0) {
-          if (G0 > 0) rprev = __ldcg(a.r_el + G0 - 1);
-          else rprev = a.halo_left ? rcp_newton(xl[1] - xl[0]) : 0.0;
-        }
+        for (int j = 0; j < BS_R; ++j) Sv[j] = j < gm.len ? __ldcg(a.s_ex + G0 + j) : 1.0;
       }
       __syncthreads();  // every chunk is in registers: the stage can take the next tile
       if (t == 0 && kk > 0 && staged(tile - 1)) request_rs(tile - 1);
-      ti_rows_from_scratch(Rv, Sv, rprev, G0 + a.halo_left, gm.len, a, K, A, C, S, F);
+      ti_rows_from_scratch(X, Sv, G0 + a.halo_left, gm.len, a, K, A, C, S, F);
     }
     if (gm.len >= 2) {
       double o[8], u[BS_R];
@@ -601,12 +591,11 @@ inline int onelaunch_run(BigSys* s, OneLaunchArgs args, int (&caps)[2], cudaStre
   const size_t tiles = (m + BS_TILE - 1) / BS_TILE;
   // (the rule tables live in shared memory; a last tile of one row would leave its CTA a one-row system)
   if (tiles < 2 || args.rule.m <= 0 || args.rule.m > OL_TAB_CAP || m % BS_TILE == 1) return -1;
-  CUtensorMap cx, cr, cs;
-  int use_tma = s->tma &&
-                !((reinterpret_cast<size_t>(args.k.p0) | reinterpret_cast<size_t>(args.r_el) | reinterpret_cast<size_t>(args.s_ex)) & 15) &&
-                bigsys_map(s, args.k.p0, m, &cx) && bigsys_map(s, args.r_el, m, &cr) && bigsys_map(s, args.s_ex, m, &cs);
-  if (!use_tma) std::memset(&cx, 0, sizeof cx), cr = cx, cs = cx;
-  void* params[] = {&cx, &cr, &cs, &args, &use_tma};
+  CUtensorMap cx, cs;
+  int use_tma = s->tma && !((reinterpret_cast<size_t>(args.k.p0) | reinterpret_cast<size_t>(args.s_ex)) & 15) &&
+                bigsys_map(s, args.k.p0, m, &cx) && bigsys_map(s, args.s_ex, m, &cs);
+  if (!use_tma) std::memset(&cx, 0, sizeof cx), cs = cx;
+  void* params[] = {&cx, &cs, &args, &use_tma};
   int rc = onelaunch_try<72, 2>(args, tiles, caps[0], params, st, launches, grid_out);
   if (rc < 0) rc = onelaunch_try<256, 1>(args, tiles, caps[1], params, st, launches, grid_out);
   return rc;
