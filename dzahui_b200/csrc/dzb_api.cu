@@ -1250,7 +1250,10 @@ int dzb_diffusion_ti_create(const dzb_mesh* m, double mu, double b, double bc_le
       !env_set("DZB_NO_ONELAUNCH")) {
     rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
     if (!rc) rc = dalloc(&s->ol_s, s->n);
-    if (!rc) rc = dalloc(&s->ol_pool, 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n)));
+    const size_t pool = 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n));
+    if (!rc) rc = dalloc(&s->ol_pool, pool);
+    // the f arrays of the levels B and C are only ever written where a Dirichlet row's image lands: zero everywhere else, for good
+    if (!rc && cudaMemsetAsync(s->ol_pool, 0, pool * sizeof(double), g_stream) != cudaSuccess) rc = fail(DZB_CUDA, "cudaMemsetAsync");
     if (!rc) rc = dalloc(&s->d_cls, 2);
     if (!rc) {
       s->fused = true;
@@ -1503,7 +1506,10 @@ int dzb_diffusion_ti_create_block(const dzb_mesh* m, int has_left, int has_right
     rc = dalloc(&s->x_own, s->n_alloc + s->x_pad + 2);
     if (!rc) rc = dalloc(&s->ol_red, 4 * 8 * (size_t)dzb::OL_P1M);
     if (!rc) rc = dalloc(&s->ol_s, s->n);
-    if (!rc) rc = dalloc(&s->ol_pool, 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n)));
+    const size_t pool = 5 * (dzb::onelaunch_rows_b(s->n) + dzb::onelaunch_rows_c(s->n));
+    if (!rc) rc = dalloc(&s->ol_pool, pool);
+    // the f arrays of the levels B and C are only ever written where a Dirichlet row's image lands: zero everywhere else, for good
+    if (!rc && cudaMemsetAsync(s->ol_pool, 0, pool * sizeof(double), g_stream) != cudaSuccess) rc = fail(DZB_CUDA, "cudaMemsetAsync");
     if (!rc) rc = dalloc(&s->d_cls, 2);
     if (!rc && cudaMemcpyAsync(s->x_own + s->x_pad, m->d_nodes, s->n_alloc * sizeof(double), cudaMemcpyDeviceToDevice, g_stream) != cudaSuccess)
       rc = fail(DZB_CUDA, "D2D node coordinates");

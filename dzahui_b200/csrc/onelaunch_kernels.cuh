@@ -221,8 +221,9 @@ __device__ __forceinline__ void ti_rows_from_scratch(const double (&X)[12], cons
 
 // ---- levels B and C: rows (a, c, s, f) in global scratch ---------------------------------------------------------------
 // rows r0 .. r0+len of the arrays g[0..3] -> registers (L2 loads: the rows were written by this CTA moments ago)
+// with_f == false: the chunk's right-hand sides are known to be zero (see f_chunk) and are not read.
 __device__ __forceinline__ void rows_load(double* const (&g)[4], long long r0, int len, double (&A)[BS_R], double (&C)[BS_R],
-                                          double (&S)[BS_R], double (&F)[BS_R]) {
+                                          double (&S)[BS_R], double (&F)[BS_R], bool with_f) {
   if (len == BS_R && !(r0 & 1)) {
     const double2* q0 = reinterpret_cast<const double2*>(g[0] + r0);
     const double2* q1 = reinterpret_cast<const double2*>(g[1] + r0);
@@ -230,7 +231,8 @@ __device__ __forceinline__ void rows_load(double* const (&g)[4], long long r0, i
     const double2* q3 = reinterpret_cast<const double2*>(g[3] + r0);
 #pragma unroll
     for (int j = 0; j < BS_R / 2; ++j) {
-      const double2 v0 = __ldcg(q0 + j), v1 = __ldcg(q1 + j), v2 = __ldcg(q2 + j), v3 = __ldcg(q3 + j);
+      const double2 v0 = __ldcg(q0 + j), v1 = __ldcg(q1 + j), v2 = __ldcg(q2 + j);
+      const double2 v3 = with_f ? __ldcg(q3 + j) : make_double2(0.0, 0.0);
       A[2 * j] = v0.x, A[2 * j + 1] = v0.y, C[2 * j] = v1.x, C[2 * j + 1] = v1.y;
       S[2 * j] = v2.x, S[2 * j + 1] = v2.y, F[2 * j] = v3.x, F[2 * j + 1] = v3.y;
     }
@@ -239,15 +241,25 @@ __device__ __forceinline__ void rows_load(double* const (&g)[4], long long r0, i
     for (int j = 0; j < BS_R; ++j) {
       const bool in = j < len;
       A[j] = in ? __ldcg(g[0] + r0 + j) : 0.0, C[j] = in ? __ldcg(g[1] + r0 + j) : 0.0;
-      S[j] = in ? __ldcg(g[2] + r0 + j) : 1.0, F[j] = in ? __ldcg(g[3] + r0 + j) : 0.0;
+      S[j] = in ? __ldcg(g[2] + r0 + j) : 1.0, F[j] = (in && with_f) ? __ldcg(g[3] + r0 + j) : 0.0;
     }
   }
 }
 // the two reduced rows of a chunk -> rows q, q + 1 (q even) of the arrays g[0..3]
-__device__ __forceinline__ void rows_store2(double* const (&g)[4], long long q, const double (&o)[8]) {
+__device__ __forceinline__ void rows_store2(double* const (&g)[4], long long q, const double (&o)[8], bool with_f) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) *reinterpret_cast<double2*>(g[k] + q) = make_double2(o[k], o[4 + k]);
+  for (int k = 0; k < 3; ++k) *reinterpret_cast<double2*>(g[k] + q) = make_double2(o[k], o[4 + k]);
+  if (with_f) *reinterpret_cast<double2*>(g[3] + q) = make_double2(o[3], o[7]);
 }
+// The right-hand side of the static problem is zero but for the two Dirichlet rows (time_independent.rs:168-182), and a chunk
+// of zero right-hand sides reduces to zero right-hand sides exactly.  At every level only the first chunk of the CTA that holds
+// the bar's first row and the last chunk of the CTA that holds its last row carry a right-hand side: nobody else writes or reads
+// the f arrays of the levels B and C (a quarter of their traffic; the launcher's scratch is zero-filled once, and positions
+// nobody writes stay zero).  An open end (a block of a split bar) has no Dirichlet row.
+struct FChunks {
+  bool first, last;  // this CTA holds the closed first / last row of the system
+  __device__ __forceinline__ bool operator()(int c, int nc) const { return (first && c == 0) || (last && c == nc - 1); }
+};
 template <bool KEEP>
 __device__ __forceinline__ void chunk_sweep(double (&A)[BS_R], double (&C)[BS_R], double (&S)[BS_R], double (&F)[BS_R], int len,
                                             double (&o)[8]) {
@@ -255,25 +267,26 @@ __device__ __forceinline__ void chunk_sweep(double (&A)[BS_R], double (&C)[BS_R]
   else chunk0_sweep<KEEP, false>(A, C, S, F, len, o);
 }
 // One streaming level, forward: the CTA's m rows at src[0..3][base ..] -> 2 rows per chunk at dst[0..3][dbase ..]
-__device__ __forceinline__ void level_forward(double* const (&src)[4], long long base, int m, double* const (&dst)[4], long long dbase, int t) {
+__device__ __forceinline__ void level_forward(double* const (&src)[4], long long base, int m, double* const (&dst)[4], long long dbase, int t,
+                                              const FChunks& fc) {
   const int nc = (m + BS_R - 1) / BS_R;
   for (int c = t; c < nc; c += BS_THREADS) {
     const ChunkGeom gm = chunk_geom(m, c, 0);
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
-    rows_load(src, base + gm.g0, gm.len, A, C, S, F);
+    rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nc));
     chunk_sweep<false>(A, C, S, F, gm.len, o);
-    rows_store2(dst, dbase + 2 * c, o);
+    rows_store2(dst, dbase + 2 * c, o, fc(c, nc));  // (its image is chunk c / 4 of the next level: first / last again)
   }
 }
 // ... and backward: usrc[ubase + 2 c], [.. + 1] hold u of the chunk's first / last row; u of all its rows -> udst[base ..]
 __device__ __forceinline__ void level_backward(double* const (&src)[4], long long base, int m, const double* usrc, long long ubase,
-                                               double* udst, int t) {
+                                               double* udst, int t, const FChunks& fc) {
   const int nc = (m + BS_R - 1) / BS_R;
   for (int c = t; c < nc; c += BS_THREADS) {
     const ChunkGeom gm = chunk_geom(m, c, 0);
     const double2 ends = __ldcg(reinterpret_cast<const double2*>(usrc + ubase + 2 * c));
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
-    rows_load(src, base + gm.g0, gm.len, A, C, S, F);
+    rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nc));
     chunk_sweep<true>(A, C, S, F, gm.len, o);
     chunk0_backward(A, C, S, F, gm.len, ends.x, ends.y, u);
     double* dst = udst + base + gm.g0;
@@ -312,6 +325,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     tb1 = blockIdx.x + 1 == gridDim.x ? ntiles : min(ntiles, ((long long)blockIdx.x + 1) * units / gridDim.x);
   }
   const int T = (int)(tb1 - tb0);  // >= 1: the launcher never starts more CTAs than tiles
+  const FChunks fc{tb0 == 0 && !(k.flags & BS_OPEN_LEFT), tb1 == ntiles && !(k.flags & BS_OPEN_RIGHT)};
   // the CTA's systems: level A rows [R0, R0 + mA) of the bar, then mB = 2 chunks(mA) rows at gb[..][oB ..], mC, mD (shared memory)
   const long long R0 = tb0 * BS_TILE;
   const int mA = (int)(min(k.m, tb1 * BS_TILE) - R0);
@@ -383,7 +397,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     if (gm.len >= 2) {
       double o[8];
       chunk_sweep<false>(A, C, S, F, gm.len, o);
-      rows_store2(a.gb, oB + 2 * c, o);
+      rows_store2(a.gb, oB + 2 * c, o, fc(c, nA));
     }
   }
   if (classify) {
@@ -396,14 +410,14 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   ol_stamp(a, 1);
   // ---- levels B and C forward (no barrier inside a level), level D in shared memory down to the CTA's two interface rows
   __syncthreads();
-  level_forward(a.gb, oB, mB, a.gc, oC, t);
+  level_forward(a.gb, oB, mB, a.gc, oC, t, fc);
   __syncthreads();
   ol_stamp(a, 6);
   LevelPtr c1 = sm.cta.level(0);
   for (int c = t; c < nC; c += BS_THREADS) {
     const ChunkGeom gm = chunk_geom(mC, c, 0);
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
-    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F);
+    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F, fc(c, nC));
     chunk_sweep<false>(A, C, S, F, gm.len, o);
     const int p0 = row_slot(2 * c, mD, PC), p1 = row_slot(2 * c + 1, mD, PC);
     c1.a[p0] = o[0], c1.c[p0] = o[1], c1.s[p0] = o[2], c1.d[p0] = o[3];
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     const ChunkGeom gm = chunk_geom(mC, c, 0);
     const double us = c1.d[row_slot(2 * c, mD, PC)], ue = c1.d[row_slot(2 * c + 1, mD, PC)];
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
-    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F);
+    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F, fc(c, nC));
     chunk_sweep<true>(A, C, S, F, gm.len, o);
     chunk0_backward(A, C, S, F, gm.len, us, ue, u);
 #pragma unroll
@@ -474,7 +488,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       if (j < gm.len) a.uc[oC + gm.g0 + j] = u[j];
   }
   __syncthreads();
-  level_backward(a.gb, oB, mB, a.uc, oC, a.ub, t);
+  level_backward(a.gb, oB, mB, a.uc, oC, a.ub, t, fc);
   __syncthreads();
 
   // ---- level A backward: the tiles again, last one first
