@@ -58,13 +58,85 @@ struct OneLaunchArgs {
                      // peer mailboxes (comm_kernels.cuh) between the passes and every rank solves the 2-rows-per-block system
 };
 
+// A small tridiagonal system in shared memory, reduced to its first and last row by CYCLIC REDUCTION, in place.
+// The pyramids of bigsys_kernels.cuh reduce 8 rows to 2 per level with one thread sweeping a chunk serially: five levels of
+// ~1 us each for the ~550 rows a CTA is left with, and again for the 2-rows-per-CTA system — measured 8 + 13.6 us forward and
+// ~9 us back per solve, with seven warps of eight parked at barriers.  Here a level halves the system with ALL rows at once:
+// at stride st the rows (2q + 1) st are eliminated from their kept neighbours 2q st and (2q + 2) st (one barrier, a dozen
+// multiply-adds and two reciprocals per kept row), ~log2(m) levels of ~0.15 us.  Row m-1 is always kept — it carries the
+// coupling to whatever follows the system (the next CTA, the next block of a split bar) exactly like row 0 carries the one
+// to what precedes it — so the result has the shape the callers already use: two rows coupling (u_0, u_{m-1}) to each other
+// and to the outside.  Rows stay in the row-excess form (a, c, s, f), diagonal = s - a - c: for an M-matrix (a, c <= 0 < diagonal)
+// the multipliers -a_i / d_j are non-negative and every update adds numbers of one sign, as in the chunk sweeps.
+// Eliminated rows keep their entries for the back-substitution, which writes u over f (d[]), last level first.
+// Row r lives at slot at(r) = r + r / 16: the strides 2 st of the levels are powers of two, which without the padding would
+// put every active row of a level into the same bank (measured: ~0.7 us per level instead of ~0.2).
+template <int CAP>
+struct CrSystem {
+  static constexpr int SLOTS = CAP + CAP / 16 + 1;
+  double a[SLOTS], c[SLOTS], s[SLOTS], d[SLOTS];
+  __device__ __forceinline__ static int at(int r) { return r + (r >> 4); }
+  // the kept neighbour to the right of active row j at stride st
+  __device__ __forceinline__ static int right_of(int j, int st, int m) { return j + st < m - 1 ? j + st : m - 1; }
+  __device__ __forceinline__ void reduce(int t, int m) {
+    for (int lg = 0; (1 << lg) < m - 1; ++lg) {  // stride st = 2^lg (shifts: an integer division per level would cost as much as the level)
+      const int st = 1 << lg;
+      __syncthreads();
+      const int nk = ((m - 2) >> (lg + 1)) + 1;  // regular kept rows 0, 2 st, ... (<= m - 2); slot nk is row m-1
+      for (int q = t; q <= nk; q += BS_THREADS) {
+        int i, jl = -1, jr = -1;
+        if (q < nk) {
+          i = q << (lg + 1);
+          if (q > 0) jl = i - st;
+          if (i + st < m - 1) jr = i + st;
+        } else {
+          i = m - 1;
+          const int mult = (m - 2) >> lg;  // its neighbour to the left at this stride is mult st: eliminated iff mult is odd
+          if (mult & 1) jl = mult << lg;
+        }
+        const int pi = at(i);
+        double ai = a[pi], ci = c[pi], si = s[pi], fi = d[pi];
+        if (jl >= 0) {
+          const int pj = at(jl);
+          const double aj = a[pj], cj = c[pj], sj = s[pj];
+          const double k1 = -ai * pivot_rcp((sj - aj) - cj);
+          si = fma(k1, sj, si), fi = fma(k1, d[pj], fi), ai = k1 * aj;
+        }
+        if (jr >= 0) {
+          const int pj = at(jr);
+          const double aj = a[pj], cj = c[pj], sj = s[pj];
+          const double k2 = -ci * pivot_rcp((sj - aj) - cj);
+          si = fma(k2, sj, si), fi = fma(k2, d[pj], fi), ci = k2 * cj;
+        }
+        a[pi] = ai, c[pi] = ci, s[pi] = si, d[pi] = fi;  // (nobody reads a kept row at this level but its own thread)
+      }
+    }
+    __syncthreads();
+  }
+  // d[at(0)] and d[at(m-1)] hold u_0 and u_{m-1}; every other d[at(j)] becomes u_j
+  __device__ __forceinline__ void backsolve(int t, int m) {
+    int st = 1;
+    while (2 * st < m - 1) st <<= 1;  // the last stride reduce() used (none when m <= 2)
+    for (; st >= 1 && m > 2; st >>= 1) {
+      __syncthreads();
+      for (int j = (2 * t + 1) * st; j < m - 1; j += 2 * BS_THREADS * st) {
+        const int pj = at(j);
+        const double aj = a[pj], cj = c[pj];
+        const double num = fma(-cj, d[at(right_of(j, st, m))], fma(-aj, d[at(j - st)], d[pj]));
+        d[pj] = num * pivot_rcp((s[pj] - aj) - cj);
+      }
+    }
+    __syncthreads();
+  }
+};
+
 template <int P1C>
 struct OneLaunchSmem {
   union Work {
     alignas(1024) double stage[2][BS_TILE];       // TMA stage.  level A forward: x in [0]; backward: 1/h in [0], excess in [1]
-    Pyramid<OL_P1M> mid;                          // only between the two passes, when no copy is in flight
+    CrSystem<8 * OL_P1M> mid;                     // only between the two passes, when no copy is in flight
   } w;
-  Pyramid<P1C> cta;                               // level D
+  CrSystem<8 * P1C> cta;                          // level D
   double4 uv[OL_TAB_CAP + 1];
   double qx[OL_TAB_CAP];
   unsigned short guessf[GUESS_BINS + 2];
@@ -331,7 +403,6 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   const int mA = (int)(min(k.m, tb1 * BS_TILE) - R0);
   const int nA = (mA + BS_R - 1) / BS_R, mB = 2 * nA, nB = (mB + BS_R - 1) / BS_R, mC = 2 * nB, nC = (mC + BS_R - 1) / BS_R, mD = 2 * nC;
   const long long oB = tb0 * OL_ROWS_B, oC = tb0 * OL_ROWS_C;
-  constexpr int PC = lvl_stride(P1C);
   const TiK K = make_tik(a.rule, a.P);
   for (int j = t; j <= a.rule.m; j += BS_THREADS) sm.uv[j] = a.rule.uv[j];
   for (int j = t; j < a.rule.m; j += BS_THREADS) sm.qx[j] = a.rule.x[j];
@@ -413,24 +484,21 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   level_forward(a.gb, oB, mB, a.gc, oC, t, fc);
   __syncthreads();
   ol_stamp(a, 6);
-  LevelPtr c1 = sm.cta.level(0);
   for (int c = t; c < nC; c += BS_THREADS) {
     const ChunkGeom gm = chunk_geom(mC, c, 0);
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
     rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F, fc(c, nC));
     chunk_sweep<false>(A, C, S, F, gm.len, o);
-    const int p0 = row_slot(2 * c, mD, PC), p1 = row_slot(2 * c + 1, mD, PC);
-    c1.a[p0] = o[0], c1.c[p0] = o[1], c1.s[p0] = o[2], c1.d[p0] = o[3];
-    c1.a[p1] = o[4], c1.c[p1] = o[5], c1.s[p1] = o[6], c1.d[p1] = o[7];
+    const int p0 = sm.cta.at(2 * c), p1 = sm.cta.at(2 * c + 1);
+    sm.cta.a[p0] = o[0], sm.cta.c[p0] = o[1], sm.cta.s[p0] = o[2], sm.cta.d[p0] = o[3];
+    sm.cta.a[p1] = o[4], sm.cta.c[p1] = o[5], sm.cta.s[p1] = o[6], sm.cta.d[p1] = o[7];
   }
   ol_stamp(a, 7);
-  sm.cta.reduce_cold(t, mD);
-  {
-    LevelPtr top = sm.cta.top();
-    if (t < 2) {
-      const long long o = 2LL * blockIdx.x + t;
-      k.red_a[o] = top.a[t], k.red_c[o] = top.c[t], k.red_s[o] = top.s[t], k.red_f[o] = top.d[t];
-    }
+  sm.cta.reduce(t, mD);
+  if (t < 2) {  // the CTA's two interface rows: its first and its last
+    const long long o = 2LL * blockIdx.x + t;
+    const int r = sm.cta.at(t ? mD - 1 : 0);
+    k.red_a[o] = sm.cta.a[r], k.red_c[o] = sm.cta.c[r], k.red_s[o] = sm.cta.s[r], k.red_f[o] = sm.cta.d[r];
   }
   asm volatile("fence.proxy.async.global;" ::: "memory");  // writers' side of the cross-proxy ordering (see request_rs): both are needed
   __threadfence();
@@ -440,21 +508,20 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   // ---- the 2-rows-per-CTA system, solved by every CTA for itself (the work area is free: no copy is in flight)
   {
     const int m2 = 2 * (int)gridDim.x;
-    constexpr int PM = lvl_stride(OL_P1M);
-    LevelPtr l1 = sm.w.mid.level(0);
+    auto& mid = sm.w.mid;
     for (int rr = t; rr < m2; rr += BS_THREADS) {
-      const int p = row_slot(rr, m2, PM);
-      l1.a[p] = __ldcg(k.red_a + rr), l1.c[p] = __ldcg(k.red_c + rr), l1.s[p] = __ldcg(k.red_s + rr), l1.d[p] = __ldcg(k.red_f + rr);
+      const int pr = mid.at(rr);
+      mid.a[pr] = __ldcg(k.red_a + rr), mid.c[pr] = __ldcg(k.red_c + rr), mid.s[pr] = __ldcg(k.red_s + rr), mid.d[pr] = __ldcg(k.red_f + rr);
     }
-    sm.w.mid.reduce_cold(t, m2);
-    LevelPtr top = sm.w.mid.top();
+    mid.reduce(t, m2);
+    const int last = mid.at(m2 - 1);
     if (a.px.world > 1) {
       // One block of a split bar: its two rows keep their couplings to the neighbouring blocks.  CTA 0 posts them to every
       // rank (every CTA holds the same bits), every CTA collects all of them from the local mailbox and solves the
       // 2-rows-per-block interface system for itself: no launch, no host, one NVLink store + flag per peer.
       if (t < a.px.world) {
         if (blockIdx.x == 0) {
-          const double v[8] = {top.a[0], top.c[0], top.s[0], top.d[0], top.a[1], top.c[1], top.s[1], top.d[1]};
+          const double v[8] = {mid.a[0], mid.c[0], mid.s[0], mid.d[0], mid.a[last], mid.c[last], mid.s[last], mid.d[last]};
           mb_post(a.px, t, v);
         }
         mb_wait(a.px, t, sm.xrows + 8 * t);
@@ -462,23 +529,23 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       __syncthreads();
       if (t == 0) {
         interface_solve_serial(sm.xrows, 2 * a.px.world, sm.xends, sm.xwork);
-        top.d[0] = sm.xends[2 * a.px.rank], top.d[1] = sm.xends[2 * a.px.rank + 1];
+        mid.d[0] = sm.xends[2 * a.px.rank], mid.d[last] = sm.xends[2 * a.px.rank + 1];
       }
-    } else if (t == 0) {  // closed 2 x 2 system (a_0 = c_1 = 0), as in mid_body
-      const double c0 = top.c[0], s0 = top.s[0], f0 = top.d[0], a1 = top.a[1], s1 = top.s[1], f1 = top.d[1];
+    } else if (t == 0) {  // closed 2 x 2 system (a_0 = c_last = 0), as in mid_body
+      const double c0 = mid.c[0], s0 = mid.s[0], f0 = mid.d[0], a1 = mid.a[last], s1 = mid.s[last], f1 = mid.d[last];
       const double det = (s0 * s1 - s0 * a1) - c0 * s1;
-      top.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;
-      top.d[1] = ((s0 - c0) * f1 - a1 * f0) / det;
+      mid.d[0] = ((s1 - a1) * f0 - c0 * f1) / det;
+      mid.d[last] = ((s0 - c0) * f1 - a1 * f0) / det;
     }
-    sm.w.mid.backsolve_cold(t, m2);
-    if (t < 2) sm.cta.top().d[t] = l1.d[row_slot(2 * (int)blockIdx.x + t, m2, PM)];
+    mid.backsolve(t, m2);
+    if (t < 2) sm.cta.d[sm.cta.at(t ? mD - 1 : 0)] = mid.d[mid.at(2 * (int)blockIdx.x + t)];
   }
-  sm.cta.backsolve_cold(t, mD);  // starts and ends with a CTA barrier: the work area is free again afterwards
+  sm.cta.backsolve(t, mD);  // starts and ends with a CTA barrier: the work area is free again afterwards
   ol_stamp(a, 4);
   // ---- levels C and B backward
   for (int c = t; c < nC; c += BS_THREADS) {
     const ChunkGeom gm = chunk_geom(mC, c, 0);
-    const double us = c1.d[row_slot(2 * c, mD, PC)], ue = c1.d[row_slot(2 * c + 1, mD, PC)];
+    const double us = sm.cta.d[sm.cta.at(2 * c)], ue = sm.cta.d[sm.cta.at(2 * c + 1)];
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
     rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F, fc(c, nC));
     chunk_sweep<true>(A, C, S, F, gm.len, o);
