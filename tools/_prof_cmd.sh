@@ -1,5 +1,8 @@
-N=$1
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29577"
-timeout 400 $T tools/split_bar_check.py --nodes 10000000 > gpurun_out/r3j_split${N}.txt 2>&1
-DZB_COMM_NO_PEER=1 timeout 400 $T tools/split_bar_check.py --nodes 10000000 --no-check --assembly fast > gpurun_out/r3j_split${N}_nccl.txt 2>&1
-timeout 600 $T bench.py --gpus $N --steps 100 > gpurun_out/r3j_bench${N}.json 2> gpurun_out/r3j_bench${N}.err
+for s in 0 60 100 140 180; do
+echo "skew $s" >> gpurun_out/r3k_skew.txt
+DZB_OL_SKEW=$s python tools/time_long_solve.py 10000000 4000000 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({k:round(v['ms'],4) for k,v in d.items()})" >> gpurun_out/r3k_skew.txt
+done
+DZB_OL_SKEW=100 python -m pytest tests/test_gpu_onelaunch.py -x -q 2>&1 | tail -2 >> gpurun_out/r3k_skew.txt
