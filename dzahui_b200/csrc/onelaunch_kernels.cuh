@@ -625,7 +625,10 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
-// Two builds: level D of 72 chunks (18 tiles per CTA) at two CTAs per SM (128 registers), of 256 chunks (64 tiles) at one.
+// Two builds: level D of up to 1024 rows (32 tiles per CTA: 1.9 10^7 rows on a B200) at two CTAs per SM (128 registers), of up to
+// 2048 rows (64 tiles) at one CTA per SM for devices where two do not fit.  (The cyclic reduction needs 34 bytes of shared memory
+// per level-D row; with the pyramids the two-per-SM build stopped at 18 tiles per CTA and anything longer ran at one CTA per
+// SM, 0.27 instead of ~0.21 ms at 1.2 10^7 rows.)
 // (Three CTAs per SM with 80 registers spill and are slower: 0.275 against 0.209 ms at 10^7 rows.)
 template <int P1C, int MINB>
 inline int onelaunch_capacity() {
@@ -677,7 +680,7 @@ inline int onelaunch_run(BigSys* s, OneLaunchArgs args, int (&caps)[2], cudaStre
                 bigsys_map(s, args.k.p0, m, &cx) && bigsys_map(s, args.s_ex, m, &cs);
   if (!use_tma) std::memset(&cx, 0, sizeof cx), cs = cx;
   void* params[] = {&cx, &cs, &args, &use_tma};
-  int rc = onelaunch_try<72, 2>(args, tiles, caps[0], params, st, launches, grid_out);
+  int rc = onelaunch_try<128, 2>(args, tiles, caps[0], params, st, launches, grid_out);
   if (rc < 0) rc = onelaunch_try<256, 1>(args, tiles, caps[1], params, st, launches, grid_out);
   return rc;
 }

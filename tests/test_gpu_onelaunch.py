@@ -39,8 +39,9 @@ def fast_parallel(gpu):
 
 # two tiles exactly, ragged tails (7 + 2 split, single left-over row), fewer tiles than CTAs, exactly one tile per CTA on a
 # 148-SM part (296), more tiles than CTAs with uneven tile counts per CTA, the (TILE - 1) + 2 split of the last two tiles
+# ... and a bar long enough (more than 18 tiles per CTA at two CTAs per SM) for the one-CTA-per-SM build with its 2048-row level D
 @pytest.mark.parametrize("n", [4096, 4097, 4105, 6000, 2048 * 37 + 1, 2048 * 296, 2048 * 296 + 1, 2048 * 297 + 1234, 1_000_003,
-                               2048 * 1000 + 9, 5_000_001])
+                               2048 * 1000 + 9, 5_000_001, 12_000_007])
 def test_onelaunch_vs_f128_and_multilaunch(gpu, oracle, n):
     mesh = jittered(n, n)
     p = gpu.DiffussionParams.time_independent().mu(1.0).b(0.5).boundary_conditions(-2.0, 7.0).build()
