@@ -403,6 +403,11 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   const int mA = (int)(min(k.m, tb1 * BS_TILE) - R0);
   const int nA = (mA + BS_R - 1) / BS_R, mB = 2 * nA, nB = (mB + BS_R - 1) / BS_R, mC = 2 * nB, nC = (mC + BS_R - 1) / BS_R, mD = 2 * nC;
   const long long oB = tb0 * OL_ROWS_B, oC = tb0 * OL_ROWS_C;
+  // How many chunk levels the CTA goes through before its system fits the shared-memory cyclic reduction (8 P1C rows):
+  // 1: level A's reduced rows go there directly (no global scratch at all: up to 8 P1C / 512 tiles per CTA);
+  // 2: level B is swept from global scratch into it; 3: levels B and C.  A CTA-local choice.
+  const int depth = mB <= 8 * P1C ? 1 : (mC <= 8 * P1C ? 2 : 3);
+  const int mS = depth == 1 ? mB : (depth == 2 ? mC : mD);  // rows of the CTA's shared-memory system
   const TiK K = make_tik(a.rule, a.P);
   for (int j = t; j <= a.rule.m; j += BS_THREADS) sm.uv[j] = a.rule.uv[j];
   for (int j = t; j < a.rule.m; j += BS_THREADS) sm.qx[j] = a.rule.x[j];
@@ -468,7 +473,13 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     if (gm.len >= 2) {
       double o[8];
       chunk_sweep<false>(A, C, S, F, gm.len, o);
-      rows_store2(a.gb, oB + 2 * c, o, fc(c, nA));
+      if (depth == 1) {
+        const int p0 = sm.cta.at(2 * c), p1 = sm.cta.at(2 * c + 1);
+        sm.cta.a[p0] = o[0], sm.cta.c[p0] = o[1], sm.cta.s[p0] = o[2], sm.cta.d[p0] = o[3];
+        sm.cta.a[p1] = o[4], sm.cta.c[p1] = o[5], sm.cta.s[p1] = o[6], sm.cta.d[p1] = o[7];
+      } else {
+        rows_store2(a.gb, oB + 2 * c, o, fc(c, nA));
+      }
     }
   }
   if (classify) {
@@ -479,25 +490,33 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     }
   }
   ol_stamp(a, 1);
-  // ---- levels B and C forward (no barrier inside a level), level D in shared memory down to the CTA's two interface rows
+  // ---- levels B and C forward as far as needed (no barrier inside a level), then the CTA's system in shared memory down to
+  // its two interface rows
   __syncthreads();
-  level_forward(a.gb, oB, mB, a.gc, oC, t, fc);
-  __syncthreads();
+  if (depth == 3) {
+    level_forward(a.gb, oB, mB, a.gc, oC, t, fc);
+    __syncthreads();
+  }
   ol_stamp(a, 6);
-  for (int c = t; c < nC; c += BS_THREADS) {
-    const ChunkGeom gm = chunk_geom(mC, c, 0);
-    double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
-    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F, fc(c, nC));
-    chunk_sweep<false>(A, C, S, F, gm.len, o);
-    const int p0 = sm.cta.at(2 * c), p1 = sm.cta.at(2 * c + 1);
-    sm.cta.a[p0] = o[0], sm.cta.c[p0] = o[1], sm.cta.s[p0] = o[2], sm.cta.d[p0] = o[3];
-    sm.cta.a[p1] = o[4], sm.cta.c[p1] = o[5], sm.cta.s[p1] = o[6], sm.cta.d[p1] = o[7];
+  if (depth >= 2) {  // the last global level -> shared memory
+    double* const(&src)[4] = depth == 3 ? a.gc : a.gb;
+    const long long base = depth == 3 ? oC : oB;
+    const int mL = depth == 3 ? mC : mB, nL = depth == 3 ? nC : nB;
+    for (int c = t; c < nL; c += BS_THREADS) {
+      const ChunkGeom gm = chunk_geom(mL, c, 0);
+      double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
+      rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nL));
+      chunk_sweep<false>(A, C, S, F, gm.len, o);
+      const int p0 = sm.cta.at(2 * c), p1 = sm.cta.at(2 * c + 1);
+      sm.cta.a[p0] = o[0], sm.cta.c[p0] = o[1], sm.cta.s[p0] = o[2], sm.cta.d[p0] = o[3];
+      sm.cta.a[p1] = o[4], sm.cta.c[p1] = o[5], sm.cta.s[p1] = o[6], sm.cta.d[p1] = o[7];
+    }
   }
   ol_stamp(a, 7);
-  sm.cta.reduce(t, mD);
+  sm.cta.reduce(t, mS);
   if (t < 2) {  // the CTA's two interface rows: its first and its last
     const long long o = 2LL * blockIdx.x + t;
-    const int r = sm.cta.at(t ? mD - 1 : 0);
+    const int r = sm.cta.at(t ? mS - 1 : 0);
     k.red_a[o] = sm.cta.a[r], k.red_c[o] = sm.cta.c[r], k.red_s[o] = sm.cta.s[r], k.red_f[o] = sm.cta.d[r];
   }
   asm volatile("fence.proxy.async.global;" ::: "memory");  // writers' side of the cross-proxy ordering (see request_rs): both are needed
@@ -538,25 +557,33 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       mid.d[last] = ((s0 - c0) * f1 - a1 * f0) / det;
     }
     mid.backsolve(t, m2);
-    if (t < 2) sm.cta.d[sm.cta.at(t ? mD - 1 : 0)] = mid.d[mid.at(2 * (int)blockIdx.x + t)];
+    if (t < 2) sm.cta.d[sm.cta.at(t ? mS - 1 : 0)] = mid.d[mid.at(2 * (int)blockIdx.x + t)];
   }
-  sm.cta.backsolve(t, mD);  // starts and ends with a CTA barrier: the work area is free again afterwards
+  sm.cta.backsolve(t, mS);  // starts and ends with a CTA barrier: the work area is free again afterwards
   ol_stamp(a, 4);
-  // ---- levels C and B backward
-  for (int c = t; c < nC; c += BS_THREADS) {
-    const ChunkGeom gm = chunk_geom(mC, c, 0);
-    const double us = sm.cta.d[sm.cta.at(2 * c)], ue = sm.cta.d[sm.cta.at(2 * c + 1)];
-    double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
-    rows_load(a.gc, oC + gm.g0, gm.len, A, C, S, F, fc(c, nC));
-    chunk_sweep<true>(A, C, S, F, gm.len, o);
-    chunk0_backward(A, C, S, F, gm.len, us, ue, u);
+  // ---- the global levels backward
+  if (depth >= 2) {  // shared memory -> the last global level
+    double* const(&src)[4] = depth == 3 ? a.gc : a.gb;
+    const long long base = depth == 3 ? oC : oB;
+    const int mL = depth == 3 ? mC : mB, nL = depth == 3 ? nC : nB;
+    double* udst = depth == 3 ? a.uc : a.ub;
+    for (int c = t; c < nL; c += BS_THREADS) {
+      const ChunkGeom gm = chunk_geom(mL, c, 0);
+      const double us = sm.cta.d[sm.cta.at(2 * c)], ue = sm.cta.d[sm.cta.at(2 * c + 1)];
+      double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
+      rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nL));
+      chunk_sweep<true>(A, C, S, F, gm.len, o);
+      chunk0_backward(A, C, S, F, gm.len, us, ue, u);
 #pragma unroll
-    for (int j = 0; j < BS_R; ++j)
-      if (j < gm.len) a.uc[oC + gm.g0 + j] = u[j];
+      for (int j = 0; j < BS_R; ++j)
+        if (j < gm.len) udst[base + gm.g0 + j] = u[j];
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  level_backward(a.gb, oB, mB, a.uc, oC, a.ub, t, fc);
-  __syncthreads();
+  if (depth == 3) {
+    level_backward(a.gb, oB, mB, a.uc, oC, a.ub, t, fc);
+    __syncthreads();
+  }
 
   // ---- level A backward: the tiles again, last one first
   auto request_rs = [&](long long tile) {  // thread 0
@@ -581,7 +608,10 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     const ChunkGeom gm = chunk_geom(mA, c, 0);
     const long long G0 = R0 + gm.g0;
     double2 ends = make_double2(0.0, 0.0);
-    if (gm.len >= 2) ends = __ldcg(reinterpret_cast<const double2*>(a.ub + oB + 2 * c));
+    if (gm.len >= 2) {
+      if (depth == 1) ends = make_double2(sm.cta.d[sm.cta.at(2 * c)], sm.cta.d[sm.cta.at(2 * c + 1)]);
+      else ends = __ldcg(reinterpret_cast<const double2*>(a.ub + oB + 2 * c));
+    }
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R];
     {
       double X[12], Sv[BS_R];
@@ -625,8 +655,10 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
-// Two builds: level D of up to 1024 rows (32 tiles per CTA: 1.9 10^7 rows on a B200) at two CTAs per SM (128 registers), of up to
-// 2048 rows (64 tiles) at one CTA per SM for devices where two do not fit.  (The cyclic reduction needs 34 bytes of shared memory
+// Two builds: a shared-memory system of up to 1024 rows (32 tiles per CTA: 1.9 10^7 rows on a B200; up to 2 tiles per CTA without
+// any global level, up to 8 with one) at two CTAs per SM (128 registers), of up to 2048 rows (64 tiles) at one CTA per SM for
+// devices where two do not fit.  (1536 rows would take the blocks of a bar split over 8 GPUs without a global level, but the
+// 17 KB of shared memory come out of the L1: 2-4 % slower at 10^7 rows and beyond.)  (The cyclic reduction needs 34 bytes of shared memory
 // per level-D row; with the pyramids the two-per-SM build stopped at 18 tiles per CTA and anything longer ran at one CTA per
 // SM, 0.27 instead of ~0.21 ms at 1.2 10^7 rows.)
 // (Three CTAs per SM with 80 registers spill and are slower: 0.275 against 0.209 ms at 10^7 rows.)
