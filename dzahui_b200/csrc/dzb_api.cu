@@ -415,6 +415,8 @@ struct dzb_solver {
   // accumulated by the kernel and looked at when somebody reads the result (no host round trip inside a collective solve)
   size_t x_pad = 0;
   bool cls_pending = false;
+  bool ol_checked_valid = false;             // the one-launch kernel has checked the coordinates stamped ol_checked_version itself:
+  unsigned long long ol_checked_version = 0;  // later solves of the same coordinates skip the per-row checks
 };
 
 struct dzb_comm;
@@ -1134,9 +1136,11 @@ static int static_materialise(dzb_solver* s) {
 // system (matrix class, size, no cooperative launch) and the caller goes on with materialised bands.
 static int static_solve_onelaunch(dzb_solver* s, bool* done, const dzb::PeerBox* px = nullptr) {
   *done = false;
-  const bool known = s->classified_valid && s->classified_version == s->x_version;
+  // `known`: the kernel itself has looked at these coordinates (every row covered by the closed form, matrix class).  A class
+  // taken from materialised bands (at creation) says nothing about the former, so it only serves to rule the path OUT.
+  const bool known = s->ol_checked_valid && s->ol_checked_version == s->x_version;
   if (!s->is_block) {
-    if (known && !s->classified_ok) return DZB_OK;
+    if (s->classified_valid && s->classified_version == s->x_version && !s->classified_ok) return DZB_OK;
     if (s->fused_bad_valid && s->fused_bad_version == s->x_version) return DZB_OK;
   }
   dzb::OneLaunchArgs a{};
@@ -1174,7 +1178,7 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done, const dzb::PeerBox*
     return DZB_OK;
   }
   if (s->is_block) {  // a collective: never waits for the host; the flags are looked at by dzb_solver_block_read / _status
-    if (!known) s->cls_pending = true, s->classified_valid = true, s->classified_version = s->x_version, s->classified_ok = true;
+    if (!known) s->cls_pending = true, s->ol_checked_valid = true, s->ol_checked_version = s->x_version;
     *done = true;
     return DZB_OK;
   }
@@ -1223,6 +1227,7 @@ static int static_solve_onelaunch(dzb_solver* s, bool* done, const dzb::PeerBox*
     }
     s->classified_valid = true, s->classified_version = s->x_version, s->classified_ok = f[0] != 3;
     if (!s->classified_ok) return DZB_OK;
+    s->ol_checked_valid = true, s->ol_checked_version = s->x_version;
   }
   *done = true;
   return DZB_OK;

@@ -209,10 +209,15 @@ __device__ __forceinline__ void ti_rows_from_nodes(const double (&X)[12], long l
 #pragma unroll
   for (int j = 0; j < BS_R; ++j) {
     const bool inter = j >= jlo && j < jhi;
-    bool ok = E[j].ok && E[j + 1].ok;
-    ok = ok && (j < jl2 || !(X[j + 1] < X[j]));
-    ok = ok && (j >= jh2 || !(X[j + 4] < X[j + 3]));
-    bad = bad || (inter && !ok);
+    // whether the closed form covers the row is a property of the coordinates: looked at (together with the matrix class) the
+    // first time these coordinates are solved for, taken for granted afterwards
+    bool ok = true;
+    if (CLASSIFY) {
+      ok = E[j].ok && E[j + 1].ok;
+      ok = ok && (j < jl2 || !(X[j + 1] < X[j]));
+      ok = ok && (j >= jh2 || !(X[j + 4] < X[j + 3]));
+      bad = bad || (inter && !ok);
+    }
     double lo, di, up;
     ti_row(E[j], E[j + 1], X[j + 1], X[j + 2], X[j + 3], K, tb.uv, tb.guessf, tb.qx, tb.m, lo, di, up, inter && ok);
     const double ex = excess3(lo, di, up);

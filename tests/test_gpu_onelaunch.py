@@ -158,3 +158,29 @@ def test_onelaunch_refuses_what_the_partitioned_solver_must_not_touch(gpu, oracl
     assert np.array_equal(np.isfinite(u), ok)
     if ok.all():
         assert rel_l2(u, ref) <= 1e-8
+
+
+def test_degenerate_spacing_at_creation(gpu, oracle):
+    """the same degenerate mesh handed to the constructor: the class the constructor takes from the materialised bands says
+    nothing about closed-form coverage, so the first solve must still let the kernel look at every row and fall back"""
+    n = 20_000
+    bad = jittered(n, 4)
+    bad[5000] = np.nextafter(bad[4999], 1.0)
+    bad[12000] = bad[12001]
+    p = gpu.DiffussionParams.time_independent().mu(1.0).b(1.0).boundary_conditions(1.0, 15.0).build()
+    s = gpu.DiffussionSolverTimeIndependent(p, bad, 150, fast_parallel(gpu))
+    u = s.solve(0.0)
+    assert ONE not in s.path()
+    lo, di, up, rhs = s.bands()
+    ref = oracle.thomas(lo, di, up, rhs)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(u), ok)
+    if ok.all():
+        assert rel_l2(u, ref) <= 1e-8
+    s.close()
+    good = jittered(n, 5)
+    s = gpu.DiffussionSolverTimeIndependent(p, good, 150, fast_parallel(gpu))
+    u = s.solve(0.0)
+    assert ONE in s.path()
+    assert s.solve(0.0).tobytes() == u.tobytes()      # the second solve skips the per-row checks: same bits
+    s.close()
