@@ -136,13 +136,18 @@ struct OneLaunchSmem {
     alignas(1024) double stage[2][BS_TILE];       // TMA stage.  level A forward: x in [0]; backward: 1/h in [0], excess in [1]
     CrSystem<8 * OL_P1M> mid;                     // only between the two passes, when no copy is in flight
   } w;
-  CrSystem<8 * P1C> cta;                          // level D
+  // level D.  With two or more chunk levels (depth >= 2) the system is dead while level A runs — its rows arrive after the
+  // forward pass and its solutions have been handed to global scratch before the backward pass — so its space doubles as
+  // the backward pass's second stage (stage2()): two tiles in flight per CTA without another 32 KB taken from the L1
+  alignas(1024) CrSystem<8 * P1C> cta;
+  static_assert(sizeof(CrSystem<8 * P1C>) >= 2 * BS_TILE * sizeof(double), "the second stage lives in the level-D system");
+  __device__ __forceinline__ double* stage2(int which) { return reinterpret_cast<double*>(&cta) + which * BS_TILE; }
   double4 uv[OL_TAB_CAP + 1];
   double qx[OL_TAB_CAP];
   unsigned short guessf[GUESS_BINS + 2];
-  alignas(16) double halo[4];                     // the two values either side of a staged tile (forward: x; backward: [0..1] = 1/h)
+  alignas(16) double halo[8];                     // the two coordinates either side of a staged tile ([4..7]: of the tile in the second stage)
   double xrows[MB_MAX * 8], xends[2 * MB_MAX], xwork[4 * MB_MAX];  // split bar: everybody's interface rows, their solution
-  alignas(8) unsigned long long mbar;
+  alignas(8) unsigned long long mbar, mbar2;     // mbar2: the second stage of the backward pass
 };
 // 16 or 32 bytes next to a staged tile, through the same mbarrier (plain bulk copy: 16-byte aligned, size a multiple of 16)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   for (int j = t; j < GUESS_BINS + 2; j += BS_THREADS) sm.guessf[j] = a.rule.guessf[j];
   const OlTables tb{sm.uv, sm.guessf, sm.qx, a.rule.m};
   const bool classify = a.class_flags != nullptr;
-  if (t == 0) mbar_init(&sm.mbar, 1);
+  if (t == 0) mbar_init(&sm.mbar, 1), mbar_init(&sm.mbar2, 1);
   __syncthreads();
   auto staged = [&](long long tile) { return use_tma && (tile + 1) * BS_TILE <= k.m; };  // (m % BS_TILE == 1 is refused by the launcher)
   unsigned phase = 0;
@@ -590,26 +595,38 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     __syncthreads();
   }
 
-  // ---- level A backward: the tiles again, last one first
-  auto request_rs = [&](long long tile) {  // thread 0
+  // ---- level A backward: the tiles again, last one first.  This pass waits for its tiles if only one is in flight (ncu: a tenth
+  // of the kernel's stall samples sat on the mbarrier here — 32 KB per tile against 16 KB forward, and less arithmetic to hide them
+  // behind), so with depth >= 2 the tiles alternate between the work area and the dead level-D system: the request for the tile
+  // after next goes out as soon as this tile's chunks are in registers
+  const bool two_stages = depth >= 2;
+  auto request_rs = [&](long long tile, int b) {  // thread 0
     // as in request_x; here the source, too, was written with ordinary stores (the forward pass, other threads, another CTA
     // for the value left of the CTA's first tile): generic -> async ordering for both state spaces, from the issuing thread,
     // after it has synchronised with the writers (the grid barrier and the CTA barriers since)
     asm volatile("fence.proxy.async;" ::: "memory");
     const bool hh = x_halo(tile);
-    mbar_arrive_expect_tx(&sm.mbar, (unsigned)(2 * BS_TILE * sizeof(double)) + (hh ? 32u : 0u));
+    unsigned long long* mb = b ? &sm.mbar2 : &sm.mbar;
+    mbar_arrive_expect_tx(mb, (unsigned)(2 * BS_TILE * sizeof(double)) + (hh ? 32u : 0u));
     const int row = (int)(tile * BS_TMA_BOX);
-    tma_load_box(sm.w.stage[0], &map_x, row, &sm.mbar);
-    tma_load_box(sm.w.stage[1], &map_s, row, &sm.mbar);
+    tma_load_box(b ? sm.stage2(0) : sm.w.stage[0], &map_x, row, mb);
+    tma_load_box(b ? sm.stage2(1) : sm.w.stage[1], &map_s, row, mb);
     if (hh) {
-      bulk_load(sm.halo, k.p0 + tile * BS_TILE - 2, 16, &sm.mbar);
-      bulk_load(sm.halo + 2, k.p0 + (tile + 1) * BS_TILE, 16, &sm.mbar);
+      bulk_load(sm.halo + 4 * b, k.p0 + tile * BS_TILE - 2, 16, mb);
+      bulk_load(sm.halo + 4 * b + 2, k.p0 + (tile + 1) * BS_TILE, 16, mb);
     }
   };
-  if (t == 0 && staged(tb1 - 1)) request_rs(tb1 - 1);  // (its proxy fence also covers the ordinary stores of the middle solve into the work area)
+  // (the first request's proxy fence also covers the ordinary stores of the middle solve into the work area and of level D)
+  if (t == 0) {
+    if (staged(tb1 - 1)) request_rs(tb1 - 1, 0);
+    if (two_stages && T >= 2 && staged(tb1 - 2)) request_rs(tb1 - 2, 1);
+  }
+  unsigned phase2 = 0;
+  const int ahead = two_stages ? 2 : 1;
   for (int kk = T - 1; kk >= 0; --kk) {
     const long long tile = tb0 + kk;
     const int c = kk * BS_THREADS + t;
+    const int b = two_stages ? ((T - 1 - kk) & 1) : 0;  // the stage this tile went to
     const ChunkGeom gm = chunk_geom(mA, c, 0);
     const long long G0 = R0 + gm.g0;
     double2 ends = make_double2(0.0, 0.0);
@@ -621,17 +638,22 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     {
       double X[12], Sv[BS_R];
       if (staged(tile)) {
-        mbar_wait(&sm.mbar, phase);
-        phase ^= 1;
-        nodes_from_stage(sm.w.stage[0], sm.halo, x_halo(tile), a, G0, t, X);
-        stage_chunk(sm.w.stage[1], t, Sv);
+        if (b) {
+          mbar_wait(&sm.mbar2, phase2);
+          phase2 ^= 1;
+        } else {
+          mbar_wait(&sm.mbar, phase);
+          phase ^= 1;
+        }
+        nodes_from_stage(b ? sm.stage2(0) : sm.w.stage[0], sm.halo + 4 * b, x_halo(tile), a, G0, t, X);
+        stage_chunk(b ? sm.stage2(1) : sm.w.stage[1], t, Sv);
       } else {
         nodes_direct(a, G0, X);
 #pragma unroll
         for (int j = 0; j < BS_R; ++j) Sv[j] = j < gm.len ? __ldcg(a.s_ex + G0 + j) : 1.0;
       }
-      __syncthreads();  // every chunk is in registers: the stage can take the next tile
-      if (t == 0 && kk > 0 && staged(tile - 1)) request_rs(tile - 1);
+      __syncthreads();  // every chunk is in registers: the stage can take the tile after next (the next one with a single stage)
+      if (t == 0 && kk >= ahead && staged(tile - ahead)) request_rs(tile - ahead, b);
       ti_rows_from_scratch(X, Sv, G0 + a.halo_left, gm.len, a, K, A, C, S, F);
     }
     if (gm.len >= 2) {
