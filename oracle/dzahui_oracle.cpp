@@ -952,6 +952,96 @@ int dzo_thomas_f80(const double* lo, const double* di, const double* up, const d
   return thomas_ext<long double>(lo, di, up, b, n, out);
 }
 
+// ---- "what the reference means to compute": its static diffusion system (time_independent.rs:91-182) evaluated in EXACT
+// arithmetic (__float128: 113 bits, ~1e-34) on the reference's own f64 inputs — mesh coordinates, the rule's f64 nodes
+// x_j = cos(theta_j) and weights w_j, j = 1..G-1 (:130-136), mu, b, the boundary values — and solved in __float128 without ever
+// rounding a band entry to f64.  On a long bar the f64 rounding noise of the band entries, whoever assembles them, is the
+// leading error of the solution; this is the yardstick that tells how far the reference's own f64 result and a
+// differently rounded assembly each are from the system they both approximate.
+// In exact arithmetic the three quadrature sums of interior row i (a = x_{i-1}, c = x_i, e = x_{i+1}; h1 = c-a, h2 = e-c, H = e-a)
+// only depend on the rule through its moments (the integrands are first-degree polynomials of x_j on each piece):
+//   prev = -mu T0 / (2 h1) - b (T0 + T1) / 4,    next = -mu T0 / (2 h2) + b (T0 - T1) / 4,
+//   diag = (H/2) [ mu (WL/h1^2 + WR/h2^2) + b (H/2) ((WL + XL)/h1^2 - (WR - XR)/h2^2) ],
+// T0 = sum w_j, T1 = sum w_j x_j; WL, XL (WR, XR) the same sums over the nodes whose image (a+e)/2 + (H/2) x_j lies left of c
+// (not left of c): the piece phi_i is evaluated on (piecewise_polynomials_1degree.rs:133-148, strict <).
+// brute != 0 evaluates the sums node by node instead (the reference's loop, every operation in __float128): the check of the
+// closed form (tests/test_oracle.py).
+}  // extern "C"
+typedef __float128 q128;
+static void intended_row(const double* mesh, size_t i, const std::vector<double>& xs, const std::vector<double>& ws,
+                         const std::vector<q128>& pw, const std::vector<q128>& px, q128 mu, q128 b, int brute, q128* lo, q128* di,
+                         q128* up) {
+  const q128 a = mesh[i - 1], c = mesh[i], e = mesh[i + 1];
+  const q128 h1 = c - a, h2 = e - c, H = e - a;
+  const size_t m = xs.size();
+  if (brute) {
+    q128 sp = 0, sn = 0, sd = 0;
+    for (size_t j = 0; j < m; ++j) {
+      const q128 x = xs[j], w = ws[j];
+      const q128 tp = (a + c) / 2 + (h1 / 2) * x, tn = (c + e) / 2 + (h2 / 2) * x, ts = (a + e) / 2 + (H / 2) * x;
+      // phi_i = (t - a)/h1 on [a, c), (e - t)/h2 on [c, e); phi_{i-1} = (c - t)/h1 on [a, c); phi_{i+1} = (t - c)/h2 on [c, e)
+      sp += (mu * (1 / h1) * (-1 / h1) + b * (-1 / h1) * ((tp - a) / h1)) * (h1 / 2) * w;
+      sn += (mu * (-1 / h2) * (1 / h2) + b * (1 / h2) * ((e - tn) / h2)) * (h2 / 2) * w;
+      if (ts < c) sd += (mu * (1 / h1) * (1 / h1) + b * (1 / h1) * ((ts - a) / h1)) * (H / 2) * w;
+      else sd += (mu * (-1 / h2) * (-1 / h2) + b * (-1 / h2) * ((e - ts) / h2)) * (H / 2) * w;
+    }
+    *lo = sp, *up = sn, *di = sd;
+    return;
+  }
+  const q128 T0 = pw[m], T1 = px[m];
+  // nodes decrease with j: the images left of the kink are j = s .. m-1, s = first j with (a+e)/2 + (H/2) x_j < c
+  size_t l = 0, r = m;
+  while (l < r) {
+    const size_t mid = (l + r) / 2;
+    if ((a + e) / 2 + (H / 2) * (q128)xs[mid] < c) r = mid;
+    else l = mid + 1;
+  }
+  const q128 WR = pw[l], XR = px[l], WL = T0 - WR, XL = T1 - XR;
+  *lo = -mu * T0 / (2 * h1) - b * (T0 + T1) / 4;
+  *up = -mu * T0 / (2 * h2) + b * (T0 - T1) / 4;
+  *di = (H / 2) * (mu * (WL / (h1 * h1) + WR / (h2 * h2)) + b * (H / 2) * ((WL + XL) / (h1 * h1) - (WR - XR) / (h2 * h2)));
+}
+extern "C" {
+// u (rounded to f64 at the very end) of the exact-arithmetic system; lo/di/up (optional, may be null): its bands rounded to f64
+int dzo_ti_intended_f128(const double* mesh, size_t n, double mu, double b, double bc0, double bc1, size_t G, int brute, int threads,
+                         double* u, double* lo, double* di, double* up) {
+  if (n < 3) return WRONG_DIMS;
+  std::vector<double> xs, ws;
+  int rc = quad_table(G, &xs, &ws);
+  if (rc) return rc;
+  const size_t m = xs.size();
+  for (size_t j = 1; j < m; ++j)
+    if (!(xs[j] < xs[j - 1])) return INTEGRATION;  // the bisection wants decreasing nodes
+  std::vector<q128> pw(m + 1), px(m + 1);  // prefix sums over j < s
+  pw[0] = 0, px[0] = 0;
+  for (size_t j = 0; j < m; ++j) pw[j + 1] = pw[j] + (q128)ws[j], px[j + 1] = px[j] + (q128)ws[j] * (q128)xs[j];
+  std::vector<q128> L(n), D(n), U(n), F(n);
+  L[0] = 0, D[0] = 1, U[0] = 0, F[0] = bc0;                  // :168-182: Dirichlet rows
+  L[n - 1] = 0, D[n - 1] = 1, U[n - 1] = 0, F[n - 1] = bc1;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+  for (long long i = 1; i < (long long)n - 1; ++i) {
+    intended_row(mesh, (size_t)i, xs, ws, pw, px, (q128)mu, (q128)b, brute, &L[i], &D[i], &U[i]);
+    F[i] = 0;
+  }
+  if (lo)
+    for (size_t i = 0; i < n; ++i) lo[i] = (double)L[i], di[i] = (double)D[i], up[i] = (double)U[i];
+  // solve_by_thomas's recurrences (matrix_solver/mod.rs:17-48), in place
+  U[0] = U[0] / D[0], F[0] = F[0] / D[0];
+  for (size_t i = 1; i < n - 1; ++i) {
+    const q128 den = D[i] - L[i] * U[i - 1];
+    U[i] = U[i] / den;
+    F[i] = (F[i] - L[i] * F[i - 1]) / den;
+  }
+  F[n - 1] = (F[n - 1] - L[n - 1] * F[n - 2]) / (D[n - 1] - L[n - 1] * U[n - 2]);
+  q128 s = F[n - 1];
+  u[n - 1] = (double)s;
+  for (size_t i = n - 1; i-- > 0;) {
+    s = F[i] - U[i] * s;
+    u[i] = (double)s;
+  }
+  return OK;
+}
+
 // ---- 2D ingestion ("next" row f3): mesh/mesh_builder.rs:342-500 (build_mesh_2d), :89-129 (obj_face_checker),
 // :623-680 (merge_sort).  Boundary vertices = vertices of the edges that belong to exactly one triangle.
 struct Mesh2D {

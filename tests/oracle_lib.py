@@ -128,6 +128,20 @@ def thomas(lo, di, up, rhs, kind="f64"):
     return out
 
 
+def ti_intended_f128(mesh, mu, b, bc, G, brute=False, threads=1, bands=False):
+    """Static diffusion system of the reference evaluated and solved in exact (__float128) arithmetic on its f64 inputs:
+    -> u (f64), or (u, lo, di, up) with the exact bands rounded to f64.  brute: node-by-node sums instead of the moments."""
+    mesh = _arr(mesh)
+    n = len(mesh)
+    u = np.zeros(n)
+    lo, di, up = (np.zeros(n) for _ in range(3)) if bands else (None, None, None)
+    null = C.cast(None, _dp)
+    _chk(lib().dzo_ti_intended_f128(_p(mesh), C.c_size_t(n), C.c_double(mu), C.c_double(b), C.c_double(bc[0]), C.c_double(bc[1]),
+                                    C.c_size_t(G), int(bool(brute)), int(threads), _p(u), _p(lo) if bands else null,
+                                    _p(di) if bands else null, _p(up) if bands else null))
+    return (u, lo, di, up) if bands else u
+
+
 def thomas_dense(a, b):
     a = _arr(a)
     b = _arr(b)

@@ -252,6 +252,36 @@ def test_extended_precision_thomas_close(golden):
         assert np.linalg.norm(u - t) / np.linalg.norm(t) < 1e-13
 
 
+def test_exact_arithmetic_system_closed_form_equals_node_loop():
+    """dzo_ti_intended_f128 (the reference's static system, time_independent.rs:91-182, in __float128 on its f64 inputs): the
+    moment form the long-bar yardstick uses is the node-by-node loop, and the f64 oracle's bands are its bands up to f64
+    rounding of a 149- / 349-term sum."""
+    rng = np.random.default_rng(3)
+    for n, G in [(50, 150), (200, 150), (37, 350), (30, 20)]:
+        x = np.sort(rng.uniform(0.0, 3.0, n))
+        ub, lb, db, pb = o.ti_intended_f128(x, 1.3, 0.7, (1.0, 15.0), G, brute=True, bands=True)
+        uc, lc, dc, pc = o.ti_intended_f128(x, 1.3, 0.7, (1.0, 15.0), G, brute=False, bands=True, threads=2)
+        assert np.array_equal(ub, uc) and np.array_equal(lb, lc) and np.array_equal(db, dc) and np.array_equal(pb, pc)
+        lo, di, up, rhs = o.ti_assemble(x, 1.3, 0.7, (1.0, 15.0), G)
+        for got, want in ((lo, lc), (di, dc), (up, pc)):
+            assert np.max(np.abs(got[1:-1] - want[1:-1]) / np.abs(want[1:-1])) < 5e-15
+        assert dc[0] == 1.0 and dc[-1] == 1.0 and lc[0] == 0.0 and pc[-1] == 0.0
+        u64 = o.thomas(lo, di, up, rhs)
+        assert np.linalg.norm(u64 - uc) / np.linalg.norm(uc) < 1e-11  # short bars: the reference is at its intended system
+
+
+def test_reference_f64_result_is_noise_limited_on_a_long_bar():
+    """On BASELINE config 4's regular bar the reference's own f64 result is far from the system it means to solve — and solving
+    its f64 bands exactly does not help: the distance is the rounding noise of the band entries."""
+    n = 200_000
+    x = np.linspace(0.0, 1.0, n)
+    truth = o.ti_intended_f128(x, 1.0, 1.0, (1.0, 15.0), 150, threads=o.hardware_threads())
+    lo, di, up, rhs = o.ti_assemble(x, 1.0, 1.0, (1.0, 15.0), 150, threads=o.hardware_threads())
+    e64 = np.linalg.norm(o.thomas(lo, di, up, rhs) - truth) / np.linalg.norm(truth)
+    e128 = np.linalg.norm(o.thomas(lo, di, up, rhs, kind="f128") - truth) / np.linalg.norm(truth)
+    assert 1e-8 < e64 < 1e-3 and abs(e64 - e128) < 0.05 * e64
+
+
 # ---------------------------------------------------------------- ingestion (mesh_builder.rs:204-328, mesh/mod.rs:54-68)
 def test_ingest_1dbar(golden, assets_dir):
     m = o.mesh_ingest_1d(assets_dir + "/1dbar.obj")
