@@ -7,7 +7,7 @@ For the regular bar of BASELINE config 4 (mu = b = 1, bc (1, 15), G = 150) at se
   auto   = the library's default mode (bands bit-identical to the reference's, partitioned solve),
   fast   = closed-form rows (one launch at these sizes).
 Prints one JSON object per size with the relative L2 distances.  Needs a GPU; tuning / documentation aid.
-Usage: python tools/c4_intended_check.py [n ...]"""
+Usage: python tools/c4_intended_check.py [--jitter] [n ...]"""
 import json
 import os
 import sys
@@ -28,10 +28,15 @@ def rel(a, b):
 
 
 def main():
-    sizes = [int(float(a)) for a in sys.argv[1:]] or [100_000, 1_000_000, 10_000_000]
+    argv = [a for a in sys.argv[1:] if a != "--jitter"]
+    jitter = "--jitter" in sys.argv[1:]   # element lengths within 0.4 % of each other (tests/test_gpu_onelaunch.py::jittered) instead of equal
+    sizes = [int(float(a)) for a in argv] or [100_000, 1_000_000, 10_000_000]
     threads = max(1, len(os.sched_getaffinity(0)))
     for n in sizes:
-        x = np.linspace(0.0, 1.0, n)
+        if jitter:
+            x = np.concatenate([[0.0], np.cumsum(np.random.default_rng(5).uniform(0.996, 1.004, n - 1))]) / n
+        else:
+            x = np.linspace(0.0, 1.0, n)
         t0 = time.time()
         truth = o.ti_intended_f128(x, 1.0, 1.0, (1.0, 15.0), 150, threads=threads)
         t_truth = time.time() - t0
@@ -40,7 +45,7 @@ def main():
         ref_exact_solve = o.thomas(lo, di, up, rhs, kind="f128")
         mesh = dz.Mesh.from_nodes(x)
         p = params.DiffussionParams.time_independent().mu(1.0).b(1.0).boundary_conditions(1.0, 15.0).build()
-        out = {"n": n, "truth_seconds": round(t_truth, 2),
+        out = {"n": n, "mesh": "jittered 0.4 %" if jitter else "regular", "truth_seconds": round(t_truth, 2),
                "relL2_reference_f64_vs_truth": rel(ref, truth),
                "relL2_reference_bands_solved_in_f128_vs_truth": rel(ref_exact_solve, truth)}
         for name, mode in (("auto", solvers.ASSEMBLY_AUTO), ("fast", solvers.ASSEMBLY_FAST)):
