@@ -571,6 +571,28 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   }
   sm.cta.backsolve(t, mS);  // starts and ends with a CTA barrier: the work area is free again afterwards
   ol_stamp(a, 4);
+  const bool two_stages = depth >= 2;
+  auto request_rs = [&](long long tile, int b) {  // thread 0
+    // as in request_x; here the source, too, was written with ordinary stores (the forward pass, other threads, another CTA
+    // for the value left of the CTA's first tile): generic -> async ordering for both state spaces, from the issuing thread,
+    // after it has synchronised with the writers (the grid barrier and the CTA barriers since)
+    asm volatile("fence.proxy.async;" ::: "memory");
+    const bool hh = x_halo(tile);
+    unsigned long long* mb = b ? &sm.mbar2 : &sm.mbar;
+    mbar_arrive_expect_tx(mb, (unsigned)(2 * BS_TILE * sizeof(double)) + (hh ? 32u : 0u));
+    const int row = (int)(tile * BS_TMA_BOX);
+    tma_load_box(b ? sm.stage2(0) : sm.w.stage[0], &map_x, row, mb);
+    tma_load_box(b ? sm.stage2(1) : sm.w.stage[1], &map_s, row, mb);
+    if (hh) {
+      bulk_load(sm.halo + 4 * b, k.p0 + tile * BS_TILE - 2, 16, mb);
+      bulk_load(sm.halo + 4 * b + 2, k.p0 + (tile + 1) * BS_TILE, 16, mb);
+    }
+  };
+  // The first two tiles of the backward pass are asked for as soon as their stages are free — the work area now (the middle
+  // system is solved, and the proxy fence of the request covers its ordinary stores), the level-D system's space once its
+  // solutions have been handed down — so that they land while the global levels are swept backward (ncu: the wait for the
+  // first tile was 4 % of the kernel's stall samples when the requests followed those sweeps).
+  if (t == 0 && staged(tb1 - 1)) request_rs(tb1 - 1, 0);
   // ---- the global levels backward
   if (depth >= 2) {  // shared memory -> the last global level
     double* const(&src)[4] = depth == 3 ? a.gc : a.gb;
@@ -589,6 +611,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
         if (j < gm.len) udst[base + gm.g0 + j] = u[j];
     }
     __syncthreads();
+    if (t == 0 && T >= 2 && staged(tb1 - 2)) request_rs(tb1 - 2, 1);  // (two_stages: depth >= 2)
   }
   if (depth == 3) {
     level_backward(a.gb, oB, mB, a.uc, oC, a.ub, t, fc);
@@ -599,28 +622,6 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   // of the kernel's stall samples sat on the mbarrier here — 32 KB per tile against 16 KB forward, and less arithmetic to hide them
   // behind), so with depth >= 2 the tiles alternate between the work area and the dead level-D system: the request for the tile
   // after next goes out as soon as this tile's chunks are in registers
-  const bool two_stages = depth >= 2;
-  auto request_rs = [&](long long tile, int b) {  // thread 0
-    // as in request_x; here the source, too, was written with ordinary stores (the forward pass, other threads, another CTA
-    // for the value left of the CTA's first tile): generic -> async ordering for both state spaces, from the issuing thread,
-    // after it has synchronised with the writers (the grid barrier and the CTA barriers since)
-    asm volatile("fence.proxy.async;" ::: "memory");
-    const bool hh = x_halo(tile);
-    unsigned long long* mb = b ? &sm.mbar2 : &sm.mbar;
-    mbar_arrive_expect_tx(mb, (unsigned)(2 * BS_TILE * sizeof(double)) + (hh ? 32u : 0u));
-    const int row = (int)(tile * BS_TMA_BOX);
-    tma_load_box(b ? sm.stage2(0) : sm.w.stage[0], &map_x, row, mb);
-    tma_load_box(b ? sm.stage2(1) : sm.w.stage[1], &map_s, row, mb);
-    if (hh) {
-      bulk_load(sm.halo + 4 * b, k.p0 + tile * BS_TILE - 2, 16, mb);
-      bulk_load(sm.halo + 4 * b + 2, k.p0 + (tile + 1) * BS_TILE, 16, mb);
-    }
-  };
-  // (the first request's proxy fence also covers the ordinary stores of the middle solve into the work area and of level D)
-  if (t == 0) {
-    if (staged(tb1 - 1)) request_rs(tb1 - 1, 0);
-    if (two_stages && T >= 2 && staged(tb1 - 2)) request_rs(tb1 - 2, 1);
-  }
   unsigned phase2 = 0;
   const int ahead = two_stages ? 2 : 1;
   for (int kk = T - 1; kk >= 0; --kk) {

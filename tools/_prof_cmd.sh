@@ -1,4 +1,3 @@
-timeout 300 python tools/c4_intended_check.py --jitter 100000 1000000 10000000 > gpurun_out/r4f_intended_jitter.txt 2> gpurun_out/r4f_intended.err
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r4f_tests.txt
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r4f_smoke.txt 2>&1
-timeout 600 python bench.py > gpurun_out/r4f_bench.json 2> gpurun_out/r4f_bench.err
+timeout 400 python -m pytest tests/test_gpu_onelaunch.py tests/test_gpu_split_bar.py -x -q 2>&1 | tail -3 > gpurun_out/r4g_tests.txt
+timeout 200 python tools/time_long_solve.py 1000000 2500000 5000000 10000000 12000007 19000000 2>&1 | tail -1 > gpurun_out/r4g_sizes.json
+DZB_OL_TRACE=1 DZB_OL_TRACE_FILE=gpurun_out/r4g_ctas.txt timeout 100 python tools/time_long_solve.py 10000000 > /dev/null 2>&1
