@@ -419,16 +419,10 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   const int depth = mB <= 8 * P1C ? 1 : (mC <= 8 * P1C ? 2 : 3);
   const int mS = depth == 1 ? mB : (depth == 2 ? mC : mD);  // rows of the CTA's shared-memory system
   const TiK K = make_tik(a.rule, a.P);
-  for (int j = t; j <= a.rule.m; j += BS_THREADS) sm.uv[j] = a.rule.uv[j];
-  for (int j = t; j < a.rule.m; j += BS_THREADS) sm.qx[j] = a.rule.x[j];
-  for (int j = t; j < GUESS_BINS + 2; j += BS_THREADS) sm.guessf[j] = a.rule.guessf[j];
   const OlTables tb{sm.uv, sm.guessf, sm.qx, a.rule.m};
   const bool classify = a.class_flags != nullptr;
-  if (t == 0) mbar_init(&sm.mbar, 1), mbar_init(&sm.mbar2, 1);
-  __syncthreads();
   auto staged = [&](long long tile) { return use_tma && (tile + 1) * BS_TILE <= k.m; };  // (m % BS_TILE == 1 is refused by the launcher)
   unsigned phase = 0;
-  ol_stamp(a, 0);
 
   // ---- level A forward: assemble, leave (1/h, s) per row, two reduced rows per chunk -> level B
   // the two coordinates either side of a staged tile ride along as two 16-byte bulk copies when both pairs exist (every tile
@@ -448,7 +442,16 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       bulk_load(sm.halo + 2, k.p0 + (tile + 1) * BS_TILE, 16, &sm.mbar);
     }
   };
-  if (t == 0 && staged(tb0)) request_x(tb0);
+  // the first tile is on its way while the CTA copies the rule tables (the barrier after them also publishes the mbarriers)
+  if (t == 0) {
+    mbar_init(&sm.mbar, 1), mbar_init(&sm.mbar2, 1);
+    if (staged(tb0)) request_x(tb0);
+  }
+  for (int j = t; j <= a.rule.m; j += BS_THREADS) sm.uv[j] = a.rule.uv[j];
+  for (int j = t; j < a.rule.m; j += BS_THREADS) sm.qx[j] = a.rule.x[j];
+  for (int j = t; j < GUESS_BINS + 2; j += BS_THREADS) sm.guessf[j] = a.rule.guessf[j];
+  __syncthreads();
+  ol_stamp(a, 0);
   int cls = 0;
   bool bad = false;
   for (int kk = 0; kk < T; ++kk) {
@@ -606,9 +609,15 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nL));
       chunk_sweep<true>(A, C, S, F, gm.len, o);
       chunk0_backward(A, C, S, F, gm.len, us, ue, u);
+      double* dst = udst + base + gm.g0;
+      if (gm.len == BS_R && !((base + gm.g0) & 1)) {
 #pragma unroll
-      for (int j = 0; j < BS_R; ++j)
-        if (j < gm.len) udst[base + gm.g0 + j] = u[j];
+        for (int j = 0; j < BS_R / 2; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(u[2 * j], u[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BS_R; ++j)
+          if (j < gm.len) dst[j] = u[j];
+      }
     }
     __syncthreads();
     if (t == 0 && T >= 2 && staged(tb1 - 2)) request_rs(tb1 - 2, 1);  // (two_stages: depth >= 2)
