@@ -313,8 +313,8 @@ __device__ __forceinline__ void rows_load(double* const (&g)[4], long long r0, i
     const double2* q3 = reinterpret_cast<const double2*>(g[3] + r0);
 #pragma unroll
     for (int j = 0; j < BS_R / 2; ++j) {
-      const double2 v0 = __ldcg(q0 + j), v1 = __ldcg(q1 + j), v2 = __ldcg(q2 + j);
-      const double2 v3 = with_f ? __ldcg(q3 + j) : make_double2(0.0, 0.0);
+      const double2 v0 = __ldca(q0 + j), v1 = __ldca(q1 + j), v2 = __ldca(q2 + j);
+      const double2 v3 = with_f ? __ldca(q3 + j) : make_double2(0.0, 0.0);
       A[2 * j] = v0.x, A[2 * j + 1] = v0.y, C[2 * j] = v1.x, C[2 * j + 1] = v1.y;
       S[2 * j] = v2.x, S[2 * j + 1] = v2.y, F[2 * j] = v3.x, F[2 * j + 1] = v3.y;
     }
@@ -322,10 +322,18 @@ __device__ __forceinline__ void rows_load(double* const (&g)[4], long long r0, i
 #pragma unroll
     for (int j = 0; j < BS_R; ++j) {
       const bool in = j < len;
-      A[j] = in ? __ldcg(g[0] + r0 + j) : 0.0, C[j] = in ? __ldcg(g[1] + r0 + j) : 0.0;
-      S[j] = in ? __ldcg(g[2] + r0 + j) : 1.0, F[j] = (in && with_f) ? __ldcg(g[3] + r0 + j) : 0.0;
+      A[j] = in ? __ldca(g[0] + r0 + j) : 0.0, C[j] = in ? __ldca(g[1] + r0 + j) : 0.0;
+      S[j] = in ? __ldca(g[2] + r0 + j) : 1.0, F[j] = (in && with_f) ? __ldca(g[3] + r0 + j) : 0.0;
     }
   }
+}
+// The levels B and C are private to the CTA (written and read by its own threads, never by another SM), so their loads may go
+// through the L1 — and a thread can ask for the lines of its NEXT chunk before it sweeps this one: the sweeps of these levels
+// were waits for the L2 (ncu: long_sb + lg on their first use of a loaded row, ~9 % of the kernel's stall samples).
+__device__ __forceinline__ void rows_prefetch(double* const (&g)[4], long long r0, bool with_f) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(g[k] + r0));
+  if (with_f) asm volatile("prefetch.global.L1 [%0];" ::"l"(g[3] + r0));
 }
 // the two reduced rows of a chunk -> rows q, q + 1 (q even) of the arrays g[0..3]
 __device__ __forceinline__ void rows_store2(double* const (&g)[4], long long q, const double (&o)[8], bool with_f) {
@@ -355,6 +363,7 @@ __device__ __forceinline__ void level_forward(double* const (&src)[4], long long
   for (int c = t; c < nc; c += BS_THREADS) {
     const ChunkGeom gm = chunk_geom(m, c, 0);
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
+    if (c + BS_THREADS < nc) rows_prefetch(src, base + chunk_geom(m, c + BS_THREADS, 0).g0, fc(c + BS_THREADS, nc));
     rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nc));
     chunk_sweep<false>(A, C, S, F, gm.len, o);
     rows_store2(dst, dbase + 2 * c, o, fc(c, nc));  // (its image is chunk c / 4 of the next level: first / last again)
@@ -368,6 +377,7 @@ __device__ __forceinline__ void level_backward(double* const (&src)[4], long lon
     const ChunkGeom gm = chunk_geom(m, c, 0);
     const double2 ends = __ldcg(reinterpret_cast<const double2*>(usrc + ubase + 2 * c));
     double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
+    if (c + BS_THREADS < nc) rows_prefetch(src, base + chunk_geom(m, c + BS_THREADS, 0).g0, fc(c + BS_THREADS, nc));
     rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nc));
     chunk_sweep<true>(A, C, S, F, gm.len, o);
     chunk0_backward(A, C, S, F, gm.len, ends.x, ends.y, u);
@@ -518,6 +528,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
     for (int c = t; c < nL; c += BS_THREADS) {
       const ChunkGeom gm = chunk_geom(mL, c, 0);
       double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8];
+      if (c + BS_THREADS < nL) rows_prefetch(src, base + chunk_geom(mL, c + BS_THREADS, 0).g0, fc(c + BS_THREADS, nL));
       rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nL));
       chunk_sweep<false>(A, C, S, F, gm.len, o);
       const int p0 = sm.cta.at(2 * c), p1 = sm.cta.at(2 * c + 1);
@@ -606,6 +617,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       const ChunkGeom gm = chunk_geom(mL, c, 0);
       const double us = sm.cta.d[sm.cta.at(2 * c)], ue = sm.cta.d[sm.cta.at(2 * c + 1)];
       double A[BS_R], C[BS_R], S[BS_R], F[BS_R], o[8], u[BS_R];
+      if (c + BS_THREADS < nL) rows_prefetch(src, base + chunk_geom(mL, c + BS_THREADS, 0).g0, fc(c + BS_THREADS, nL));
       rows_load(src, base + gm.g0, gm.len, A, C, S, F, fc(c, nL));
       chunk_sweep<true>(A, C, S, F, gm.len, o);
       chunk0_backward(A, C, S, F, gm.len, us, ue, u);
