@@ -207,3 +207,21 @@ def test_closed_form_bar_against_the_exact_arithmetic_system(gpu, oracle, n):
     print(f"n={n}: relL2 vs the exact-arithmetic system: reference f64 {e_ref:.3e}, closed form (one launch) {e_fast:.3e}, default {e_auto:.3e}")
     assert e_fast <= max(TOL_NODAL, e_ref)
     assert e_auto <= max(TOL_NODAL, 1.001 * e_ref)
+
+
+@pytest.mark.parametrize("n", [300_007, 1_000_000])
+def test_closed_form_jittered_bar_matches_the_reference_f64_directly(gpu, oracle, n):
+    """On a bar whose elements are not all equal the static system is well conditioned (row sums at the 1e-2 level, not 0), and
+    the closed-form one-launch path meets the plain tolerance against the reference's own f64 result — quadrature-loop assembly
+    (time_independent.rs:91-182) + solve_by_thomas (matrix_solver/mod.rs:17-48) — with no three-way rule: relL2 <= 1e-10."""
+    x = jittered(n, seed=5) * 1.0
+    lo, di, up, rhs = oracle.ti_assemble(x, 1.0, 1.0, (1.0, 15.0), 150, threads=oracle.hardware_threads())
+    ref = oracle.thomas(lo, di, up, rhs)
+    p = gpu.DiffussionParams.time_independent().mu(1.0).b(1.0).boundary_conditions(1.0, 15.0).build()
+    s = gpu.DiffussionSolverTimeIndependent(p, x, 150, fast_parallel(gpu))
+    u = s.solve(0.0)
+    assert ONE in s.path()
+    e = rel_l2(u, ref)
+    print(f"n={n}: relL2(closed form one launch, reference f64) = {e:.3e}")
+    assert e <= TOL_NODAL
+    assert u[0] == 1.0 and u[-1] == 15.0
