@@ -383,6 +383,11 @@ def measure_c4(cx, n, assembly, steps, warmup, parity_ref=None, e2e_steps=0):
                                                 "assemble_ms ~ 0, everything is in solve_ms)") if one_launch
                        else "x 8 + bands out 32 + bands in twice 64 + u 8 = 112",
                        "traffic": None, "peak_source": cx.peak_src, "frac_of_8TBs_spec": ach / 8000.0}
+    if one_launch:  # ncu's DRAM bytes of one launch at this size, while the kernel's sources are the ones it was captured from
+        traffic, lbl = measured_traffic("k_tri_onelaunch", str(n))
+        out["roofline"].update({"traffic": traffic, **lbl})
+        if traffic:
+            out["roofline"]["frac_on_measured_traffic"] = traffic / (ms * 1e-3) / 1e9 / cx.peak
     if assembly != "fast":
         # the reference-arithmetic assembly is fp64-pipe bound, not HBM bound: G-1 quadrature nodes x 27 separately rounded
         # operations per row (no FMA: the reference never contracts) against 64 fp64 lanes per SM per clock

@@ -1,5 +1,3 @@
-N=$1
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29577"
-timeout 200 python -m pytest tests/test_gpu_split_bar.py -x -q 2>&1 | tail -3 > gpurun_out/r4t_tests${N}.txt
-timeout 300 $T tools/split_bar_check.py --nodes 10000000 > gpurun_out/r4t_split${N}.txt 2>&1
-timeout 400 $T bench.py --gpus $N --steps 100 > gpurun_out/r4t_bench${N}.json 2> gpurun_out/r4t_bench${N}.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r5a_tests.txt
+ncu --set full --import-source on --clock-control none -k regex:k_tri_onelaunch -s 20 -c 3 -o gpurun_out/r5a_onelaunch -f python tools/time_long_solve.py 10000000 > gpurun_out/r5a_ncu.log 2>&1
+DZB_OL_TRACE=1 DZB_OL_TRACE_FILE=gpurun_out/r5a_ctas.txt timeout 100 python tools/time_long_solve.py 10000000 > /dev/null 2>&1
