@@ -54,6 +54,9 @@ struct OneLaunchArgs {
   unsigned long long* trace;  // tuning aid (DZB_OL_TRACE=1): [8 gridDim.x] %globaltimer at the phase boundaries of every CTA; nullptr normally
   int* class_flags;  // [0]: k_tri_classify's bits or'ed over every interior row (bit 0: not M-like, bit 1: not mass-like);
                      // [1]: != 0 when some row is outside the closed form.  nullptr: already known for these coordinates
+  const int* perm;   // [gridDim.x] position of CTA blockIdx.x in the bar (nullptr: blockIdx.x): the host lays the CTAs out so that
+                     // the two of an SM hold NEIGHBOURING tile ranges, one tile longer and one shorter (onelaunch_placement)
+  int* probe_smid;   // != nullptr: placement probe — every CTA reports the SM it runs on and returns
   PeerBox px;        // world > 1: the system is one block of a bar split across GPUs; its two interface rows go through the
                      // peer mailboxes (comm_kernels.cuh) between the passes and every rank solves the 2-rows-per-block system
 };
@@ -404,17 +407,30 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const TileArgs& k = a.k;
   const int t = threadIdx.x;
+  if (a.probe_smid) {
+    if (t == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      a.probe_smid[blockIdx.x] = (int)smid;
+    }
+    return;
+  }
+  const int vb = a.perm ? a.perm[blockIdx.x] : (int)blockIdx.x;  // the CTA's position along the bar
   const long long ntiles = (k.m + BS_TILE - 1) / BS_TILE;
   // Contiguous tile ranges, an even share each.  (The two CTAs of an SM do not finish pass 1 together: the one placed first wins
   // the issue slots and is done after ~75 us at 10^7 rows, its neighbour after ~95 us.  Giving the first arrival — found with a
   // per-%smid arrival counter, blockIdx does not tell — a larger share evened the two out and changed nothing: the SM takes as
-  // long for its 33 tiles either way, so the split stays even.)  A ragged last tile takes the direct-load path, which costs about two staged
+  // long for its 33 tiles either way, so the split stays even.)  What does matter is how many tiles an SM gets IN TOTAL: the
+  // block scheduler of a B200 puts CTAs b and b + 142 (b + 6 on six SMs) on one SM — the same in every launch on every box
+  // looked at — and with 16.5 tiles per CTA laid out by blockIdx both of them got 16 or both 17: half the SMs had 34 tiles, half
+  // 32, and everybody waited for the 34s, at the grid barrier and at the end.  The host therefore probes the placement once
+  // (probe_smid) and hands each CTA a position `vb` such that the two CTAs of an SM are neighbours along the bar: 33 tiles per SM.  A ragged last tile takes the direct-load path, which costs about two staged
   // tiles, and everybody would wait for its CTA at the grid barrier: it counts twice in the split
   long long tb0, tb1;
   {
     const long long units = ntiles + ((use_tma && (k.m % BS_TILE)) ? 1 : 0);
-    tb0 = min(ntiles, (long long)blockIdx.x * units / gridDim.x);
-    tb1 = blockIdx.x + 1 == gridDim.x ? ntiles : min(ntiles, ((long long)blockIdx.x + 1) * units / gridDim.x);
+    tb0 = min(ntiles, (long long)vb * units / gridDim.x);
+    tb1 = vb + 1 == (int)gridDim.x ? ntiles : min(ntiles, ((long long)vb + 1) * units / gridDim.x);
   }
   const int T = (int)(tb1 - tb0);  // >= 1: the launcher never starts more CTAs than tiles
   const FChunks fc{tb0 == 0 && !(k.flags & BS_OPEN_LEFT), tb1 == ntiles && !(k.flags & BS_OPEN_RIGHT)};
@@ -539,7 +555,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
   ol_stamp(a, 7);
   sm.cta.reduce(t, mS);
   if (t < 2) {  // the CTA's two interface rows: its first and its last
-    const long long o = 2LL * blockIdx.x + t;
+    const long long o = 2LL * vb + t;
     const int r = sm.cta.at(t ? mS - 1 : 0);
     k.red_a[o] = sm.cta.a[r], k.red_c[o] = sm.cta.c[r], k.red_s[o] = sm.cta.s[r], k.red_f[o] = sm.cta.d[r];
   }
@@ -581,7 +597,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) k_tri_onelaunch(const __grid
       mid.d[last] = ((s0 - c0) * f1 - a1 * f0) / det;
     }
     mid.backsolve(t, m2);
-    if (t < 2) sm.cta.d[sm.cta.at(t ? mS - 1 : 0)] = mid.d[mid.at(2 * (int)blockIdx.x + t)];
+    if (t < 2) sm.cta.d[sm.cta.at(t ? mS - 1 : 0)] = mid.d[mid.at(2 * vb + t)];
   }
   sm.cta.backsolve(t, mS);  // starts and ends with a CTA barrier: the work area is free again afterwards
   ol_stamp(a, 4);
@@ -730,9 +746,73 @@ inline int onelaunch_capacity() {
   return std::min(per_sm * sms, 8 * OL_P1M / 2);  // the middle system holds 2 rows per CTA in 8 OL_P1M rows
 }
 
+inline bool onelaunch_no_placement() {  // lay the CTAs out by blockIdx: the default until DZB_OL_PLACEMENT=1 asks for the probe
+  static const bool off = std::getenv("DZB_OL_PLACEMENT") == nullptr;
+  return off;
+}
 // rows of scratch the levels B and C need for an m-row system (per array)
 inline size_t onelaunch_rows_b(size_t m) { return ((m + BS_TILE - 1) / BS_TILE) * (size_t)OL_ROWS_B; }
 inline size_t onelaunch_rows_c(size_t m) { return ((m + BS_TILE - 1) / BS_TILE) * (size_t)OL_ROWS_C; }
+
+// Where the block scheduler puts the CTAs of a full grid (per device and instantiation, asked once): perm[b] = position along the
+// bar of CTA b such that the CTAs sharing an SM are neighbours (2 k, 2 k + 1, ...).  Identity (nullptr) unless every SM holds
+// the same number of CTAs; a placement that differs from the probed one costs balance, never correctness — perm is a
+// permutation whatever the hardware does.
+struct OlPlacement {
+  bool tried = false;
+  int grid = 0;
+  int* d_perm = nullptr;
+};
+template <int P1C, int MINB>
+inline OlPlacement& onelaunch_placement() {
+  static OlPlacement p[BS_MAX_DEVICES];
+  return p[bigsys_device()];
+}
+template <int P1C, int MINB>
+inline void onelaunch_probe(OlPlacement& pl, OneLaunchArgs& args, int grid, void** params, cudaStream_t st) {
+  pl.tried = true;
+  int* d_smid = nullptr;
+  if (cudaMalloc((void**)&d_smid, grid * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  std::vector<int> smid(grid, -1), perm(grid, -1);
+  const OneLaunchArgs saved = args;
+  args.probe_smid = d_smid;
+  bool ok = cudaLaunchCooperativeKernel((const void*)k_tri_onelaunch<P1C, MINB>, dim3((unsigned)grid), dim3(BS_THREADS), params,
+                                        sizeof(OneLaunchSmem<P1C>), st) == cudaSuccess &&
+            cudaMemcpyAsync(smid.data(), d_smid, grid * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+            cudaStreamSynchronize(st) == cudaSuccess;
+  args = saved;
+  cudaFree(d_smid);
+  if (!ok) {
+    cudaGetLastError();
+    return;
+  }
+  // SMs in the order of their first CTA; every SM must hold the same number of CTAs
+  std::vector<int> order;
+  std::vector<std::vector<int>> on_sm;
+  for (int b = 0; b < grid; ++b) {
+    if (smid[b] < 0) return;
+    if ((size_t)smid[b] >= on_sm.size()) on_sm.resize(smid[b] + 1);
+    if (on_sm[smid[b]].empty()) order.push_back(smid[b]);
+    on_sm[smid[b]].push_back(b);
+  }
+  const size_t per = on_sm[order[0]].size();
+  if (per < 2 || per * order.size() != (size_t)grid) return;
+  int v = 0;
+  for (int sm : order) {
+    if (on_sm[sm].size() != per) return;
+    for (int b : on_sm[sm]) perm[b] = v++;
+  }
+  if (cudaMalloc((void**)&pl.d_perm, grid * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(pl.d_perm, perm.data(), grid * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    pl.d_perm = nullptr;
+    return;
+  }
+  pl.grid = grid;
+}
 
 template <int P1C, int MINB>
 inline int onelaunch_try(OneLaunchArgs& args, size_t tiles, int& cap, void** params, cudaStream_t st, unsigned long long* launches,
@@ -742,6 +822,12 @@ inline int onelaunch_try(OneLaunchArgs& args, size_t tiles, int& cap, void** par
   *grid_out = (int)grid;
   // level D holds 32 rows per tile (tiles + 1: a ragged last tile counts twice in the kernel's split of the tiles over the CTAs)
   if (grid == 0 || (tiles + 1 + grid - 1) / grid > (size_t)(8 * P1C / OL_ROWS_D)) return -1;
+  args.perm = nullptr, args.probe_smid = nullptr;
+  if (MINB >= 2 && (int)grid == cap && !onelaunch_no_placement()) {  // a full grid: more than one CTA per SM
+    OlPlacement& pl = onelaunch_placement<P1C, MINB>();
+    if (!pl.tried) onelaunch_probe<P1C, MINB>(pl, args, (int)grid, params, st);
+    if (pl.grid == (int)grid) args.perm = pl.d_perm;
+  }
   ++*launches;
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tri_onelaunch<P1C, MINB>, dim3((unsigned)grid), dim3(BS_THREADS), params,
                                               sizeof(OneLaunchSmem<P1C>), st);

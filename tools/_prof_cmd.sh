@@ -1,4 +1,4 @@
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r5b_smoke.txt 2>&1
-timeout 600 python bench.py > gpurun_out/r5b_bench.json 2> gpurun_out/r5b_bench.err
-timeout 300 python bench.py --impl reference --steps 40 --warmup 3 > gpurun_out/r5b_ref.json 2> gpurun_out/r5b_ref.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r5b_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/r5b_ncu_bench.log 2>&1
+DZB_OL_PLACEMENT=1 timeout 400 python -m pytest tests/test_gpu_onelaunch.py tests/test_gpu_split_bar.py -x -q 2>&1 | tail -3 > gpurun_out/r5c_tests.txt
+DZB_OL_PLACEMENT=1 timeout 200 python tools/time_long_solve.py 1000000 2500000 5000000 10000000 12000007 19000000 2>&1 | tail -1 > gpurun_out/r5c_sizes.json
+timeout 200 python tools/time_long_solve.py 5000000 10000000 19000000 2>&1 | tail -1 > gpurun_out/r5c_sizes_noplace.json
+DZB_OL_PLACEMENT=1 DZB_OL_TRACE=1 DZB_OL_TRACE_FILE=gpurun_out/r5c_ctas.txt timeout 100 python tools/time_long_solve.py 10000000 > /dev/null 2>&1
