@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdzahui_b200.so")
 SOURCES = ["dzb_api.cu", "gl_quadrature.cpp", "mesh_ingest.cpp", "csv_writer.cpp"]
-HEADERS = ["assembly_kernels.cuh", "tridiag_kernels.cuh", "bigsys_kernels.cuh", "onelaunch_kernels.cuh", "comm_kernels.cuh", "dzb_comm.inl", "euler_kernels.cuh", "mesh2d_kernels.cuh", "gl_quadrature.h", "mesh_ingest.h",
+HEADERS = ["assembly_kernels.cuh", "tridiag_kernels.cuh", "bigsys_kernels.cuh", "onelaunch_kernels.cuh", "ol_layout.h", "comm_kernels.cuh", "dzb_comm.inl", "euler_kernels.cuh", "mesh2d_kernels.cuh", "gl_quadrature.h", "mesh_ingest.h",
            "gl_tables_generated.h", os.path.join("..", "..", "include", "dzahui_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-Xptxas", "-v"]

@@ -34,6 +34,7 @@
 #pragma once
 #include "assembly_kernels.cuh"
 #include "bigsys_kernels.cuh"
+#include "ol_layout.h"
 
 namespace dzb {
 
@@ -792,25 +793,7 @@ inline void onelaunch_probe(OlPlacement& pl, OneLaunchArgs& args, int grid, void
     cudaGetLastError();
     return;
   }
-  // SMs in the order of their first CTA; every SM must hold the same number of CTAs
-  std::vector<int> order;
-  std::vector<std::vector<int>> on_sm;
-  for (int b = 0; b < grid; ++b) {
-    if (smid[b] < 0) return;
-    if ((size_t)smid[b] >= on_sm.size()) on_sm.resize(smid[b] + 1);
-    if (on_sm[smid[b]].empty()) order.push_back(smid[b]);
-    on_sm[smid[b]].push_back(b);
-  }
-  const size_t per = on_sm[order[0]].size();
-  if (per < 2 || per * order.size() != (size_t)grid) return;
-  int v = 0;
-  for (int sm : order) {
-    if (on_sm[sm].size() != per) return;
-    // the CTA placed first gets the LAST of the SM's positions: with 16.5 tiles per CTA the odd positions hold 17 tiles, and the
-    // first CTA of an SM is the faster one (it wins the issue slots: it was 6.6 us ahead of its neighbour on equal shares)
-    for (size_t q = 0; q < per; ++q) perm[on_sm[sm][q]] = v + (int)(per - 1 - q);
-    v += (int)per;
-  }
+  if (!onelaunch_layout(smid.data(), grid, perm.data())) return;  // (ol_layout.h)
   if (cudaMalloc((void**)&pl.d_perm, grid * sizeof(int)) != cudaSuccess ||
       cudaMemcpy(pl.d_perm, perm.data(), grid * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
