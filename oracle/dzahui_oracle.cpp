@@ -1001,7 +1001,68 @@ static void intended_row(const double* mesh, size_t i, const std::vector<double>
   *up = -mu * T0 / (2 * h2) + b * (T0 - T1) / 4;
   *di = (H / 2) * (mu * (WL / (h1 * h1) + WR / (h2 * h2)) + b * (H / 2) * ((WL + XL) / (h1 * h1) - (WR - XR) / (h2 * h2)));
 }
+// The mass matrix of the time-dependent solver (time_dependent.rs:180-190) the same way: second moments as well.
+//   prev = (h1/8)(T0 - T2),  next = (h2/8)(T0 - T2),  diag = (H^3/8) [ (WL + 2 XL + QL)/h1^2 + (WR - 2 XR + QR)/h2^2 ],
+// T2 = sum w_j x_j^2, QL / QR its parts left / right of the kink.  (S of that solver is minus the static system's rows, :226-233.)
+static void intended_mass_row(const double* mesh, size_t i, const std::vector<double>& xs, const std::vector<double>& ws,
+                              const std::vector<q128>& pw, const std::vector<q128>& px, const std::vector<q128>& pq, int brute,
+                              q128* lo, q128* di, q128* up) {
+  const q128 a = mesh[i - 1], c = mesh[i], e = mesh[i + 1];
+  const q128 h1 = c - a, h2 = e - c, H = e - a;
+  const size_t m = xs.size();
+  if (brute) {
+    q128 sp = 0, sn = 0, sd = 0;
+    for (size_t j = 0; j < m; ++j) {
+      const q128 x = xs[j], w = ws[j];
+      const q128 tp = (a + c) / 2 + (h1 / 2) * x, tn = (c + e) / 2 + (h2 / 2) * x, ts = (a + e) / 2 + (H / 2) * x;
+      sp += ((tp - a) / h1) * ((c - tp) / h1) * (h1 / 2) * w;
+      sn += ((e - tn) / h2) * ((tn - c) / h2) * (h2 / 2) * w;
+      const q128 v = ts < c ? (ts - a) / h1 : (e - ts) / h2;
+      sd += (v * v) * (H / 2) * w;
+    }
+    *lo = sp, *up = sn, *di = sd;
+    return;
+  }
+  const q128 T0 = pw[m], T1 = px[m], T2 = pq[m];
+  size_t l = 0, r = m;
+  while (l < r) {
+    const size_t mid = (l + r) / 2;
+    if ((a + e) / 2 + (H / 2) * (q128)xs[mid] < c) r = mid;
+    else l = mid + 1;
+  }
+  const q128 WR = pw[l], XR = px[l], QR = pq[l], WL = T0 - WR, XL = T1 - XR, QL = T2 - QR;
+  *lo = (h1 / 8) * (T0 - T2);
+  *up = (h2 / 8) * (T0 - T2);
+  *di = (H * H * H / 8) * ((WL + 2 * XL + QL) / (h1 * h1) + (WR - 2 * XR + QR) / (h2 * h2));
+}
 extern "C" {
+// M and S of the time-dependent solver in exact arithmetic, rounded to f64 at the very end (identity rows at both ends, :236-239)
+int dzo_td_intended_f128(const double* mesh, size_t n, double mu, double b, size_t G, int brute, int threads, double* mlo, double* mdi,
+                         double* mup, double* slo, double* sdi, double* sup) {
+  if (n < 3) return WRONG_DIMS;
+  std::vector<double> xs, ws;
+  int rc = quad_table(G, &xs, &ws);
+  if (rc) return rc;
+  const size_t m = xs.size();
+  for (size_t j = 1; j < m; ++j)
+    if (!(xs[j] < xs[j - 1])) return INTEGRATION;
+  std::vector<q128> pw(m + 1), px(m + 1), pq(m + 1);
+  pw[0] = 0, px[0] = 0, pq[0] = 0;
+  for (size_t j = 0; j < m; ++j) {
+    const q128 w = ws[j], x = xs[j];
+    pw[j + 1] = pw[j] + w, px[j + 1] = px[j] + w * x, pq[j + 1] = pq[j] + w * x * x;
+  }
+  for (size_t i = 0; i < n; ++i) mlo[i] = mup[i] = slo[i] = sup[i] = 0.0, mdi[i] = sdi[i] = 1.0;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+  for (long long i = 1; i < (long long)n - 1; ++i) {
+    q128 l, d, u;
+    intended_mass_row(mesh, (size_t)i, xs, ws, pw, px, pq, brute, &l, &d, &u);
+    mlo[i] = (double)l, mdi[i] = (double)d, mup[i] = (double)u;
+    intended_row(mesh, (size_t)i, xs, ws, pw, px, (q128)mu, (q128)b, brute, &l, &d, &u);
+    slo[i] = (double)(-l), sdi[i] = (double)(-d), sup[i] = (double)(-u);
+  }
+  return OK;
+}
 // u (rounded to f64 at the very end) of the exact-arithmetic system; lo/di/up (optional, may be null): its bands rounded to f64
 int dzo_ti_intended_f128(const double* mesh, size_t n, double mu, double b, double bc0, double bc1, size_t G, int brute, int threads,
                          double* u, double* lo, double* di, double* up) {

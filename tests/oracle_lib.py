@@ -142,6 +142,17 @@ def ti_intended_f128(mesh, mu, b, bc, G, brute=False, threads=1, bands=False):
     return (u, lo, di, up) if bands else u
 
 
+def td_intended_f128(mesh, mu, b, G, brute=False, threads=1):
+    """M and S of the time-dependent solver (time_dependent.rs:110-247) evaluated in exact (__float128) arithmetic on the
+    reference's f64 inputs, rounded to f64 at the end -> (mlo, mdi, mup, slo, sdi, sup)."""
+    mesh = _arr(mesh)
+    n = len(mesh)
+    a = [np.zeros(n) for _ in range(6)]
+    _chk(lib().dzo_td_intended_f128(_p(mesh), C.c_size_t(n), C.c_double(mu), C.c_double(b), C.c_size_t(G), int(bool(brute)),
+                                    int(threads), *[_p(x) for x in a]))
+    return tuple(a)
+
+
 def thomas_dense(a, b):
     a = _arr(a)
     b = _arr(b)
