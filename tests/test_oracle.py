@@ -270,6 +270,25 @@ def test_exact_arithmetic_system_closed_form_equals_node_loop():
         assert np.linalg.norm(u64 - uc) / np.linalg.norm(uc) < 1e-11  # short bars: the reference is at its intended system
 
 
+def test_exact_arithmetic_mass_and_stiffness_agree_with_the_oracle_loop():
+    """dzo_td_intended_f128: M and S of the time-dependent solver (time_dependent.rs:110-247) from the rule's moments in
+    __float128 — an independent derivation of what the line-by-line restatement sums node by node.  Moment form == node loop
+    (identical after rounding); the f64 oracle agrees to the rounding of a (G-1)-term sum, per row relative to the row's scale."""
+    rng = np.random.default_rng(4)
+    for n, G in [(60, 150), (33, 350), (25, 20), (40, 101)]:
+        x = np.sort(rng.uniform(-2.0, 3.0, n))
+        brute = o.td_intended_f128(x, 1.3, 0.7, G, brute=True)
+        exact = o.td_intended_f128(x, 1.3, 0.7, G, brute=False, threads=2)
+        assert all(np.array_equal(p, q) for p, q in zip(brute, exact))
+        got = o.td_assemble(x, 1.3, 0.7, G)
+        for k in (0, 3):  # M bands, S bands
+            scale = sum(np.abs(exact[k + j]) for j in range(3))
+            for j in range(3):
+                assert np.max(np.abs(got[k + j] - exact[k + j]) / scale) < 2e-14
+        for band, end in zip(exact, (0.0, 1.0, 0.0, 0.0, 1.0, 0.0)):
+            assert band[0] == end and band[-1] == end      # identity rows at both ends (:236-239)
+
+
 def test_reference_f64_result_is_noise_limited_on_a_long_bar():
     """On BASELINE config 4's regular bar the reference's own f64 result is far from the system it means to solve — and solving
     its f64 bands exactly does not help: the distance is the rounding noise of the band entries."""
