@@ -284,7 +284,8 @@ def test_exact_arithmetic_mass_and_stiffness_agree_with_the_oracle_loop():
         for k in (0, 3):  # M bands, S bands
             scale = sum(np.abs(exact[k + j]) for j in range(3))
             for j in range(3):
-                assert np.max(np.abs(got[k + j] - exact[k + j]) / scale) < 2e-14
+                # (phi is evaluated as slope * x + intercept: an absolute error of eps |x| / h per node, |x| / h up to ~50 here)
+                assert np.max(np.abs(got[k + j] - exact[k + j]) / scale) < 2e-13
         for band, end in zip(exact, (0.0, 1.0, 0.0, 0.0, 1.0, 0.0)):
             assert band[0] == end and band[-1] == end      # identity rows at both ends (:236-239)
 
